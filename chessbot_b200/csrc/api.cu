@@ -1,0 +1,465 @@
+// Device side of the C ABI (include/chessbot_b200.h): context, network weights and the batched
+// search driver.  Kernels live in encode.cu / conv.cu / heads.cu / mcts.cu.
+#include <math.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/chessbot_b200.h"
+#include "kernels.cuh"
+
+namespace cb {
+__global__ void read_roots_kernel(SearchParams sp, uint16_t* moves, int32_t* n, float* w, float* q, double* p, int32_t* n_children,
+                                  int32_t* root_n, int32_t* tree_nodes) {
+    const int tree = blockIdx.x;
+    if (tree >= sp.n_trees) return;
+    const TreeState& ts = sp.trees[tree];
+    const Node& r = sp.nodes[ts.root_node];
+    if (threadIdx.x == 0) { n_children[tree] = r.n_children; root_n[tree] = r.N; tree_nodes[tree] = ts.n_nodes; }
+    for (int i = threadIdx.x; i < r.n_children; i += blockDim.x) {
+        const Node& c = sp.nodes[r.first_child + i];
+        const size_t o = (size_t)tree * MAX_MOVES + i;
+        moves[o] = c.move; n[o] = c.N; w[o] = c.W; q[o] = c.Q;
+        p[o] = ts.noisy ? sp.root_p64[o] : (double)c.P;
+    }
+}
+__global__ void waiting_flags_kernel(const TreeState* trees, int n, uint8_t* flags) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flags[i] = trees[i].status == 1 || trees[i].status == 2;
+}
+__global__ void count_unfinished_kernel(const TreeState* trees, int n, int32_t* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && trees[i].status != 3 && trees[i].status != 0) atomicAdd(out, 1);
+}
+}  // namespace cb
+
+using namespace cb;
+
+namespace {
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    int alloc(size_t count, bool zero = true) {
+        free_();
+        n = count;
+        if (!count) return 0;
+        CB_CUDA_OK(cudaMalloc(&p, count * sizeof(T)));
+        if (zero) CB_CUDA_OK(cudaMemset(p, 0, count * sizeof(T)));
+        return 0;
+    }
+    void free_() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    ~DevBuf() { free_(); }
+};
+
+struct ConvLayer {
+    DevBuf<__nv_bfloat16> w;
+    DevBuf<float> scale, shift;
+    int kc = 0, cj_in = 0;
+};
+
+struct Net {
+    int filters = 0, cpad = 0, blocks = 0, max_batch = 0;
+    float slope = 0.3f, eps = 1e-3f;
+    std::map<std::string, std::vector<float>> host;  // staged Keras-layout tensors
+    std::vector<ConvLayer> layers;                   // stem + 2 per block
+    DevBuf<float> head_w, head_bn, fc1, fc2, wp, wpt;
+    DevBuf<__nv_bfloat16> act[3];
+    DevBuf<float> head_raw, pfeat;
+    bool ready = false;
+};
+
+struct Search {
+    int max_trees = 0, n_trees = 0, max_sims = 0, eval_mode = 0;
+    uint32_t seed = 0;
+    DevBuf<Node> nodes;
+    DevBuf<Pos> pos;
+    DevBuf<TreeState> trees;
+    DevBuf<int32_t> node_count, pos_count, frame_idx, counters, scratch_i32;
+    DevBuf<uint16_t> pend_moves;
+    DevBuf<double> root_p64, noise, cpuct_tab, sqrt_tab;
+    DevBuf<float> value, expvals;
+    DevBuf<uint32_t> synth_hash;
+    DevBuf<__nv_bfloat16> planes_act;
+    DevBuf<int16_t> planes_i16;
+    DevBuf<uint8_t> flags;
+    // read-back staging
+    DevBuf<uint16_t> r_moves; DevBuf<int32_t> r_n, r_nc, r_rootn, r_nodes; DevBuf<float> r_w, r_q; DevBuf<double> r_p;
+    SearchParams sp{};
+};
+}  // namespace
+
+struct cb_ctx {
+    int device = 0, sms = 0;
+    DevBuf<float> exp_table;
+    Net net;
+    Search search;
+};
+
+static int upload(void* dst, const void* src, size_t bytes) {
+    CB_CUDA_OK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" {
+
+cb_ctx* cb_ctx_create(int device) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cb_set_error("no CUDA device: chessbot_b200 has no CPU fallback");
+        return nullptr;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) { cb_set_error("cudaSetDevice failed"); return nullptr; }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    if (prop.major != 10) {
+        cb_set_error(std::string("chessbot_b200 needs an sm_100 GPU, found sm_") + std::to_string(prop.major * 10 + prop.minor));
+        return nullptr;
+    }
+    cb_ctx* ctx = new cb_ctx;
+    ctx->device = device;
+    ctx->sms = prop.multiProcessorCount;
+    std::vector<float> tab(65536);
+    for (uint32_t i = 0; i < 65536; ++i) {
+        uint32_t bits = i << 16;
+        float x;
+        memcpy(&x, &bits, 4);
+        tab[i] = (float)exp((double)x);
+    }
+    if (ctx->exp_table.alloc(65536) != 0 || upload(ctx->exp_table.p, tab.data(), 65536 * 4) != 0) { delete ctx; return nullptr; }
+    return ctx;
+}
+void cb_ctx_destroy(cb_ctx* ctx) { delete ctx; }
+int cb_ctx_sm_count(const cb_ctx* ctx) { return ctx->sms; }
+int cb_set_exp_table(cb_ctx* ctx, const float* table_host) { return upload(ctx->exp_table.p, table_host, 65536 * 4); }
+
+size_t cb_planes_act_bytes(int n) { return act_bytes(n, 128); }
+int cb_encode(cb_ctx*, const void* pos_dev, const int32_t* frame_idx_dev, int n, void* planes_act_dev, int16_t* planes_i16_dev, void* stream) {
+    return launch_encode((const Pos*)pos_dev, frame_idx_dev, n, (__nv_bfloat16*)planes_act_dev, planes_i16_dev, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------ network
+int cb_net_create(cb_ctx* ctx, int filters, int blocks, int max_batch, float leaky_slope, float bn_eps) {
+    if (filters < 1 || filters > 256 || blocks < 0 || max_batch < 1) { cb_set_error("cb_net_create: bad shape (filters 1..256)"); return -1; }
+    Net& net = ctx->net;
+    net = Net();
+    net.filters = filters;
+    net.cpad = (filters + 63) / 64 * 64;
+    net.blocks = blocks;
+    net.max_batch = max_batch;
+    net.slope = leaky_slope;
+    net.eps = bn_eps;
+    return 0;
+}
+int cb_net_set_tensor(cb_ctx* ctx, const char* name, const float* host, size_t count) {
+    ctx->net.host[name] = std::vector<float>(host, host + count);
+    ctx->net.ready = false;
+    return 0;
+}
+
+static int pack_conv(Net& net, ConvLayer& L, const std::vector<float>& w, int cin, int cin_pad, const std::vector<float>& bn, bool stem) {
+    const int C = net.filters, N = net.cpad;
+    if (w.size() != (size_t)9 * cin * C || bn.size() != (size_t)4 * C) { cb_set_error("conv tensor has wrong size"); return -1; }
+    L.kc = cin_pad / 64;
+    L.cj_in = cin_pad / 8;
+    std::vector<__nv_bfloat16> packed((size_t)L.kc * 9 * N * 64, __float2bfloat16(0.f));
+    for (int tap = 0; tap < 9; ++tap)
+        for (int ci = 0; ci < cin_pad; ++ci) {
+            int src_ci = ci;
+            if (stem) {  // channels 119 / 120 carry the bf16 remainders of move count / halfmove clock (encode.cu)
+                if (ci == 119) src_ci = 113;
+                else if (ci == 120) src_ci = 118;
+                else if (ci > 120) continue;
+            } else if (ci >= cin) continue;
+            const int kc = ci >> 6, k = ci & 63;
+            for (int co = 0; co < C; ++co)
+                packed[((size_t)(kc * 9 + tap) * N * 64) + ((size_t)(k >> 3) * N + co) * 8 + (k & 7)] =
+                    __float2bfloat16(w[((size_t)tap * cin + src_ci) * C + co]);
+        }
+    std::vector<float> scale(N, 0.f), shift(N, 0.f);
+    for (int c = 0; c < C; ++c) {
+        const double g = bn[c], b = bn[C + c], m = bn[2 * C + c], v = bn[3 * C + c];
+        const double s = g / sqrt(v + (double)net.eps);
+        scale[c] = (float)s;
+        shift[c] = (float)(b - m * s);
+    }
+    if (L.w.alloc(packed.size(), false) || L.scale.alloc(N, false) || L.shift.alloc(N, false)) return -1;
+    if (upload(L.w.p, packed.data(), packed.size() * 2) || upload(L.scale.p, scale.data(), N * 4) || upload(L.shift.p, shift.data(), N * 4)) return -1;
+    return 0;
+}
+
+int cb_net_finalize(cb_ctx* ctx) {
+    Net& net = ctx->net;
+    const int C = net.filters, N = net.cpad;
+    auto need = [&](const std::string& k) -> const std::vector<float>* {
+        auto it = net.host.find(k);
+        if (it == net.host.end()) { cb_set_error("missing tensor: " + k); return nullptr; }
+        return &it->second;
+    };
+    net.layers.clear();
+    net.layers.resize(1 + 2 * net.blocks);
+    const std::vector<float>*w = nullptr, *bn = nullptr;
+    if (!(w = need("stem.w")) || !(bn = need("stem.bn"))) return -1;
+    if (pack_conv(net, net.layers[0], *w, 119, 128, *bn, true)) return -1;
+    for (int i = 0; i < net.blocks; ++i)
+        for (int h = 0; h < 2; ++h) {
+            const std::string base = "res" + std::to_string(i);
+            if (!(w = need(base + (h ? ".w2" : ".w1"))) || !(bn = need(base + (h ? ".bn2" : ".bn1")))) return -1;
+            if (pack_conv(net, net.layers[1 + 2 * i + h], *w, C, N, *bn, false)) return -1;
+        }
+    const std::vector<float>*vc = nullptr, *vbn = nullptr, *fc1 = nullptr, *fc2 = nullptr, *pc = nullptr, *pbn = nullptr, *pfc = nullptr;
+    if (!(vc = need("value.conv")) || !(vbn = need("value.bn")) || !(fc1 = need("value.fc1")) || !(fc2 = need("value.fc2")) ||
+        !(pc = need("policy.conv")) || !(pbn = need("policy.bn")) || !(pfc = need("policy.fc")))
+        return -1;
+    if (vc->size() != (size_t)C || pc->size() != (size_t)2 * C || fc1->size() != (size_t)64 * C || fc2->size() != (size_t)C ||
+        pfc->size() != (size_t)128 * 4672 || vbn->size() != 4 || pbn->size() != 8) { cb_set_error("head tensor has wrong size"); return -1; }
+    std::vector<float> head_w(3 * N, 0.f), head_bn(6);
+    for (int c = 0; c < C; ++c) {
+        head_w[c] = (*vc)[c];
+        head_w[N + c] = (*pc)[c * 2];
+        head_w[2 * N + c] = (*pc)[c * 2 + 1];
+    }
+    {
+        const double s = (*vbn)[0] / sqrt((*vbn)[3] + (double)net.eps);
+        head_bn[0] = (float)s;
+        head_bn[1] = (float)((*vbn)[1] - (*vbn)[2] * s);
+        for (int c = 0; c < 2; ++c) {
+            const double sp = (*pbn)[c] / sqrt((*pbn)[6 + c] + (double)net.eps);
+            head_bn[2 + 2 * c] = (float)sp;
+            head_bn[3 + 2 * c] = (float)((*pbn)[2 + c] - (*pbn)[4 + c] * sp);
+        }
+    }
+    std::vector<float> wpt((size_t)4672 * 128);
+    for (int k = 0; k < 128; ++k)
+        for (int a = 0; a < 4672; ++a) wpt[(size_t)a * 128 + k] = (*pfc)[(size_t)k * 4672 + a];
+    if (net.head_w.alloc(3 * N, false) || net.head_bn.alloc(6, false) || net.fc1.alloc(64 * C, false) || net.fc2.alloc(C, false) ||
+        net.wp.alloc((size_t)128 * 4672, false) || net.wpt.alloc((size_t)128 * 4672, false))
+        return -1;
+    if (upload(net.head_w.p, head_w.data(), head_w.size() * 4) || upload(net.head_bn.p, head_bn.data(), 24) ||
+        upload(net.fc1.p, fc1->data(), fc1->size() * 4) || upload(net.fc2.p, fc2->data(), fc2->size() * 4) ||
+        upload(net.wp.p, pfc->data(), pfc->size() * 4) || upload(net.wpt.p, wpt.data(), wpt.size() * 4))
+        return -1;
+    const size_t act_elems = act_bytes(net.max_batch, N) / 2;
+    for (int i = 0; i < 3; ++i)
+        if (net.act[i].alloc(act_elems)) return -1;  // zeroed: border cells stay zero forever
+    const size_t mb = (size_t)(net.max_batch + 3) / 4 * 4;
+    if (net.head_raw.alloc(mb * 192) || net.pfeat.alloc(mb * 128)) return -1;
+    net.host.clear();
+    net.ready = true;
+    return 0;
+}
+
+// tower + head features; leaves pfeat/value for the callers below
+static int net_tower(cb_ctx* ctx, const void* planes_act_dev, int n, float* value_dev, cudaStream_t st) {
+    Net& net = ctx->net;
+    if (!net.ready) { cb_set_error("network not finalized"); return -1; }
+    if (n > net.max_batch) { cb_set_error("batch larger than max_batch"); return -1; }
+    const int pairs = (n + 1) / 2;
+    const __nv_bfloat16* in = (const __nv_bfloat16*)planes_act_dev;
+    int cur = -1;  // index of the act buffer holding the block input
+    const int nl = (int)net.layers.size();
+    for (int l = 0; l < nl; ++l) {
+        ConvLayer& L = net.layers[l];
+        ConvParams p{};
+        p.wgt = L.w.p; p.scale = L.scale.p; p.shift = L.shift.p;
+        p.pairs = pairs; p.kc = L.kc; p.cj_in = L.cj_in; p.n = net.cpad; p.slope = net.slope;
+        int out_i;
+        if (l == 0) { p.in = in; out_i = 0; p.skip = nullptr; }
+        else if (l & 1) { p.in = net.act[cur].p; out_i = (cur + 1) % 3; p.skip = nullptr; }       // first conv of a block
+        else { p.in = net.act[(cur + 1) % 3].p; out_i = (cur + 2) % 3; p.skip = net.act[cur].p; }  // second conv + skip
+        p.out = net.act[out_i].p;
+        if (l == nl - 1) { p.head_w = net.head_w.p; p.head_out = net.head_raw.p; }
+        if (launch_conv3x3(p, ctx->sms, st)) return -1;
+        if (l == 0 || !(l & 1)) cur = out_i;
+    }
+    HeadParams hp{net.head_raw.p, net.head_bn.p, net.fc1.p, net.fc2.p, net.filters, net.slope, value_dev, net.pfeat.p};
+    return launch_head_features(hp, n, st);
+}
+
+int cb_net_forward(cb_ctx* ctx, const void* planes_act_dev, int n, float* value_dev, void* logits_bf16_dev, float* logits_f32_dev, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (net_tower(ctx, planes_act_dev, n, value_dev, st)) return -1;
+    if (logits_bf16_dev || logits_f32_dev)
+        return launch_policy_dense(ctx->net.pfeat.p, ctx->net.wp.p, n, (__nv_bfloat16*)logits_bf16_dev, logits_f32_dev, st);
+    return 0;
+}
+
+int cb_synth_forward(cb_ctx* ctx, const int16_t* planes_i16_dev, int n, uint32_t seed, float* value_dev, void* logits_bf16_dev, void* stream) {
+    Search& s = ctx->search;
+    if (s.synth_hash.n < (size_t)n && s.synth_hash.alloc(n)) return -1;
+    return launch_synth(planes_i16_dev, n, seed, s.synth_hash.p, value_dev, (__nv_bfloat16*)logits_bf16_dev, (cudaStream_t)stream);
+}
+
+int cb_policy_softmax(cb_ctx* ctx, const void* pos_dev, const int32_t* cur_idx_dev, int n, const void* logits_bf16_dev,
+                      uint16_t* out_moves_dev, int16_t* out_actions_dev, float* out_priors_dev, int32_t* out_n_dev, void* stream) {
+    return launch_policy_softmax((const Pos*)pos_dev, cur_idx_dev, n, (const __nv_bfloat16*)logits_bf16_dev, ctx->exp_table.p,
+                                 out_moves_dev, out_actions_dev, out_priors_dev, out_n_dev, (cudaStream_t)stream);
+}
+
+int cb_debug_conv_layer(cb_ctx* ctx, int layer, const void* in_act_dev, const void* skip_act_dev, void* out_act_dev, int n_boards,
+                        int use_reference, void* stream) {
+    Net& net = ctx->net;
+    if (!net.ready || layer < 0 || layer >= (int)net.layers.size()) { cb_set_error("bad layer"); return -1; }
+    ConvLayer& L = net.layers[layer];
+    ConvParams p{};
+    p.in = (const __nv_bfloat16*)in_act_dev; p.out = (__nv_bfloat16*)out_act_dev; p.skip = (const __nv_bfloat16*)skip_act_dev;
+    p.wgt = L.w.p; p.scale = L.scale.p; p.shift = L.shift.p;
+    p.pairs = (n_boards + 1) / 2; p.kc = L.kc; p.cj_in = L.cj_in; p.n = net.cpad; p.slope = net.slope;
+    return use_reference ? launch_conv3x3_reference(p, (cudaStream_t)stream) : launch_conv3x3(p, ctx->sms, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------ search
+int cb_search_create(cb_ctx* ctx, int max_trees, int max_nodes, int max_positions, int max_sims) {
+    Search& s = ctx->search;
+    s.max_trees = max_trees;
+    s.max_sims = max_sims;
+    const size_t mt = max_trees, mm = (size_t)max_trees * MAX_MOVES;
+    if (s.nodes.alloc(max_nodes, false) || s.pos.alloc(max_positions, false) || s.trees.alloc(mt) || s.node_count.alloc(1) ||
+        s.pos_count.alloc(1) || s.frame_idx.alloc(mt * 8) || s.counters.alloc(4) || s.scratch_i32.alloc(4) || s.pend_moves.alloc(mm) ||
+        s.root_p64.alloc(mm) || s.noise.alloc(mm) || s.value.alloc(mt) || s.synth_hash.alloc(mt) ||
+        s.planes_act.alloc(act_bytes(max_trees, 128) / 2) || s.planes_i16.alloc(mt * 7616) || s.flags.alloc(mt) ||
+        s.r_moves.alloc(mm) || s.r_n.alloc(mm) || s.r_w.alloc(mm) || s.r_q.alloc(mm) || s.r_p.alloc(mm) || s.r_nc.alloc(mt) ||
+        s.r_rootn.alloc(mt) || s.r_nodes.alloc(mt))
+        return -1;
+    // ucb constants from the host libm, like the reference computes them (mcts.py:136-140)
+    const int tl = max_sims + 8;
+    std::vector<double> ct(tl), sq(tl);
+    for (int n = 0; n < tl; ++n) {
+        ct[n] = log((double)(n + 19652 + 1) / 19652.0) + 1.25;
+        sq[n] = pow((double)n, 0.5);
+    }
+    if (s.cpuct_tab.alloc(tl, false) || s.sqrt_tab.alloc(tl, false) || upload(s.cpuct_tab.p, ct.data(), tl * 8) ||
+        upload(s.sqrt_tab.p, sq.data(), tl * 8))
+        return -1;
+    SearchParams& sp = s.sp;
+    sp.nodes = s.nodes.p; sp.node_count = s.node_count.p; sp.max_nodes = max_nodes;
+    sp.pos = s.pos.p; sp.pos_count = s.pos_count.p; sp.max_pos = max_positions;
+    sp.trees = s.trees.p; sp.pend_moves = s.pend_moves.p; sp.frame_idx = s.frame_idx.p; sp.root_p64 = s.root_p64.p;
+    sp.noise = s.noise.p; sp.cpuct_tab = s.cpuct_tab.p; sp.sqrt_tab = s.sqrt_tab.p; sp.tab_len = tl;
+    sp.value = s.value.p; sp.synth_hash = s.synth_hash.p; sp.exp_table = ctx->exp_table.p; sp.counters = s.counters.p;
+    return 0;
+}
+
+int cb_search_begin(cb_ctx* ctx, int n_trees, const void* records_host, const int32_t* rec_len, const int32_t* sims,
+                    const double* cpuct, const uint8_t* has_noise, const double* noise, int max_game_length, int eval_mode,
+                    uint32_t synth_seed, void* stream) {
+    Search& s = ctx->search;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_trees > s.max_trees) { cb_set_error("n_trees > max_trees"); return -1; }
+    if (eval_mode == CB_EVAL_NET && !ctx->net.ready) { cb_set_error("CB_EVAL_NET without a finalized network"); return -1; }
+    if (eval_mode == CB_EVAL_NET && n_trees > ctx->net.max_batch) { cb_set_error("n_trees > network max_batch"); return -1; }
+    s.n_trees = n_trees;
+    s.eval_mode = eval_mode;
+    s.seed = synth_seed;
+    size_t total = 0;
+    for (int i = 0; i < n_trees; ++i) total += rec_len[i];
+    if ((int64_t)total >= s.sp.max_pos) { cb_set_error("root records exceed the position pool"); return -1; }
+    std::vector<Pos> rec((const Pos*)records_host, (const Pos*)records_host + total);
+    std::vector<TreeState> ts(n_trees);
+    size_t off = 0;
+    for (int i = 0; i < n_trees; ++i) {
+        if (rec_len[i] < 1) { cb_set_error("empty game record"); return -1; }
+        if (sims[i] > s.max_sims) { cb_set_error("sims > max_sims"); return -1; }
+        for (int k = 0; k < rec_len[i]; ++k) rec[off + k].pad_[0] = k ? (uint32_t)(off + k - 1) : 0xFFFFFFFFu;  // predecessor link
+        memset(&ts[i], 0, sizeof(TreeState));
+        ts[i].root_pos = (int32_t)(off + rec_len[i] - 1);
+        ts[i].sims_target = sims[i];
+        ts[i].status = 1;
+        ts[i].noisy = has_noise && has_noise[i] && noise;
+        ts[i].max_len = max_game_length;
+        ts[i].cpuct = cpuct ? cpuct[i] : -1.0;
+        off += rec_len[i];
+    }
+    const int32_t zero = 0, pc = (int32_t)total;
+    CB_CUDA_OK(cudaMemcpyAsync(s.pos.p, rec.data(), total * sizeof(Pos), cudaMemcpyHostToDevice, st));
+    CB_CUDA_OK(cudaMemcpyAsync(s.trees.p, ts.data(), n_trees * sizeof(TreeState), cudaMemcpyHostToDevice, st));
+    CB_CUDA_OK(cudaMemcpyAsync(s.node_count.p, &zero, 4, cudaMemcpyHostToDevice, st));
+    CB_CUDA_OK(cudaMemcpyAsync(s.pos_count.p, &pc, 4, cudaMemcpyHostToDevice, st));
+    CB_CUDA_OK(cudaMemsetAsync(s.counters.p, 0, 16, st));
+    if (noise) CB_CUDA_OK(cudaMemcpyAsync(s.noise.p, noise, (size_t)n_trees * MAX_MOVES * 8, cudaMemcpyHostToDevice, st));
+    CB_CUDA_OK(cudaStreamSynchronize(st));  // host staging vectors go out of scope
+    s.sp.n_trees = n_trees;
+    s.sp.eval_mode = eval_mode;
+    s.sp.pfeat = ctx->net.pfeat.p;
+    s.sp.wpt = ctx->net.wpt.p;
+    s.sp.expvals = s.expvals.p;
+    return launch_mcts_begin(s.sp, st);
+}
+
+int cb_search_step(cb_ctx* ctx, void* stream) {
+    Search& s = ctx->search;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (s.eval_mode == CB_EVAL_NET) {
+        if (launch_encode(s.pos.p, s.frame_idx.p, s.n_trees, s.planes_act.p, nullptr, st)) return -1;
+        if (net_tower(ctx, s.planes_act.p, s.n_trees, s.value.p, st)) return -1;
+    } else if (s.eval_mode == CB_EVAL_SYNTH) {
+        if (launch_encode(s.pos.p, s.frame_idx.p, s.n_trees, nullptr, s.planes_i16.p, st)) return -1;
+        if (launch_synth(s.planes_i16.p, s.n_trees, s.seed, s.synth_hash.p, s.value.p, nullptr, st)) return -1;
+    } else {
+        cb_set_error("cb_search_step: external evaluation uses cb_search_step_external");
+        return -1;
+    }
+    return launch_mcts_step(s.sp, st);
+}
+int cb_search_run(cb_ctx* ctx, int steps, void* stream) {
+    for (int i = 0; i < steps; ++i)
+        if (cb_search_step(ctx, stream)) return -1;
+    return 0;
+}
+int cb_search_pending_planes_sync(cb_ctx* ctx, int16_t* planes_host, uint8_t* waiting_host, void* stream) {
+    Search& s = ctx->search;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (launch_encode(s.pos.p, s.frame_idx.p, s.n_trees, nullptr, s.planes_i16.p, st)) return -1;
+    waiting_flags_kernel<<<(s.n_trees + 127) / 128, 128, 0, st>>>(s.trees.p, s.n_trees, s.flags.p);
+    CB_CUDA_OK(cudaMemcpyAsync(planes_host, s.planes_i16.p, (size_t)s.n_trees * 7616 * 2, cudaMemcpyDeviceToHost, st));
+    CB_CUDA_OK(cudaMemcpyAsync(waiting_host, s.flags.p, s.n_trees, cudaMemcpyDeviceToHost, st));
+    CB_CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+}
+int cb_search_step_external(cb_ctx* ctx, const float* value_host, const float* expvals_host, void* stream) {
+    Search& s = ctx->search;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (s.expvals.n < (size_t)s.n_trees * 4672) {
+        if (s.expvals.alloc((size_t)s.max_trees * 4672)) return -1;
+        s.sp.expvals = s.expvals.p;
+    }
+    CB_CUDA_OK(cudaMemcpyAsync(s.value.p, value_host, (size_t)s.n_trees * 4, cudaMemcpyHostToDevice, st));
+    CB_CUDA_OK(cudaMemcpyAsync(s.expvals.p, expvals_host, (size_t)s.n_trees * 4672 * 4, cudaMemcpyHostToDevice, st));
+    if (launch_mcts_step(s.sp, st)) return -1;
+    CB_CUDA_OK(cudaStreamSynchronize(st));  // the host buffers may be reused by the caller
+    return 0;
+}
+int cb_search_status_sync(cb_ctx* ctx, int64_t* counters, void* stream) {
+    Search& s = ctx->search;
+    cudaStream_t st = (cudaStream_t)stream;
+    CB_CUDA_OK(cudaMemsetAsync(s.scratch_i32.p, 0, 4, st));
+    count_unfinished_kernel<<<(s.n_trees + 127) / 128, 128, 0, st>>>(s.trees.p, s.n_trees, s.scratch_i32.p);
+    int32_t unfinished = 0, c[4];
+    CB_CUDA_OK(cudaMemcpyAsync(&unfinished, s.scratch_i32.p, 4, cudaMemcpyDeviceToHost, st));
+    CB_CUDA_OK(cudaMemcpyAsync(c, s.counters.p, 16, cudaMemcpyDeviceToHost, st));
+    CB_CUDA_OK(cudaStreamSynchronize(st));
+    counters[0] = unfinished; counters[1] = c[0]; counters[2] = c[1]; counters[3] = c[2];
+    return 0;
+}
+int cb_search_read_roots_sync(cb_ctx* ctx, uint16_t* moves, int32_t* n, float* w, float* q, double* p, int32_t* n_children,
+                              int32_t* root_n, int32_t* tree_nodes, void* stream) {
+    Search& s = ctx->search;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t mm = (size_t)s.n_trees * MAX_MOVES, mt = s.n_trees;
+    read_roots_kernel<<<s.n_trees, 64, 0, st>>>(s.sp, s.r_moves.p, s.r_n.p, s.r_w.p, s.r_q.p, s.r_p.p, s.r_nc.p, s.r_rootn.p, s.r_nodes.p);
+    CB_CUDA_OK(cudaGetLastError());
+    CB_CUDA_OK(cudaMemcpyAsync(moves, s.r_moves.p, mm * 2, cudaMemcpyDeviceToHost, st));
+    CB_CUDA_OK(cudaMemcpyAsync(n, s.r_n.p, mm * 4, cudaMemcpyDeviceToHost, st));
+    CB_CUDA_OK(cudaMemcpyAsync(w, s.r_w.p, mm * 4, cudaMemcpyDeviceToHost, st));
+    CB_CUDA_OK(cudaMemcpyAsync(q, s.r_q.p, mm * 4, cudaMemcpyDeviceToHost, st));
+    CB_CUDA_OK(cudaMemcpyAsync(p, s.r_p.p, mm * 8, cudaMemcpyDeviceToHost, st));
+    CB_CUDA_OK(cudaMemcpyAsync(n_children, s.r_nc.p, mt * 4, cudaMemcpyDeviceToHost, st));
+    CB_CUDA_OK(cudaMemcpyAsync(root_n, s.r_rootn.p, mt * 4, cudaMemcpyDeviceToHost, st));
+    CB_CUDA_OK(cudaMemcpyAsync(tree_nodes, s.r_nodes.p, mt * 4, cudaMemcpyDeviceToHost, st));
+    CB_CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,267 @@
+// K2 — 3x3 "same" convolution + BatchNorm + (residual add) + LeakyReLU of the residual tower
+// (model.py:19-28,35-37) as an implicit GEMM on tcgen05 tensor cores.
+//
+//   D[m, co] = sum_{tap, ci} A_tap[m, ci] * W[tap][ci][co]      m = (row, board, col) of 2 boards = 128 rows
+//
+// * A is never materialised: the activations of a board pair sit in HBM in the tile-native layout
+//   (common.cuh) with a zero border, one bulk async copy (UBLKCP) brings 64 channels of the pair
+//   into shared memory, and each of the nine taps is just a different start address of the
+//   K-major / no-swizzle UMMA descriptor (LBO 3200 B between the two 8-channel core matrices,
+//   SBO 160 B between 8-pixel groups).
+// * W is pre-packed per (k-chunk, tap) as a [8][N][8] bf16 block = one bulk copy per stage.
+// * One persistent CTA per SM works on units of FOUR boards: two 128-row tiles share every weight
+//   stage (halves the L2->smem weight traffic per MMA), accumulating into two 128 x N fp32
+//   accumulators that fill TMEM (2 x 256 columns).
+// * Warp roles: warp 0 = bulk-copy producer, warp 1 = MMA issuer (one lane) + TMEM owner,
+//   warps 2..5 = epilogue (tcgen05.ld -> BN scale/shift -> +skip -> LeakyReLU -> bf16 -> HBM in the
+//   same tile-native layout; optionally the three 1x1 head convolutions of model.py:43,52 as dot
+//   products over the fp32 row).
+#include "kernels.cuh"
+
+namespace cb {
+
+constexpr int CONV_THREADS = 192;
+constexpr int A_SLOTS = 2, B_SLOTS = 3;
+constexpr int A_SLOT_BYTES = 2 * ACT_K64_BYTES;  // two board pairs x 64 channels
+constexpr int B_SLOT_BYTES = 256 * 128;          // N <= 256 rows x 64 k x bf16
+
+
+struct ConvSmem {
+    uint64_t a_full[A_SLOTS], a_empty[A_SLOTS], b_full[B_SLOTS], b_empty[B_SLOTS], acc_full, acc_empty;
+    uint32_t tmem_base;
+    uint32_t pad_;
+};
+constexpr int CONV_SMEM_PARAM_FLOATS = 256 * 2 + 256 * 3;
+constexpr size_t CONV_SMEM_BYTES = 1024 + A_SLOTS * A_SLOT_BYTES + B_SLOTS * B_SLOT_BYTES + CONV_SMEM_PARAM_FLOATS * 4;
+
+__global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tcgen05_kernel(ConvParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    ConvSmem* s = reinterpret_cast<ConvSmem*>(smem);
+    uint8_t* a_buf = smem + 1024;
+    uint8_t* b_buf = a_buf + A_SLOTS * A_SLOT_BYTES;
+    float* s_scale = reinterpret_cast<float*>(b_buf + B_SLOTS * B_SLOT_BYTES);
+    float* s_shift = s_scale + 256;
+    float* s_head = s_shift + 256;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int units = (p.pairs + 1) / 2;
+    const int n = p.n;
+
+    for (int i = threadIdx.x; i < n; i += CONV_THREADS) {
+        s_scale[i] = p.scale[i];
+        s_shift[i] = p.shift[i];
+        if (p.head_w) {
+            s_head[i] = p.head_w[i];
+            s_head[256 + i] = p.head_w[n + i];
+            s_head[512 + i] = p.head_w[2 * n + i];
+        }
+    }
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < A_SLOTS; ++i) { ptx::mbar_init(&s->a_full[i], 1); ptx::mbar_init(&s->a_empty[i], 1); }
+        for (int i = 0; i < B_SLOTS; ++i) { ptx::mbar_init(&s->b_full[i], 1); ptx::mbar_init(&s->b_empty[i], 1); }
+        ptx::mbar_init(&s->acc_full, 1);
+        ptx::mbar_init(&s->acc_empty, 4);  // one arrival per epilogue warp
+        ptx::fence_barrier_init();
+    }
+    if (warp == 1) {
+        ptx::tmem_alloc(&s->tmem_base, 512);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem = s->tmem_base;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ producer
+        if (lane == 0) {
+            uint32_t a_it = 0, b_it = 0;
+            const uint32_t b_bytes = (uint32_t)n * 128;
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const int ntiles = (2 * u + 1 < p.pairs) ? 2 : 1;
+                for (int kc = 0; kc < p.kc; ++kc) {
+                    const int as = a_it % A_SLOTS;
+                    ptx::mbar_wait(&s->a_empty[as], ((a_it / A_SLOTS) & 1) ^ 1);
+                    ptx::mbar_expect_tx(&s->a_full[as], (uint32_t)ntiles * ACT_K64_BYTES);
+                    for (int t = 0; t < ntiles; ++t) {
+                        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.in) +
+                                             ((size_t)(2 * u + t) * p.cj_in + 8 * kc) * ACT_CHUNK_BYTES;
+                        ptx::bulk_g2s(a_buf + as * A_SLOT_BYTES + t * ACT_K64_BYTES, src, ACT_K64_BYTES, &s->a_full[as]);
+                    }
+                    ++a_it;
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int bs = b_it % B_SLOTS;
+                        ptx::mbar_wait(&s->b_empty[bs], ((b_it / B_SLOTS) & 1) ^ 1);
+                        ptx::mbar_expect_tx(&s->b_full[bs], b_bytes);
+                        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wgt) + (size_t)(kc * 9 + tap) * b_bytes;
+                        ptx::bulk_g2s(b_buf + bs * B_SLOT_BYTES, src, b_bytes, &s->b_full[bs]);
+                        ++b_it;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = ptx::idesc_bf16_f32(128, n);
+            uint32_t a_it = 0, b_it = 0, u_it = 0;
+            for (int u = blockIdx.x; u < units; u += gridDim.x, ++u_it) {
+                const int ntiles = (2 * u + 1 < p.pairs) ? 2 : 1;
+                ptx::mbar_wait(&s->acc_empty, (u_it & 1) ^ 1);
+                ptx::tc_fence_after();
+                for (int kc = 0; kc < p.kc; ++kc) {
+                    const int as = a_it % A_SLOTS;
+                    ptx::mbar_wait(&s->a_full[as], (a_it / A_SLOTS) & 1);
+                    const uint32_t a_base = ptx::smem_u32(a_buf + as * A_SLOT_BYTES);
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int bs = b_it % B_SLOTS;
+                        ptx::mbar_wait(&s->b_full[bs], (b_it / B_SLOTS) & 1);
+                        ptx::tc_fence_after();
+                        const uint32_t b_base = ptx::smem_u32(b_buf + bs * B_SLOT_BYTES);
+                        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                        const uint32_t a_tap = a_base + (uint32_t)(((1 + dy) * 20 + 1 + dx) * 16);
+                        for (int t = 0; t < ntiles; ++t) {
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {
+                                const uint64_t ad = ptx::smem_desc(a_tap + t * ACT_K64_BYTES + ks * 2 * ACT_CHUNK_BYTES,
+                                                                   ACT_CHUNK_BYTES, 160);
+                                const uint64_t bd = ptx::smem_desc(b_base + ks * 2 * n * 16, (uint32_t)n * 16, 128);
+                                ptx::umma_bf16(tmem + t * 256, ad, bd, idesc, (kc | tap | ks) != 0);
+                            }
+                        }
+                        ptx::umma_commit(&s->b_empty[bs]);  // weight stage consumed when these MMAs retire
+                        ++b_it;
+                    }
+                    ptx::umma_commit(&s->a_empty[as]);
+                    ++a_it;
+                }
+                ptx::umma_commit(&s->acc_full);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        const int q = warp & 3;          // TMEM lane quarter this warp may read
+        const int m = q * 32 + lane;     // accumulator row
+        const int g = m >> 3, col = m & 7, row = g >> 1, bip = g & 1;
+        const int cell = act_cell(row, bip, col);
+        const int cjo = n >> 3;
+        uint32_t u_it = 0;
+        for (int u = blockIdx.x; u < units; u += gridDim.x, ++u_it) {
+            const int ntiles = (2 * u + 1 < p.pairs) ? 2 : 1;
+            ptx::mbar_wait(&s->acc_full, u_it & 1);
+            ptx::tc_fence_after();
+            for (int t = 0; t < ntiles; ++t) {
+                const int pair = 2 * u + t;
+                float h0 = 0.f, h1 = 0.f, h2 = 0.f;
+                for (int cb = 0; cb < n / 32; ++cb) {
+                    uint4 sk[4];
+                    if (p.skip) {
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj)
+                            sk[jj] = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.skip) +
+                                                                     act_offset_bytes(pair, cjo, cb * 4 + jj, cell));
+                    }
+                    uint32_t acc[32];
+                    ptx::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + t * 256 + cb * 32, acc);
+                    ptx::tmem_wait_ld();
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        float v[8];
+                        const uint32_t* skw = reinterpret_cast<const uint32_t*>(&sk[jj]);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int ch = cb * 32 + jj * 8 + e;
+                            float x = fmaf(__uint_as_float(acc[jj * 8 + e]), s_scale[ch], s_shift[ch]);
+                            if (p.skip) {
+                                uint32_t w = skw[e >> 1];
+                                x += __uint_as_float((e & 1) ? (w & 0xFFFF0000u) : (w << 16));
+                            }
+                            x = x > 0.f ? x : x * p.slope;
+                            v[e] = x;
+                            if (p.head_w) {
+                                h0 = fmaf(x, s_head[ch], h0);
+                                h1 = fmaf(x, s_head[256 + ch], h1);
+                                h2 = fmaf(x, s_head[512 + ch], h2);
+                            }
+                        }
+                        uint4 o;
+                        __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]), t1 = __floats2bfloat162_rn(v[2], v[3]);
+                        __nv_bfloat162 t2 = __floats2bfloat162_rn(v[4], v[5]), t3 = __floats2bfloat162_rn(v[6], v[7]);
+                        o.x = *reinterpret_cast<uint32_t*>(&t0);
+                        o.y = *reinterpret_cast<uint32_t*>(&t1);
+                        o.z = *reinterpret_cast<uint32_t*>(&t2);
+                        o.w = *reinterpret_cast<uint32_t*>(&t3);
+                        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) +
+                                                  act_offset_bytes(pair, cjo, cb * 4 + jj, cell)) = o;
+                    }
+                }
+                if (p.head_w) {
+                    float* ho = p.head_out + ((size_t)(pair * 2 + bip) * 64 + row * 8 + col) * 3;
+                    ho[0] = h0; ho[1] = h1; ho[2] = h2;
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&s->acc_empty);
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) ptx::tmem_dealloc(tmem, 512);
+}
+
+// Plain CUDA-core restatement of the same layer on the same bf16 inputs (fp32 accumulate).  Test
+// infrastructure for the tcgen05 kernel (exported as cb_debug_conv_reference); never on the product path.
+__global__ void conv3x3_reference_kernel(ConvParams p) {
+    const int boards = p.pairs * 2;
+    const size_t total = (size_t)boards * 64 * p.n;
+    const int cjo = p.n >> 3;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int co = (int)(idx % p.n);
+        const int sq = (int)((idx / p.n) % 64);
+        const int board = (int)(idx / ((size_t)p.n * 64));
+        const int pair = board >> 1, bip = board & 1, row = sq >> 3, col = sq & 7;
+        float acc = 0.f;
+        for (int tap = 0; tap < 9; ++tap) {
+            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+            const int cell = act_cell(row + dy, bip, col + dx);  // border cells are zero
+            for (int ci = 0; ci < p.kc * 64; ++ci) {
+                const __nv_bfloat16 a = *reinterpret_cast<const __nv_bfloat16*>(
+                    reinterpret_cast<const uint8_t*>(p.in) + act_offset_bytes(pair, p.cj_in, ci >> 3, cell) + (ci & 7) * 2);
+                const int kc = ci >> 6, k = ci & 63;
+                const __nv_bfloat16 w = p.wgt[((size_t)(kc * 9 + tap) * p.n * 64) + ((size_t)(k >> 3) * p.n + co) * 8 + (k & 7)];
+                acc = fmaf(__bfloat162float(a), __bfloat162float(w), acc);
+            }
+        }
+        float x = fmaf(acc, p.scale[co], p.shift[co]);
+        const size_t off = act_offset_bytes(pair, cjo, co >> 3, act_cell(row, bip, col)) + (co & 7) * 2;
+        if (p.skip) x += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(reinterpret_cast<const uint8_t*>(p.skip) + off));
+        x = x > 0.f ? x : x * p.slope;
+        *reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(p.out) + off) = __float2bfloat16_rn(x);
+    }
+}
+
+int launch_conv3x3(const ConvParams& p, int num_sms, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        CB_CUDA_OK(cudaFuncSetAttribute(conv3x3_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV_SMEM_BYTES));
+        attr_set = true;
+    }
+    if (p.n % 64 != 0 || p.n > 256 || p.n < 64 || p.kc < 1 || p.pairs < 1) {
+        cb_set_error("conv3x3: unsupported shape");
+        return -1;
+    }
+    const int units = (p.pairs + 1) / 2;
+    const int grid = units < num_sms ? units : num_sms;
+    conv3x3_tcgen05_kernel<<<grid, CONV_THREADS, CONV_SMEM_BYTES, stream>>>(p);
+    CB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_conv3x3_reference(const ConvParams& p, cudaStream_t stream) {
+    conv3x3_reference_kernel<<<592, 256, 0, stream>>>(p);
+    CB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace cb

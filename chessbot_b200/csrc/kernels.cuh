@@ -1,0 +1,96 @@
+// Parameter blocks and launchers shared by the kernels (conv.cu, encode.cu, heads.cu, mcts.cu) and
+// the C ABI (api.cu).
+#pragma once
+#include "common.cuh"
+#include "rules.cuh"
+
+namespace cb {
+
+struct ConvParams {
+    const __nv_bfloat16* in;    // tile-native, cj_in chunks
+    __nv_bfloat16* out;         // tile-native, n/8 chunks
+    const __nv_bfloat16* skip;  // tile-native like out, or nullptr
+    const __nv_bfloat16* wgt;   // [kc][tap][8][n][8]
+    const float* scale;         // [n] gamma / sqrt(var + eps)
+    const float* shift;         // [n] beta - mean * scale
+    const float* head_w;        // [3][n] 1x1 head conv weights (value, policy0, policy1) or nullptr
+    float* head_out;            // [boards][64][3]
+    int pairs;                  // board pairs in the batch
+    int kc;                     // input channel chunks of 64
+    int cj_in;                  // input channels / 8
+    int n;                      // output channels (multiple of 64, <= 256)
+    float slope;                // LeakyReLU negative slope (Keras default 0.3)
+};
+
+struct HeadParams {
+    const float* head_raw;   // [boards][64][3]
+    const float* bn;         // [3][2] folded scale, shift for value conv, policy conv 0, policy conv 1
+    const float* fc1;        // [64][C]
+    const float* fc2;        // [C]
+    int c;                   // filters
+    float slope;
+    float* value;            // [boards]
+    float* pfeat;            // [boards][128]
+};
+
+struct Node {  // 32 bytes; children of a node are contiguous, in legal-move order
+    int32_t N;
+    float W, Q, P;
+    int32_t first_child;
+    int32_t parent;
+    int32_t pos_id;      // position of this node in the pos pool, -1 until first visited
+    uint16_t move;       // move that leads here
+    uint8_t n_children;
+    int8_t term;         // 0 unknown / not terminal, 1 terminal value 0, 2 terminal value -1 (side to move is mated)
+};
+static_assert(sizeof(Node) == 32, "Node must be 32 bytes");
+
+enum { TREE_IDLE = 0, TREE_WAIT_ROOT = 1, TREE_WAIT_LEAF = 2, TREE_DONE = 3 };
+enum { EVAL_NET = 0, EVAL_SYNTH = 1, EVAL_EXTERNAL = 2 };
+
+struct TreeState {  // 64 bytes
+    int32_t root_node, root_pos;
+    int32_t sims_done, sims_target;
+    int32_t leaf_node, leaf_pos;
+    int32_t n_moves, status;
+    int32_t n_nodes, n_evals;
+    int32_t noisy;       // add_exploration_noise applied at the root (P held in f64)
+    int32_t max_len;     // config.max_game_length
+    double cpuct;        // < 0: AlphaZero schedule log((N+19653)/19652)+1.25, else fixed (mcts.py:135-139)
+    int32_t error, pad_;
+};
+static_assert(sizeof(TreeState) == 64, "TreeState must be 64 bytes");
+
+struct SearchParams {
+    Node* nodes; int32_t* node_count; int32_t max_nodes;
+    Pos* pos; int32_t* pos_count; int32_t max_pos;
+    TreeState* trees; int n_trees;
+    uint16_t* pend_moves;      // [n_trees][MAX_MOVES]
+    int32_t* frame_idx;        // [n_trees][8] newest first
+    double* root_p64;          // [n_trees][MAX_MOVES]
+    const double* noise;       // [n_trees][MAX_MOVES] Gamma(0.3,1) samples drawn by the host (mcts.py:158)
+    const double* cpuct_tab;   // [tab_len] log((N+19653)/19652)+1.25 from the host libm
+    const double* sqrt_tab;    // [tab_len] pow(N, 0.5) from the host libm
+    int tab_len;
+    int eval_mode;
+    const float* value;        // [n_trees]
+    const float* pfeat;        // EVAL_NET: [n_trees][128]
+    const float* wpt;          // EVAL_NET: policy Dense transposed [4672][128]
+    const uint32_t* synth_hash;  // EVAL_SYNTH: [n_trees]
+    const float* expvals;      // EVAL_EXTERNAL: [n_trees][4672] exp(logit) from the host
+    const float* exp_table;    // [65536] f32 exp indexed by bf16 bits
+    int32_t* counters;         // [0] evals, [1] sims, [2] errors
+};
+
+int launch_conv3x3(const ConvParams& p, int num_sms, cudaStream_t stream);
+int launch_conv3x3_reference(const ConvParams& p, cudaStream_t stream);
+int launch_encode(const Pos* pos_base, const int32_t* frame_idx, int n, __nv_bfloat16* planes_act, int16_t* planes_i16, cudaStream_t stream);
+int launch_head_features(const HeadParams& p, int boards, cudaStream_t stream);
+int launch_policy_dense(const float* pfeat, const float* w, int boards, __nv_bfloat16* logits_bf16, float* logits_f32, cudaStream_t stream);
+int launch_synth(const int16_t* planes_i16, int n, uint32_t seed, uint32_t* hash_out, float* value, __nv_bfloat16* logits_dense, cudaStream_t stream);
+int launch_mcts_begin(const SearchParams& sp, cudaStream_t stream);
+int launch_mcts_step(const SearchParams& sp, cudaStream_t stream);
+int launch_policy_softmax(const Pos* pos, const int32_t* cur_idx, int n, const __nv_bfloat16* logits, const float* exp_table,
+                          uint16_t* out_moves, int16_t* out_actions, float* out_priors, int32_t* out_n, cudaStream_t stream);
+
+}  // namespace cb

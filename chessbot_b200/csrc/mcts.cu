@@ -1,0 +1,325 @@
+// K6/K7/K8 — PUCT select, device chess rules at the leaf, expand and backup (mcts.py:38-161) for
+// many concurrent trees over a GPU-resident node pool.  One warp per tree, one in-flight leaf per
+// tree: every tree runs the reference's strictly sequential simulation order, the batching is
+// ACROSS trees (batch = number of games), so visit counts are those of the reference.
+//
+// One launch of mcts_step_kernel per batch step does, per tree:
+//   A. if a leaf evaluation is pending: priors for its legal moves (K5: gather, exp table, NumPy
+//      pairwise sum, divide), children appended to the node pool, value backed up to the root;
+//   B. then simulations until the next leaf that needs the network: descend by arg-max ucb
+//      (f32 arithmetic without FMA contraction; f64 at a noisy root; ties -> larger UCI string),
+//      make the move (rules.cuh), test outcome(claim_draw=True); terminal leaves are backed up
+//      immediately (the reference re-evaluates them on every visit, mcts.py:67-74) and the descent
+//      restarts; a non-terminal leaf records its ordered legal moves + the 8 frames to encode.
+#include "kernels.cuh"
+#include "policy.cuh"
+
+namespace cb {
+
+
+
+
+
+__device__ __forceinline__ const Pos* prev_pos(const Pos* base, const Pos* q) {
+    const int32_t pi = (int32_t)q->pad_[0];
+    return pi >= 0 ? base + pi : nullptr;
+}
+struct PoolPrev {
+    const Pos* base;
+    __device__ const Pos* operator()(const Pos* q) const { return prev_pos(base, q); }
+};
+
+__device__ __forceinline__ uint32_t fmix32_d(uint32_t x) {
+    x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+    return x;
+}
+
+// frames for the encoder: walk the record newest first, stop after a position with an empty move stack
+__device__ void fill_frames(const SearchParams& sp, int tree, int pos_id) {
+    int32_t* fi = sp.frame_idx + (size_t)tree * 8;
+    int cur = pos_id;
+    for (int t = 0; t < 8; ++t) {
+        fi[t] = cur;
+        if (cur >= 0) {
+            const Pos& q = sp.pos[cur];
+            cur = q.ply == 0 ? -1 : (int32_t)q.pad_[0];
+        }
+    }
+}
+
+// mcts.update (mcts.py:112-117), f32 accumulate, sign flip per ply
+__device__ void backup(Node* nodes, int node, float v) {
+    while (node >= 0) {
+        Node& nd = nodes[node];
+        nd.N += 1;
+        nd.W = __fadd_rn(nd.W, v);
+        nd.Q = __fdiv_rn(nd.W, (float)nd.N);
+        v = -v;
+        node = nd.parent;
+    }
+}
+
+constexpr int MCTS_WARPS = 4;
+
+__global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_step_kernel(SearchParams sp) {
+    __shared__ float s_p[MCTS_WARPS][MAX_MOVES];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tree = blockIdx.x * MCTS_WARPS + warp;
+    if (tree >= sp.n_trees) return;
+    TreeState& ts = sp.trees[tree];
+    int status = ts.status;
+    if (status == TREE_IDLE || status == TREE_DONE || ts.error) return;
+    float* pv = s_p[warp];
+
+    // ------------------------------------------------------------------ A. expand + backup
+    {
+        const int n = ts.n_moves, leaf = ts.leaf_node;
+        const uint16_t* moves = sp.pend_moves + (size_t)tree * MAX_MOVES;
+        const int turn = sp.pos[ts.leaf_pos].turn;
+        for (int i = lane; i < n; i += 32) {
+            const int a = move_to_action(moves[i], turn);
+            float e;
+            if (sp.eval_mode == EVAL_NET) {
+                const float4* wr = reinterpret_cast<const float4*>(sp.wpt + (size_t)a * 128);
+                const float4* pf = reinterpret_cast<const float4*>(sp.pfeat + (size_t)tree * 128);
+                float acc = 0.f;
+#pragma unroll 8
+                for (int k = 0; k < 32; ++k) {
+                    const float4 w = wr[k], f = pf[k];
+                    acc = fmaf(f.x, w.x, acc); acc = fmaf(f.y, w.y, acc); acc = fmaf(f.z, w.z, acc); acc = fmaf(f.w, w.w, acc);
+                }
+                e = sp.exp_table[__bfloat16_as_ushort(__float2bfloat16_rn(acc))];
+            } else if (sp.eval_mode == EVAL_SYNTH) {
+                const uint32_t u = fmix32_d(sp.synth_hash[tree] ^ (((uint32_t)a + 1u) * 0x9E3779B1u));
+                const float logit = (float)((int)((u >> 16) & 0xFF) - 128) / 32.0f;
+                e = sp.exp_table[__bfloat16_as_ushort(__float2bfloat16_rn(logit))];
+            } else {
+                e = sp.expvals[(size_t)tree * 4672 + a];
+            }
+            pv[i] = e;
+        }
+        __syncwarp();
+        const float sum = numpy_sum_f32_warp(pv, n, lane);
+        int base = 0;
+        if (lane == 0) {
+            base = atomicAdd(sp.node_count, n);
+            if (base + n > sp.max_nodes) { ts.error = 1; atomicAdd(&sp.counters[2], 1); }
+        }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base + n > sp.max_nodes) return;
+        const bool is_root = status == TREE_WAIT_ROOT;
+        for (int i = lane; i < n; i += 32) {
+            Node c;
+            c.N = 0; c.W = 0.f; c.Q = 0.f;
+            c.P = __fdiv_rn(pv[i], sum);
+            c.first_child = -1; c.parent = leaf; c.pos_id = -1;
+            c.move = moves[i]; c.n_children = 0; c.term = 0;
+            sp.nodes[base + i] = c;
+            if (is_root && ts.noisy) {
+                // mcts.py:161: P*(1-frac) in f32, noise*frac in f64, sum in f64
+                const float p75 = __fmul_rn(c.P, 0.75f);
+                sp.root_p64[(size_t)tree * MAX_MOVES + i] =
+                    __dadd_rn((double)p75, __dmul_rn(sp.noise[(size_t)tree * MAX_MOVES + i], 0.25));
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {
+            Node& lf = sp.nodes[leaf];
+            lf.first_child = base;
+            lf.n_children = (uint8_t)n;
+            ts.n_nodes += n;
+            ts.n_evals += 1;
+            atomicAdd(&sp.counters[0], 1);
+            if (!is_root) {
+                backup(sp.nodes, leaf, -sp.value[tree]);
+                ts.sims_done += 1;
+                atomicAdd(&sp.counters[1], 1);
+            }
+            __threadfence_block();
+        }
+        __syncwarp();
+    }
+
+    // ------------------------------------------------------------------ B. simulate to the next leaf
+    int sims_done = __shfl_sync(0xffffffffu, ts.sims_done, 0);
+    const int sims_target = ts.sims_target;
+    const bool noisy = ts.noisy != 0;
+    const double cpuct_fixed = ts.cpuct;
+    while (true) {
+        if (sims_done >= sims_target) {
+            if (lane == 0) ts.status = TREE_DONE;
+            return;
+        }
+        int node = ts.root_node;
+        int parent_pos = ts.root_pos;
+        // ---- select (mcts.py:62-64,119-140)
+        while (true) {
+            const Node nd = sp.nodes[node];
+            if (nd.n_children == 0) break;
+            if (nd.pos_id >= 0) parent_pos = nd.pos_id;
+            const int np = nd.N < sp.tab_len ? nd.N : sp.tab_len - 1;
+            const double c = cpuct_fixed < 0 ? sp.cpuct_tab[np] : cpuct_fixed;
+            const double sq = sp.sqrt_tab[np];
+            const bool f64 = noisy && node == ts.root_node;
+            double best_u = 0;
+            int best_key = -1, best_i = -1;
+            for (int i = lane; i < nd.n_children; i += 32) {
+                const Node ch = sp.nodes[nd.first_child + i];
+                double u;
+                if (f64) {
+                    double t = __dmul_rn(c, sp.root_p64[(size_t)tree * MAX_MOVES + i]);
+                    t = __dmul_rn(t, sq);
+                    t = __ddiv_rn(t, (double)(ch.N + 1));
+                    u = __dadd_rn((double)ch.Q, t);
+                } else {
+                    float t = __fmul_rn((float)c, ch.P);
+                    t = __fmul_rn(t, (float)sq);
+                    t = __fdiv_rn(t, (float)(ch.N + 1));
+                    u = (double)__fadd_rn(ch.Q, t);  // f32 value, exactly representable in f64
+                }
+                const int key = uci_sort_key(ch.move);
+                if (best_i < 0 || u > best_u || (u == best_u && key > best_key)) { best_u = u; best_key = key; best_i = i; }
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ou = __shfl_xor_sync(0xffffffffu, best_u, o);
+                const int ok = __shfl_xor_sync(0xffffffffu, best_key, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+                if (oi >= 0 && (best_i < 0 || ou > best_u || (ou == best_u && ok > best_key))) { best_u = ou; best_key = ok; best_i = oi; }
+            }
+            node = nd.first_child + best_i;
+        }
+        // ---- leaf: position, outcome (mcts.py:67, game.py:49-59)
+        int term = 0, n_moves = 0, leaf_pos = -1, err = 0;
+        if (lane == 0) {
+            Node& lf = sp.nodes[node];
+            term = lf.term;
+            leaf_pos = lf.pos_id;
+            if (leaf_pos < 0) {
+                const Pos& pp = sp.pos[parent_pos];
+                Pos np_ = push_move(pp, lf.move);
+                np_.pad_[0] = (uint32_t)parent_pos;
+                np_.occur = (uint8_t)count_occurrences(np_, &pp, PoolPrev{sp.pos});
+                leaf_pos = atomicAdd(sp.pos_count, 1);
+                if (leaf_pos >= sp.max_pos) {
+                    err = 1;
+                } else {
+                    sp.pos[leaf_pos] = np_;
+                    lf.pos_id = leaf_pos;
+                    MoveList ml;
+                    generate_legal(np_, ml);
+                    const int out = outcome_claim_draw(np_, ml, &pp, PoolPrev{sp.pos}, ts.max_len);
+                    if (out != OUT_NONE) {
+                        term = terminal_value_to_play(out) < 0 ? 2 : 1;
+                        lf.term = (int8_t)term;
+                    } else {
+                        n_moves = ml.n;
+                        uint16_t* pm = sp.pend_moves + (size_t)tree * MAX_MOVES;
+                        for (int i = 0; i < ml.n; ++i) pm[i] = ml.m[i];
+                    }
+                }
+            }
+            if (!err && term) {
+                // evaluate() returned (value, True): update(node, -value) with value = -1 or 0
+                backup(sp.nodes, node, term == 2 ? 1.0f : -0.0f);
+                ts.sims_done += 1;
+                atomicAdd(&sp.counters[1], 1);
+            } else if (!err) {
+                ts.leaf_node = node;
+                ts.leaf_pos = leaf_pos;
+                ts.n_moves = n_moves;
+                ts.status = TREE_WAIT_LEAF;
+                fill_frames(sp, tree, leaf_pos);
+            } else {
+                ts.error = 2;
+                atomicAdd(&sp.counters[2], 1);
+            }
+            __threadfence_block();
+        }
+        __syncwarp();
+        term = __shfl_sync(0xffffffffu, term, 0);
+        err = __shfl_sync(0xffffffffu, err, 0);
+        if (err || !term) return;
+        ++sims_done;
+    }
+}
+
+// Root set-up (mcts.py:50-52): node 0 of each tree with N = 1, its legal moves pending for expand.
+__global__ void __launch_bounds__(128) mcts_begin_kernel(SearchParams sp) {
+    const int tree = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tree >= sp.n_trees) return;
+    TreeState& ts = sp.trees[tree];
+    if (ts.status != TREE_WAIT_ROOT) return;
+    const int node = atomicAdd(sp.node_count, 1);
+    if (node >= sp.max_nodes) { ts.error = 1; atomicAdd(&sp.counters[2], 1); return; }
+    Node r;
+    r.N = 1; r.W = 0.f; r.Q = 0.f; r.P = 0.f;
+    r.first_child = -1; r.parent = -1; r.pos_id = ts.root_pos; r.move = 0; r.n_children = 0; r.term = 0;
+    sp.nodes[node] = r;
+    ts.root_node = node;
+    ts.leaf_node = node;
+    ts.leaf_pos = ts.root_pos;
+    ts.n_nodes = 1;
+    ts.n_evals = 0;
+    ts.sims_done = 0;
+    MoveList ml;
+    generate_legal(sp.pos[ts.root_pos], ml);
+    ts.n_moves = ml.n;
+    uint16_t* pm = sp.pend_moves + (size_t)tree * MAX_MOVES;
+    for (int i = 0; i < ml.n; ++i) pm[i] = ml.m[i];
+    fill_frames(sp, tree, ts.root_pos);
+}
+
+int launch_mcts_begin(const SearchParams& sp, cudaStream_t stream) {
+    mcts_begin_kernel<<<(sp.n_trees + 127) / 128, 128, 0, stream>>>(sp);
+    CB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+int launch_mcts_step(const SearchParams& sp, cudaStream_t stream) {
+    mcts_step_kernel<<<(sp.n_trees + MCTS_WARPS - 1) / MCTS_WARPS, MCTS_WARPS * 32, 0, stream>>>(sp);
+    CB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------ stand-alone K5
+// encode+forward+mask/softmax of BASELINE config 2: one warp per position generates the ordered legal
+// moves of pos[cur_idx[i]] and writes moves, action indices and priors.
+__global__ void __launch_bounds__(128) policy_softmax_kernel(const Pos* __restrict__ pos, const int32_t* __restrict__ cur_idx, int n,
+                                                             const __nv_bfloat16* __restrict__ logits /*[n][4672]*/,
+                                                             const float* __restrict__ exp_table, uint16_t* __restrict__ out_moves,
+                                                             int16_t* __restrict__ out_actions, float* __restrict__ out_priors,
+                                                             int32_t* __restrict__ out_n) {
+    __shared__ float s_p[4][MAX_MOVES];
+    __shared__ uint16_t s_m[4][MAX_MOVES];
+    __shared__ int s_n[4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 4 + warp;
+    if (i >= n) return;
+    const Pos& p = pos[cur_idx[i]];
+    if (lane == 0) {
+        MoveList ml;
+        generate_legal(p, ml);
+        s_n[warp] = ml.n;
+        for (int k = 0; k < ml.n; ++k) s_m[warp][k] = ml.m[k];
+    }
+    __syncwarp();
+    const int nm = s_n[warp];
+    for (int k = lane; k < nm; k += 32) {
+        const int a = move_to_action(s_m[warp][k], p.turn);
+        out_moves[(size_t)i * MAX_MOVES + k] = s_m[warp][k];
+        out_actions[(size_t)i * MAX_MOVES + k] = (int16_t)a;
+        s_p[warp][k] = exp_table[__bfloat16_as_ushort(logits[(size_t)i * 4672 + a])];
+    }
+    __syncwarp();
+    const float sum = numpy_sum_f32_warp(s_p[warp], nm, lane);
+    for (int k = lane; k < nm; k += 32) out_priors[(size_t)i * MAX_MOVES + k] = __fdiv_rn(s_p[warp][k], sum);
+    if (lane == 0) out_n[i] = nm;
+}
+int launch_policy_softmax(const Pos* pos, const int32_t* cur_idx, int n, const __nv_bfloat16* logits, const float* exp_table,
+                          uint16_t* out_moves, int16_t* out_actions, float* out_priors, int32_t* out_n, cudaStream_t stream) {
+    if (n <= 0) return 0;
+    policy_softmax_kernel<<<(n + 3) / 4, 128, 0, stream>>>(pos, cur_idx, n, logits, exp_table, out_moves, out_actions, out_priors, out_n);
+    CB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace cb

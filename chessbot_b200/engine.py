@@ -1,0 +1,223 @@
+"""Python host of the B200 hot path: owns device memory through PyTorch and calls the C ABI.
+
+PyTorch is plumbing here (allocation, streams); every computation is a hand-written sm_100a kernel in
+libchessbot_b200.so.  Nothing in this module falls back to the CPU: without a B200 `Engine()` raises.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from ._lib import CB_MAX_MOVES, CB_NUM_ACTIONS, CB_POS_BYTES, check, last_error, lib
+
+EVAL_NET, EVAL_SYNTH, EVAL_EXTERNAL = 0, 1, 2
+_engines = {}
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def numpy_exp_table():
+    """f32 exp for every bf16 bit pattern, from this host's np.exp (mcts.py:94 uses np.exp(float32))."""
+    bits = (np.arange(65536, dtype=np.uint32) << 16).view(np.float32)
+    with np.errstate(over="ignore", invalid="ignore"):
+        return np.exp(bits, dtype=np.float32)
+
+
+def act_to_nhwc(act, n, channels):
+    """tile-native activation buffer (bf16) -> [n, 8, 8, channels] (test / debug helper)."""
+    pairs = (n + 1) // 2
+    v = act.view(torch.bfloat16)[: pairs * (channels // 8) * 1600].view(pairs, channels // 8, 10, 2, 10, 8)
+    v = v[:, :, 1:9, :, 1:9, :]                       # P, j, row, b, col, e
+    return v.permute(0, 3, 2, 4, 1, 5).reshape(pairs * 2, 8, 8, channels)[:n]
+
+
+def nhwc_to_act(x):
+    """[n, 8, 8, C] (C multiple of 8) -> tile-native bf16 buffer with zero border."""
+    n, _, _, c = x.shape
+    pairs = (n + 1) // 2
+    buf = torch.zeros(pairs, c // 8, 10, 2, 10, 8, dtype=torch.bfloat16, device=x.device)
+    xp = torch.zeros(pairs * 2, 8, 8, c, dtype=torch.bfloat16, device=x.device)
+    xp[:n] = x.to(torch.bfloat16)
+    buf[:, :, 1:9, :, 1:9, :] = xp.view(pairs, 2, 8, 8, c // 8, 8).permute(0, 4, 2, 1, 3, 5)
+    return buf.reshape(-1)
+
+
+class Engine:
+    """One device context per GPU (cb_ctx)."""
+
+    def __init__(self, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("chessbot_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device("cuda", self.device_index)
+        torch.cuda.set_device(self.device_index)
+        self._h = lib.cb_ctx_create(self.device_index)
+        if not self._h:
+            raise RuntimeError(f"cb_ctx_create: {last_error()}")
+        self.sm_count = lib.cb_ctx_sm_count(self._h)
+        tab = numpy_exp_table()
+        check(lib.cb_set_exp_table(self._h, tab.ctypes.data), "set_exp_table")
+        self.net_shape = None
+        self.search_shape = None
+
+    @classmethod
+    def get(cls, device=None):
+        idx = torch.cuda.current_device() if device is None else int(device)
+        if idx not in _engines:
+            _engines[idx] = cls(idx)
+        return _engines[idx]
+
+    # ------------------------------------------------------------------ gameimage
+    def upload_records(self, records):
+        """records: list of uint8 [k_i, 96] game records (Board.export_record) -> (pos tensor, frame_idx [n,8])."""
+        lens = [len(r) for r in records]
+        flat = np.concatenate(records, axis=0)
+        # predecessor links (Pos.pad_[0], byte offset 84) and frame lists, newest first
+        ply = flat[:, 74].astype(np.int32) | (flat[:, 75].astype(np.int32) << 8)
+        frame_idx = np.full((len(records), 8), -1, dtype=np.int32)
+        off = 0
+        for i, k in enumerate(lens):
+            cur = off + k - 1
+            for t in range(8):
+                frame_idx[i, t] = cur
+                if ply[cur] == 0 or cur == off:
+                    break
+                cur -= 1
+            off += k
+        pos = torch.from_numpy(flat).to(self.device)
+        return pos, torch.from_numpy(frame_idx).to(self.device)
+
+    def encode(self, pos, frame_idx, want_act=True, want_i16=False):
+        n = frame_idx.shape[0]
+        act = torch.zeros(lib.cb_planes_act_bytes(n) // 2, dtype=torch.bfloat16, device=self.device) if want_act else None
+        i16 = torch.empty(n, 8, 8, 119, dtype=torch.int16, device=self.device) if want_i16 else None
+        check(lib.cb_encode(self._h, _ptr(pos), _ptr(frame_idx), n, _ptr(act), _ptr(i16), _stream()), "encode")
+        return act, i16
+
+    # ------------------------------------------------------------------ model
+    def load_network(self, weights, filters, blocks, max_batch, slope=0.3, eps=1e-3):
+        check(lib.cb_net_create(self._h, filters, blocks, max_batch, slope, eps), "net_create")
+        for name, arr in weights.items():
+            a = np.ascontiguousarray(arr, dtype=np.float32)
+            check(lib.cb_net_set_tensor(self._h, name.encode(), a.ctypes.data, a.size), "net_set_tensor")
+        check(lib.cb_net_finalize(self._h), "net_finalize")
+        self.net_shape = (filters, blocks, max_batch)
+
+    def forward(self, planes_act, n, want_bf16=True, want_f32=False):
+        value = torch.empty(n, dtype=torch.float32, device=self.device)
+        lb = torch.empty(n, CB_NUM_ACTIONS, dtype=torch.bfloat16, device=self.device) if want_bf16 else None
+        lf = torch.empty(n, CB_NUM_ACTIONS, dtype=torch.float32, device=self.device) if want_f32 else None
+        check(lib.cb_net_forward(self._h, _ptr(planes_act), n, _ptr(value), _ptr(lb), _ptr(lf), _stream()), "net_forward")
+        return value, lb, lf
+
+    def synth_forward(self, planes_i16, seed=0):
+        n = planes_i16.shape[0]
+        value = torch.empty(n, dtype=torch.float32, device=self.device)
+        lb = torch.empty(n, CB_NUM_ACTIONS, dtype=torch.bfloat16, device=self.device)
+        check(lib.cb_synth_forward(self._h, _ptr(planes_i16), n, seed, _ptr(value), _ptr(lb), _stream()), "synth_forward")
+        return value, lb
+
+    def policy_softmax(self, pos, cur_idx, logits_bf16):
+        n = cur_idx.shape[0]
+        moves = torch.zeros(n, CB_MAX_MOVES, dtype=torch.int16, device=self.device)
+        actions = torch.zeros(n, CB_MAX_MOVES, dtype=torch.int16, device=self.device)
+        priors = torch.zeros(n, CB_MAX_MOVES, dtype=torch.float32, device=self.device)
+        counts = torch.zeros(n, dtype=torch.int32, device=self.device)
+        check(lib.cb_policy_softmax(self._h, _ptr(pos), _ptr(cur_idx), n, _ptr(logits_bf16), _ptr(moves), _ptr(actions),
+                                    _ptr(priors), _ptr(counts), _stream()), "policy_softmax")
+        return moves, actions, priors, counts
+
+    def debug_conv_layer(self, layer, in_act, skip_act, n_boards, out_channels, use_reference=False):
+        out = torch.zeros(((n_boards + 1) // 2) * (out_channels // 8) * 1600, dtype=torch.bfloat16, device=self.device)
+        check(lib.cb_debug_conv_layer(self._h, layer, _ptr(in_act), _ptr(skip_act), _ptr(out), n_boards, int(use_reference),
+                                      _stream()), "debug_conv_layer")
+        return out
+
+    # ------------------------------------------------------------------ mcts
+    def search_create(self, max_trees, max_nodes=None, max_positions=None, max_sims=800):
+        max_nodes = max_nodes or max_trees * (max_sims + 2) * 40
+        max_positions = max_positions or max_trees * (max_sims + 2 + 160)
+        if self.search_shape == (max_trees, max_nodes, max_positions, max_sims):
+            return
+        check(lib.cb_search_create(self._h, max_trees, max_nodes, max_positions, max_sims), "search_create")
+        self.search_shape = (max_trees, max_nodes, max_positions, max_sims)
+
+    def search_begin(self, records, sims, cpuct=None, noise=None, max_game_length=512, eval_mode=EVAL_NET, seed=0):
+        """records: list of uint8 [k_i,96]; sims: int or list; cpuct: None / float / list (None = AlphaZero
+        schedule); noise: None or list (per tree) of None / float64 arrays of Gamma(0.3,1) samples."""
+        n = len(records)
+        lens = np.array([len(r) for r in records], dtype=np.int32)
+        flat = np.ascontiguousarray(np.concatenate(records, axis=0))
+        sims_a = np.full(n, sims, dtype=np.int32) if np.isscalar(sims) else np.asarray(sims, dtype=np.int32)
+        if cpuct is None or np.isscalar(cpuct):
+            cp = np.full(n, -1.0 if cpuct is None else float(cpuct), dtype=np.float64)
+        else:
+            cp = np.array([-1.0 if c is None else float(c) for c in cpuct], dtype=np.float64)
+        has_noise = np.zeros(n, dtype=np.uint8)
+        noise_a = None
+        if noise is not None:
+            noise_a = np.zeros((n, CB_MAX_MOVES), dtype=np.float64)
+            for i, z in enumerate(noise):
+                if z is not None:
+                    z = np.asarray(z, dtype=np.float64)[:CB_MAX_MOVES]
+                    noise_a[i, : len(z)] = z
+                    has_noise[i] = 1
+        self._n_trees = n
+        check(lib.cb_search_begin(self._h, n, flat.ctypes.data, lens.ctypes.data, sims_a.ctypes.data, cp.ctypes.data,
+                                  has_noise.ctypes.data, noise_a.ctypes.data if noise_a is not None else None,
+                                  max_game_length, eval_mode, seed, _stream()), "search_begin")
+
+    def search_run(self, steps):
+        check(lib.cb_search_run(self._h, steps, _stream()), "search_run")
+
+    def search_status(self):
+        c = np.zeros(4, dtype=np.int64)
+        check(lib.cb_search_status_sync(self._h, c.ctypes.data, _stream()), "search_status")
+        return {"unfinished": int(c[0]), "evals": int(c[1]), "sims": int(c[2]), "errors": int(c[3])}
+
+    def search_pending_planes(self):
+        n = self._n_trees
+        planes = np.empty((n, 8, 8, 119), dtype=np.int16)
+        waiting = np.zeros(n, dtype=np.uint8)
+        check(lib.cb_search_pending_planes_sync(self._h, planes.ctypes.data, waiting.ctypes.data, _stream()), "pending_planes")
+        return planes, waiting.astype(bool)
+
+    def search_step_external(self, values, expvals):
+        v = np.ascontiguousarray(values, dtype=np.float32)
+        e = np.ascontiguousarray(expvals, dtype=np.float32)
+        check(lib.cb_search_step_external(self._h, v.ctypes.data, e.ctypes.data, _stream()), "step_external")
+
+    def search_read_roots(self):
+        n = self._n_trees
+        moves = np.zeros((n, CB_MAX_MOVES), dtype=np.uint16)
+        N = np.zeros((n, CB_MAX_MOVES), dtype=np.int32)
+        W = np.zeros((n, CB_MAX_MOVES), dtype=np.float32)
+        Q = np.zeros((n, CB_MAX_MOVES), dtype=np.float32)
+        P = np.zeros((n, CB_MAX_MOVES), dtype=np.float64)
+        nc = np.zeros(n, dtype=np.int32)
+        root_n = np.zeros(n, dtype=np.int32)
+        nodes = np.zeros(n, dtype=np.int32)
+        check(lib.cb_search_read_roots_sync(self._h, moves.ctypes.data, N.ctypes.data, W.ctypes.data, Q.ctypes.data,
+                                            P.ctypes.data, nc.ctypes.data, root_n.ctypes.data, nodes.ctypes.data, _stream()),
+              "read_roots")
+        return {"moves": moves, "N": N, "W": W, "Q": Q, "P": P, "n_children": nc, "root_N": root_n, "nodes": nodes}
+
+    def search(self, records, sims, **kw):
+        """Complete batched search on the device network / synthetic network: returns read_roots() + counters."""
+        self.search_begin(records, sims, **kw)
+        max_sims = int(np.max(sims))
+        self.search_run(max_sims + 1)
+        st = self.search_status()
+        if st["errors"]:
+            raise RuntimeError("search: node or position pool exhausted (raise max_nodes / max_positions)")
+        if st["unfinished"]:
+            raise RuntimeError("search did not finish")
+        out = self.search_read_roots()
+        out.update(st)
+        return out

@@ -1,0 +1,132 @@
+/* chessbot_b200 — C ABI of the B200-native self-play hot path.
+ *
+ * The reference (tomaz-piko/ChessBot) has no FFI layer: its boundary is the Python module surface of
+ * main/mcts.py, model.py, gameimage.py, actionspace.py, game.py.  The Python modules
+ * in chessbot_b200/ keep those names and signatures and bind exactly the entry points below through
+ * ctypes; each declaration cites the reference interface it replaces.
+ *
+ * Conventions: plain pointers and sizes only; device buffers are caller-owned (PyTorch allocates);
+ * every device entry point takes the CUDA stream as a void* (cudaStream_t) and returns 0 on success,
+ * <0 on error with the text available from cb_last_error().  Nothing synchronises the stream unless
+ * its name ends in _sync.  Not thread-safe per context; one context per GPU.
+ */
+#ifndef CHESSBOT_B200_H
+#define CHESSBOT_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CB_NUM_ACTIONS 4672      /* config.py:16 */
+#define CB_PLANES 119            /* config.py:21 with T=8 */
+#define CB_PLANES_PAD 128        /* channel padding of the bf16 NHWC image */
+#define CB_MAX_MOVES 224
+#define CB_POS_BYTES 96          /* one position of a game record (csrc/rules.cuh: struct Pos) */
+
+const char* cb_last_error(void);
+const char* cb_version(void);
+
+/* ---- host rules: the python-chess surface game.py / gameimage.py / puzzles.py call -------------- */
+/* chess.Board(fen) / chess.Board()  (game.py:44; puzzles.py:50).  NULL fen = start position. */
+typedef struct cb_board cb_board;
+cb_board* cb_board_new(const char* fen);
+void cb_board_free(cb_board* b);
+cb_board* cb_board_copy(const cb_board* b);                 /* Board.copy(), keeps the stack (game.py:137) */
+int cb_board_push_uci(cb_board* b, const char* uci);        /* Board.push_uci (game.py:101); -1 if illegal */
+int cb_board_pop(cb_board* b);                              /* Board.pop (gameimage.py:178); -1 if empty */
+int cb_board_ply(const cb_board* b);                        /* len(board.move_stack) (game.py:25) */
+int cb_board_turn(const cb_board* b);                       /* board.turn: 1 white, 0 black (game.py:145) */
+int cb_board_halfmove_clock(const cb_board* b);             /* gameimage.py:146 */
+int cb_board_castling(const cb_board* b);                   /* cleaned rights: bit0 WK, 1 WQ, 2 BK, 3 BQ (gameimage.py:121-127) */
+int cb_board_ep_square(const cb_board* b);                  /* raw ep square or -1 */
+uint64_t cb_board_pieces_mask(const cb_board* b, int piece_type /*1..6*/, int color); /* board.pieces (gameimage.py:51,54) */
+int cb_board_legal_moves(const cb_board* b, uint16_t* moves /*[CB_MAX_MOVES]*/);      /* ordered like python-chess (game.py:85) */
+int cb_board_move_stack(const cb_board* b, uint16_t* moves, int cap);                 /* game.py:16 */
+int cb_board_outcome(const cb_board* b, int claim_draw);    /* board.outcome(claim_draw=) (game.py:57-58): cb::Outcome code */
+int cb_board_is_repetition(const cb_board* b, int count);   /* gameimage.py:73 */
+int cb_board_is_check(const cb_board* b);
+int cb_board_fen(const cb_board* b, char* out, int cap);
+int cb_board_mirror(cb_board* b);                           /* Board.apply_mirror (gameimage.py:39) */
+uint64_t cb_board_perft(const cb_board* b, int depth);
+/* Game record for the device: the last `n` positions (oldest first), enough for T=8 frames and for
+ * repetition counting back to the last irreversible move.  Returns n, or the required n if cap is too small. */
+int cb_board_export_record(const cb_board* b, void* pos_out /*[cap][CB_POS_BYTES]*/, int cap);
+/* actionspace.uci_to_action (actionspace.py:116-180): index 0..4671, -1 where the reference returns None */
+int cb_uci_to_action(const char* uci, int player_white);
+int cb_move_to_action(uint16_t move, int player_white);
+int cb_move_to_uci(uint16_t move, char out[6]);
+
+/* ---- device context --------------------------------------------------------------------------- */
+typedef struct cb_ctx cb_ctx;
+cb_ctx* cb_ctx_create(int device);                 /* one per GPU / process; NULL + cb_last_error() on failure */
+void cb_ctx_destroy(cb_ctx* ctx);
+int cb_ctx_sm_count(const cb_ctx* ctx);
+/* exp() used for priors (mcts.py:94): f32 table indexed by the bf16 bit pattern of the logit.  The Python
+ * host fills it with np.exp so priors are bit-identical to NumPy on that host; default = expf. */
+int cb_set_exp_table(cb_ctx* ctx, const float* table_host /*[65536]*/);
+
+/* ---- gameimage.board_to_image, batched (gameimage.py:149-192) ----------------------------------- */
+/* pos_dev: game-record positions; frame_idx_dev[n][8]: indices of the frames, newest first, -1 = absent.
+ * planes_act_dev: bf16 planes in the convolution's tile-native layout (cb_planes_act_bytes(n) bytes, must
+ * have been zeroed once: the border cells are never written); planes_i16_dev: the reference's own
+ * int16 [n][8][8][119] image.  Either output may be NULL. */
+size_t cb_planes_act_bytes(int n);
+int cb_encode(cb_ctx* ctx, const void* pos_dev, const int32_t* frame_idx_dev, int n, void* planes_act_dev,
+              int16_t* planes_i16_dev, void* stream);
+
+/* ---- model.py: generate_model / predict_fn forward graph (model.py:19-56,73-80) ------------------- */
+int cb_net_create(cb_ctx* ctx, int filters, int blocks, int max_batch, float leaky_slope, float bn_eps);
+/* Keras-layout float32 tensors by name: "stem.w" [3,3,119,C] HWIO, "stem.bn" [4,C] (gamma,beta,mean,var),
+ * "res{i}.w1|w2" [3,3,C,C], "res{i}.bn1|bn2" [4,C], "value.conv" [C,1], "value.bn" [4,1], "value.fc1" [64,C],
+ * "value.fc2" [C,1], "policy.conv" [C,2], "policy.bn" [4,2], "policy.fc" [128,4672]. */
+int cb_net_set_tensor(cb_ctx* ctx, const char* name, const float* host, size_t count);
+int cb_net_finalize(cb_ctx* ctx);                  /* fold BN, pack bf16 weights, upload */
+/* planes (tile-native bf16) -> value f32[n] and policy logits [n][4672] (bf16 and/or f32, either may be NULL) */
+int cb_net_forward(cb_ctx* ctx, const void* planes_act_dev, int n, float* value_dev, void* logits_bf16_dev,
+                   float* logits_f32_dev, void* stream);
+/* the reference's mock-network contract (tests/mcts_v2.py:51-67) as a device kernel: hash of the int16 planes */
+int cb_synth_forward(cb_ctx* ctx, const int16_t* planes_i16_dev, int n, uint32_t seed, float* value_dev,
+                     void* logits_bf16_dev, void* stream);
+
+/* ---- mcts.expand's gather + exp + normalise, batched (mcts.py:91-101; actionspace.py:116-180) ------- */
+/* per position i: ordered legal moves of pos_dev[cur_idx_dev[i]], their action indices and priors.
+ * outputs are [n][CB_MAX_MOVES] (moves uint16: from | to<<6 | promo<<12) and out_n[n]. */
+int cb_policy_softmax(cb_ctx* ctx, const void* pos_dev, const int32_t* cur_idx_dev, int n, const void* logits_bf16_dev,
+                      uint16_t* out_moves_dev, int16_t* out_actions_dev, float* out_priors_dev, int32_t* out_n_dev,
+                      void* stream);
+
+/* ---- mcts.run_mcts over many concurrent trees (mcts.py:38-161) ---------------------------------- */
+#define CB_EVAL_NET 0        /* the network loaded with cb_net_* */
+#define CB_EVAL_SYNTH 1      /* synthetic hash network */
+#define CB_EVAL_EXTERNAL 2   /* host callable: cb_search_pending_planes / cb_search_step_external */
+int cb_search_create(cb_ctx* ctx, int max_trees, int max_nodes, int max_positions, int max_sims);
+/* roots: concatenated game records (cb_board_export_record), rec_len[n_trees] positions each (host memory).
+ * sims[n], cpuct[n] (<0 = AlphaZero schedule, mcts.py:135-139), noise: NULL or [n][CB_MAX_MOVES] Gamma(0.3,1)
+ * samples per tree (mcts.py:158), has_noise[n] flags; max_game_length: config.py:33. */
+int cb_search_begin(cb_ctx* ctx, int n_trees, const void* records_host, const int32_t* rec_len, const int32_t* sims,
+                    const double* cpuct, const uint8_t* has_noise, const double* noise, int max_game_length, int eval_mode,
+                    uint32_t synth_seed, void* stream);
+/* one batch step: encode pending leaves, evaluate them, expand + backup, select the next leaves */
+int cb_search_step(cb_ctx* ctx, void* stream);
+int cb_search_run(cb_ctx* ctx, int steps, void* stream);     /* `steps` x cb_search_step, no host sync */
+/* external evaluation: int16 planes of the pending leaf of every tree -> host; then values + exp(logits) back */
+int cb_search_pending_planes_sync(cb_ctx* ctx, int16_t* planes_host /*[n_trees][8][8][119]*/, uint8_t* waiting_host /*[n_trees]*/, void* stream);
+int cb_search_step_external(cb_ctx* ctx, const float* value_host /*[n_trees]*/, const float* expvals_host /*[n_trees][4672]*/, void* stream);
+/* counters[4]: trees not finished, evaluations, simulations, errors (node/position pool exhausted) */
+int cb_search_status_sync(cb_ctx* ctx, int64_t* counters, void* stream);
+/* root statistics of every tree: [n_trees][CB_MAX_MOVES] arrays + n_children[n_trees], root_n[n_trees], nodes[n_trees] (host) */
+int cb_search_read_roots_sync(cb_ctx* ctx, uint16_t* moves, int32_t* n, float* w, float* q, double* p, int32_t* n_children,
+                              int32_t* root_n, int32_t* tree_nodes, void* stream);
+
+/* ---- test hooks (not on the product path) ------------------------------------------------------- */
+/* one 3x3 conv + BN + (skip) + LeakyReLU layer of the loaded net on tile-native buffers: layer 0 = stem,
+ * 2i+1 / 2i+2 = first / second conv of block i.  use_reference = plain CUDA-core kernel on the same inputs. */
+int cb_debug_conv_layer(cb_ctx* ctx, int layer, const void* in_act_dev, const void* skip_act_dev, void* out_act_dev,
+                        int n_boards, int use_reference, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

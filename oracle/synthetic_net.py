@@ -5,7 +5,7 @@ The reference's tests drive the search with a mock `network(image) -> {"value_he
 same fake backend as a kernel (`cb_synth_forward`): outputs are an integer hash of the input planes,
 so that tree parity can be checked bit for bit without the convolution tower in the loop.
 
-  h      = sum_i bf16_to_int(plane[i]) * ((i * 2654435761 + 0x9E3779B9) mod 2^32)   (mod 2^32),
+  h      = sum_i plane[i] * ((i * 2654435761 + 0x9E3779B9) mod 2^32)                 (mod 2^32),
            i = (row*8 + col)*119 + channel  (NHWC order, 119 real channels)
   value  = (((mix(h ^ seed) >> 8) & 0xFFFF) - 32768) / 32768                        (exact f32)
   logit_a= (((mix(h ^ seed ^ ((a+1) * 0x9E3779B1)) >> 16) & 0xFF) - 128) / 32       (exact bf16)
@@ -15,14 +15,6 @@ import numpy as np
 
 _COEF = ((np.arange(8 * 8 * 119, dtype=np.uint64) * 2654435761 + 0x9E3779B9) & 0xFFFFFFFF).astype(np.uint64)
 _A = ((np.arange(1, 4673, dtype=np.uint64) * 0x9E3779B1) & 0xFFFFFFFF).astype(np.uint32)
-
-
-def bf16_round_int(x):
-    """int planes as the device sees them: rounded to bf16 (exact up to 256)."""
-    f = np.asarray(x, dtype=np.float32)
-    u = f.view(np.uint32).astype(np.uint64)
-    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
-    return u.astype(np.uint32).view(np.float32).astype(np.int64)
 
 
 def fmix32(x):
@@ -36,7 +28,7 @@ def fmix32(x):
 
 
 def plane_hash(image):
-    v = bf16_round_int(np.asarray(image).reshape(-1)).astype(np.uint64)
+    v = np.asarray(image).reshape(-1).astype(np.int64).astype(np.uint64)
     return np.uint32(int((v * _COEF).sum() & 0xFFFFFFFF))
 
 

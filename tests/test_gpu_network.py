@@ -1,0 +1,100 @@
+"""K2/K3/K4 parity (-m gpu): tcgen05 convolution tower and heads through the C ABI.
+
+1. each conv layer against the plain CUDA-core kernel on the same bf16 inputs (tight: same inputs,
+   fp32 accumulation in a different order, one bf16 rounding);
+2. whole forward pass against the torch-fp32 oracle (oracle/ref_model.py) on real encoded positions.
+   north_star tolerance: policy logits and value within 2e-2 abs (bf16 vs fp32)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-2  # BASELINE.json north_star: "policy logits and values within 2e-2 abs (bf16 vs fp32)"
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from chessbot_b200.engine import Engine
+    return Engine.get()
+
+
+@pytest.mark.parametrize("filters,boards", [(64, 6), (128, 7), (256, 4), (256, 1300), (48, 10)])
+def test_conv_layers_against_cuda_core_kernel(engine, filters, boards):
+    from chessbot_b200.engine import act_to_nhwc, nhwc_to_act
+    from oracle import ref_model
+    w = ref_model.init_weights(filters, 1, seed=filters, random_bn=True)
+    engine.load_network(w, filters, 1, max_batch=boards)
+    cpad = (filters + 63) // 64 * 64
+    g = torch.Generator(device="cuda").manual_seed(boards)
+    x0 = torch.randn(boards, 8, 8, 128, device="cuda", generator=g)
+    x0[..., 121:] = 0
+    xc = torch.randn(boards, 8, 8, cpad, device="cuda", generator=g)
+    xc[..., filters:] = 0
+    for layer, inp, skip in ((0, x0, None), (1, xc, None), (2, xc, xc.flip(0))):
+        a_in = nhwc_to_act(inp)
+        a_skip = nhwc_to_act(skip) if skip is not None else None
+        out_t = engine.debug_conv_layer(layer, a_in, a_skip, boards, cpad, use_reference=False)
+        out_r = engine.debug_conv_layer(layer, a_in, a_skip, boards, cpad, use_reference=True)
+        torch.cuda.synchronize()
+        yt = act_to_nhwc(out_t, boards, cpad).float()
+        yr = act_to_nhwc(out_r, boards, cpad).float()
+        assert torch.isfinite(yt).all()
+        err = (yt - yr).abs()
+        tol = 0.01 * yr.abs() + 1e-2   # one bf16 ulp of slack around the rounding boundary
+        assert (err <= tol).all(), (layer, float(err.max()), float(yr.abs().max()))
+        assert float(yr.abs().mean()) > 1e-3
+        # the zero border of the tile-native buffer must stay zero
+        full = out_t.view(-1, cpad // 8, 10, 2, 10, 8)
+        assert not full[:, :, 0].any() and not full[:, :, 9].any() and not full[:, :, :, :, 0].any() and not full[:, :, :, :, 9].any()
+        if filters < cpad:
+            assert not yt[..., filters:].any()
+
+
+def _positions(n, seed):
+    from gpu_util import device_board, oracle_board, random_games
+    from oracle import ref_gameimage
+    games = random_games(n, seed=seed, max_plies=120)
+    boards = [device_board(f, m) for f, m in games]
+    images = np.stack([ref_gameimage.board_to_image(oracle_board(f, m), 8) for f, m in games])
+    return boards, images
+
+
+@pytest.mark.parametrize("filters,blocks,n", [(48, 4, 33), (128, 6, 64), (256, 20, 16)])
+def test_forward_against_torch_fp32_oracle(engine, filters, blocks, n):
+    from oracle import ref_model
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    w = ref_model.init_weights(filters, blocks, seed=3)
+    engine.load_network(w, filters, blocks, max_batch=n)
+    boards, images = _positions(n, seed=filters)
+    pos, fi = engine.upload_records([b.export_record() for b in boards])
+    act, _ = engine.encode(pos, fi)
+    value, lb, lf = engine.forward(act, n, want_bf16=True, want_f32=True)
+    torch.cuda.synchronize()
+    v_ref, p_ref = ref_model.forward(w, images, device="cuda")
+    v, p32, p16 = value.cpu().numpy(), lf.cpu().numpy(), lb.float().cpu().numpy()
+    err_p = np.abs(p32 - p_ref).max()
+    err_v = np.abs(v - v_ref).max()
+    print(f"\n{blocks}x{filters}: max|dlogit|={err_p:.4g} (|logit| max {np.abs(p_ref).max():.3g}), max|dvalue|={err_v:.4g}")
+    assert err_p <= TOL and err_v <= TOL
+    # the bf16 logits handed to the search are the f32 logits rounded once
+    assert np.array_equal(p16, torch.from_numpy(p32).to(torch.bfloat16).float().numpy())
+    # argmax agreement of the policy
+    assert (p32.argmax(1) == p_ref.argmax(1)).mean() > 0.9
+
+
+def test_forward_is_batch_invariant(engine):
+    # the search relies on a position's outputs not depending on its batch slot
+    from oracle import ref_model
+    w = ref_model.init_weights(64, 2, seed=5)
+    engine.load_network(w, 64, 2, max_batch=40)
+    boards, _ = _positions(40, seed=9)
+    recs = [b.export_record() for b in boards]
+    pos, fi = engine.upload_records(recs)
+    act, _ = engine.encode(pos, fi)
+    v_all, lb_all, _ = engine.forward(act, 40)
+    pos1, fi1 = engine.upload_records(recs[17:18])
+    act1, _ = engine.encode(pos1, fi1)
+    v1, lb1, _ = engine.forward(act1, 1)
+    torch.cuda.synchronize()
+    assert torch.equal(v_all[17:18], v1) and torch.equal(lb_all[17:18], lb1)

@@ -1,0 +1,177 @@
+"""K5-K8 parity (-m gpu): legal-move gather/softmax and the batched device search through the C ABI.
+
+Bars (BASELINE.json north_star): legal-move indices and visit counts bit-exact given identical network
+outputs and seeded noise.  Float semantics = the reference under NumPy 2 with a float32 network
+(oracle/ref_mcts.py header): f32 priors / W / Q / ucb, f64 at a noisy root."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from chessbot_b200.engine import Engine
+    e = Engine.get()
+    e.search_create(max_trees=64, max_nodes=4_000_000, max_positions=400_000, max_sims=800)
+    return e
+
+
+def test_policy_softmax_matches_oracle(engine):
+    from gpu_util import device_board, oracle_board, random_games
+    from chessbot_b200.board import code_to_uci
+    from oracle import ref_actionspace, ref_gameimage, synthetic_net
+    games = random_games(96, seed=5, max_plies=100)
+    boards = [device_board(f, m) for f, m in games]
+    pos, fi = engine.upload_records([b.export_record() for b in boards])
+    _, i16 = engine.encode(pos, fi, want_act=False, want_i16=True)
+    value, lb = engine.synth_forward(i16, seed=77)
+    moves, actions, priors, counts = engine.policy_softmax(pos, fi[:, 0].contiguous(), lb)
+    torch.cuda.synchronize()
+    moves, actions, priors, counts = (t.cpu().numpy() for t in (moves, actions, priors, counts))
+    for i, (f, m) in enumerate(games):
+        ob = oracle_board(f, m)
+        v_ref, logits_ref = synthetic_net.outputs(ref_gameimage.board_to_image(ob, 8), seed=77)
+        assert np.float32(value[i].item()) == v_ref
+        assert np.array_equal(lb[i].float().cpu().numpy(), logits_ref)
+        legal = [mv.uci() for mv in ob.legal_moves]
+        k = counts[i]
+        assert [code_to_uci(c) for c in moves[i, :k].astype(np.uint16)] == legal          # order too
+        acts = [ref_actionspace.uci_to_action(u, ob.turn) for u in legal]
+        assert list(actions[i, :k]) == acts
+        p = np.exp(logits_ref[acts], dtype=np.float32)
+        ref = p / np.sum(p, dtype=np.float32)
+        assert np.array_equal(priors[i, :k], ref)
+
+
+class _FixedRng:
+    def __init__(self, noise):
+        self.noise = noise
+
+    def gamma(self, a, b, n):
+        return self.noise[:n]
+
+    def choice(self, x):
+        return x[0]
+
+    def multinomial(self, n, pi):
+        o = np.zeros(len(pi), dtype=int)
+        o[int(np.argmax(pi))] = 1
+        return o
+
+
+def _compare_tree(out, i, tree, root_moves=None):
+    from chessbot_b200.board import code_to_uci
+    kids = list(tree.children(0))
+    k = out["n_children"][i]
+    assert k == len(kids)
+    assert [code_to_uci(c) for c in out["moves"][i, :k]] == [tree.move[c] for c in kids]
+    assert list(out["N"][i, :k]) == [tree.N[c] for c in kids]
+    assert np.array_equal(out["W"][i, :k], np.array([tree.W[c] for c in kids], dtype=np.float32))
+    assert np.array_equal(out["Q"][i, :k], np.array([tree.Q[c] for c in kids], dtype=np.float32))
+    assert np.array_equal(out["P"][i, :k], np.array([np.float64(tree.P[c]) for c in kids]))
+    assert out["root_N"][i] == tree.N[0] and out["nodes"][i] == len(tree.parent)
+
+
+def test_reference_golden_searches_bit_exact(engine, golden_dir):
+    """The eight searches recorded from the reference's own mcts.py (tests/golden/mcts.npz), all run
+    CONCURRENTLY as one device batch with per-tree sims / cpuct / noise."""
+    from gpu_util import device_board
+    from chessbot_b200.board import code_to_uci
+    from chessbot_b200.engine import EVAL_SYNTH
+    g = np.load(os.path.join(golden_dir, "mcts.npz"))
+    cases = json.loads(str(g["cases"]))
+    seeds = {c[5] for c in cases}
+    for seed in seeds:   # the synthetic network seed is per launch
+        idx = [i for i, c in enumerate(cases) if c[5] == seed]
+        recs = [device_board(cases[i][0], cases[i][1]).export_record() for i in idx]
+        noise = [np.random.default_rng(cases[i][5]).gamma(0.3, 1, 256) if cases[i][3] else None for i in idx]
+        out = engine.search(recs, [cases[i][2] for i in idx], cpuct=[cases[i][4] for i in idx], noise=noise,
+                            eval_mode=EVAL_SYNTH, seed=seed)
+        for j, i in enumerate(idx):
+            k = out["n_children"][j]
+            assert [code_to_uci(c) for c in out["moves"][j, :k]] == list(g[f"c{i}_moves"])
+            assert list(out["N"][j, :k]) == list(g[f"c{i}_N"]), i
+            assert np.array_equal(out["W"][j, :k].astype(np.float64), g[f"c{i}_W"]), i
+            assert np.array_equal(out["Q"][j, :k].astype(np.float64), g[f"c{i}_Q"]), i
+            assert np.array_equal(out["P"][j, :k], g[f"c{i}_P"]), i
+            assert out["root_N"][j] == int(g[f"c{i}_rootN"]) and out["nodes"][j] == int(g[f"c{i}_nodes"])
+
+
+def test_batched_synthetic_search_matches_oracle(engine):
+    """48 concurrent trees on random mid-game positions (repetitions, checks, promotions in the trees)."""
+    from gpu_util import device_board, oracle_board, random_games
+    from chessbot_b200.engine import EVAL_SYNTH
+    from oracle import ref_mcts, synthetic_net
+    from oracle.ref_game import Game, OracleConfig
+    games = random_games(48, seed=21, max_plies=140, back_bias=0.35)
+    recs = [device_board(f, m).export_record() for f, m in games]
+    sims = [40 + 7 * (i % 9) for i in range(48)]
+    noise = [np.random.default_rng(100 + i).gamma(0.3, 1, 256) if i % 2 == 0 else None for i in range(48)]
+    cpuct = [None if i % 3 else 1.0 for i in range(48)]
+    out = engine.search(recs, sims, cpuct=cpuct, noise=noise, eval_mode=EVAL_SYNTH, seed=9)
+    for i, (f, m) in enumerate(games):
+        game = Game(OracleConfig(), board=oracle_board(f, m))
+        _, tree = ref_mcts.run_mcts(game, synthetic_net.as_network(9), sims[i], 30, noise[i] is not None, cpuct[i],
+                                    rng=_FixedRng(noise[i]), noise=noise[i])
+        _compare_tree(out, i, tree)
+    assert out["sims"] == sum(sims)
+
+
+def test_device_network_search_matches_oracle_on_same_outputs(engine):
+    """Search with the tcgen05 network in the loop.  The oracle gets the SAME network outputs (the
+    device forward pass called per position through the C ABI), so visit counts must be identical."""
+    from gpu_util import device_board, oracle_board, random_games
+    from chessbot_b200.board import Board
+    from chessbot_b200.engine import EVAL_NET
+    from oracle import ref_mcts, ref_model
+    from oracle.ref_game import Game, OracleConfig
+    w = ref_model.init_weights(64, 2, seed=12)
+    engine.load_network(w, 64, 2, max_batch=64)
+    games = random_games(6, seed=33, max_plies=60)
+    recs = [device_board(f, m).export_record() for f, m in games]
+    sims = 60
+    noise = [np.random.default_rng(i).gamma(0.3, 1, 256) for i in range(6)]
+    out = engine.search(recs, sims, noise=noise, eval_mode=EVAL_NET)
+    for i, (f, m) in enumerate(games):
+        ob = oracle_board(f, m)
+        game = Game(OracleConfig(), board=ob)
+
+        class DeviceNet:
+            """network(image) evaluated by the device forward on the oracle's own game record"""
+            def __init__(self, g):
+                self.g = g
+
+        def run_with_device_outputs():
+            # the oracle asks for image -> outputs; feed it the device's outputs for the same position
+            cache = {}
+
+            def expand_hook(tree, node, g, network, exp_fn=ref_mcts.default_exp):
+                db = Board(str(f))
+                for u in [mv.uci() for mv in g.board.move_stack]:
+                    db.push_uci(u)
+                pos, fi = engine.upload_records([db.export_record()])
+                act, _ = engine.encode(pos, fi)
+                v, lb, _ = engine.forward(act, 1)
+                torch.cuda.synchronize()
+                value = np.float32(v.cpu().numpy()[0])
+                logits = lb.float().cpu().numpy()[0]
+                moves, actions = ref_mcts.legal_actions(g)
+                p = exp_fn(logits[np.asarray(actions, dtype=np.int64)])
+                s = np.sum(p, dtype=np.float32)
+                tree.add_children(node, moves, [np.float32(x / s) for x in p])
+                return value
+
+            orig = ref_mcts.expand
+            ref_mcts.expand = expand_hook
+            try:
+                return ref_mcts.run_mcts(game, None, sims, 30, True, None, rng=_FixedRng(noise[i]), noise=noise[i])
+            finally:
+                ref_mcts.expand = orig
+
+        _, tree = run_with_device_outputs()
+        _compare_tree(out, i, tree)
