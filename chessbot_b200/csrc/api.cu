@@ -57,7 +57,7 @@ struct DevBuf {
 struct ConvLayer {
     DevBuf<__nv_bfloat16> w;
     DevBuf<float> scale, shift;
-    int kc = 0, cj_in = 0;
+    int kc = 0, kc_in = 0, cj_in = 0;
 };
 
 struct Net {
@@ -162,7 +162,11 @@ int cb_net_set_tensor(cb_ctx* ctx, const char* name, const float* host, size_t c
 static int pack_conv(Net& net, ConvLayer& L, const std::vector<float>& w, int cin, int cin_pad, const std::vector<float>& bn, bool stem) {
     const int C = net.filters, N = net.cpad;
     if (w.size() != (size_t)9 * cin * C || bn.size() != (size_t)4 * C) { cb_set_error("conv tensor has wrong size"); return -1; }
-    L.kc = cin_pad / 64;
+    // The stem sees raw integer planes (move count, halfmove clock up to the hundreds): its weights are
+    // split into bf16 hi + lo halves (two K passes over the same planes) so they act at ~16-bit precision.
+    const int halves = stem ? 2 : 1;
+    L.kc_in = cin_pad / 64;
+    L.kc = L.kc_in * halves;
     L.cj_in = cin_pad / 8;
     std::vector<__nv_bfloat16> packed((size_t)L.kc * 9 * N * 64, __float2bfloat16(0.f));
     for (int tap = 0; tap < 9; ++tap)
@@ -173,10 +177,16 @@ static int pack_conv(Net& net, ConvLayer& L, const std::vector<float>& w, int ci
                 else if (ci == 120) src_ci = 118;
                 else if (ci > 120) continue;
             } else if (ci >= cin) continue;
-            const int kc = ci >> 6, k = ci & 63;
-            for (int co = 0; co < C; ++co)
-                packed[((size_t)(kc * 9 + tap) * N * 64) + ((size_t)(k >> 3) * N + co) * 8 + (k & 7)] =
-                    __float2bfloat16(w[((size_t)tap * cin + src_ci) * C + co]);
+            const int k = ci & 63;
+            for (int co = 0; co < C; ++co) {
+                const float wf = w[((size_t)tap * cin + src_ci) * C + co];
+                const __nv_bfloat16 hi = __float2bfloat16(wf);
+                for (int h = 0; h < halves; ++h) {
+                    const int kc = (ci >> 6) + h * L.kc_in;
+                    packed[((size_t)(kc * 9 + tap) * N * 64) + ((size_t)(k >> 3) * N + co) * 8 + (k & 7)] =
+                        h == 0 ? hi : __float2bfloat16(wf - __bfloat162float(hi));
+                }
+            }
         }
     std::vector<float> scale(N, 0.f), shift(N, 0.f);
     for (int c = 0; c < C; ++c) {
@@ -264,7 +274,7 @@ static int net_tower(cb_ctx* ctx, const void* planes_act_dev, int n, float* valu
         ConvLayer& L = net.layers[l];
         ConvParams p{};
         p.wgt = L.w.p; p.scale = L.scale.p; p.shift = L.shift.p;
-        p.pairs = pairs; p.kc = L.kc; p.cj_in = L.cj_in; p.n = net.cpad; p.slope = net.slope;
+        p.pairs = pairs; p.kc = L.kc; p.kc_in = L.kc_in; p.cj_in = L.cj_in; p.n = net.cpad; p.slope = net.slope;
         int out_i;
         if (l == 0) { p.in = in; out_i = 0; p.skip = nullptr; }
         else if (l & 1) { p.in = net.act[cur].p; out_i = (cur + 1) % 3; p.skip = nullptr; }       // first conv of a block
@@ -306,7 +316,7 @@ int cb_debug_conv_layer(cb_ctx* ctx, int layer, const void* in_act_dev, const vo
     ConvParams p{};
     p.in = (const __nv_bfloat16*)in_act_dev; p.out = (__nv_bfloat16*)out_act_dev; p.skip = (const __nv_bfloat16*)skip_act_dev;
     p.wgt = L.w.p; p.scale = L.scale.p; p.shift = L.shift.p;
-    p.pairs = (n_boards + 1) / 2; p.kc = L.kc; p.cj_in = L.cj_in; p.n = net.cpad; p.slope = net.slope;
+    p.pairs = (n_boards + 1) / 2; p.kc = L.kc; p.kc_in = L.kc_in; p.cj_in = L.cj_in; p.n = net.cpad; p.slope = net.slope;
     return use_reference ? launch_conv3x3_reference(p, (cudaStream_t)stream) : launch_conv3x3(p, ctx->sms, (cudaStream_t)stream);
 }
 

@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tcgen05_kernel(ConvPa
                     ptx::mbar_expect_tx(&s->a_full[as], (uint32_t)ntiles * ACT_K64_BYTES);
                     for (int t = 0; t < ntiles; ++t) {
                         const uint8_t* src = reinterpret_cast<const uint8_t*>(p.in) +
-                                             ((size_t)(2 * u + t) * p.cj_in + 8 * kc) * ACT_CHUNK_BYTES;
+                                             ((size_t)(2 * u + t) * p.cj_in + 8 * (kc % p.kc_in)) * ACT_CHUNK_BYTES;
                         ptx::bulk_g2s(a_buf + as * A_SLOT_BYTES + t * ACT_K64_BYTES, src, ACT_K64_BYTES, &s->a_full[as]);
                     }
                     ++a_it;
@@ -226,8 +226,9 @@ __global__ void conv3x3_reference_kernel(ConvParams p) {
             const int dy = tap / 3 - 1, dx = tap % 3 - 1;
             const int cell = act_cell(row + dy, bip, col + dx);  // border cells are zero
             for (int ci = 0; ci < p.kc * 64; ++ci) {
+                const int cin = ci % (p.kc_in * 64);
                 const __nv_bfloat16 a = *reinterpret_cast<const __nv_bfloat16*>(
-                    reinterpret_cast<const uint8_t*>(p.in) + act_offset_bytes(pair, p.cj_in, ci >> 3, cell) + (ci & 7) * 2);
+                    reinterpret_cast<const uint8_t*>(p.in) + act_offset_bytes(pair, p.cj_in, cin >> 3, cell) + (cin & 7) * 2);
                 const int kc = ci >> 6, k = ci & 63;
                 const __nv_bfloat16 w = p.wgt[((size_t)(kc * 9 + tap) * p.n * 64) + ((size_t)(k >> 3) * p.n + co) * 8 + (k & 7)];
                 acc = fmaf(__bfloat162float(a), __bfloat162float(w), acc);
@@ -247,7 +248,7 @@ int launch_conv3x3(const ConvParams& p, int num_sms, cudaStream_t stream) {
         CB_CUDA_OK(cudaFuncSetAttribute(conv3x3_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV_SMEM_BYTES));
         attr_set = true;
     }
-    if (p.n % 64 != 0 || p.n > 256 || p.n < 64 || p.kc < 1 || p.pairs < 1) {
+    if (p.n % 64 != 0 || p.n > 256 || p.n < 64 || p.kc < 1 || p.kc_in < 1 || p.pairs < 1) {
         cb_set_error("conv3x3: unsupported shape");
         return -1;
     }

@@ -16,7 +16,8 @@ struct ConvParams {
     const float* head_w;        // [3][n] 1x1 head conv weights (value, policy0, policy1) or nullptr
     float* head_out;            // [boards][64][3]
     int pairs;                  // board pairs in the batch
-    int kc;                     // input channel chunks of 64
+    int kc;                     // K chunks of 64 (weight blocks)
+    int kc_in;                  // distinct input chunks: A chunk of K chunk k is k % kc_in (stem: hi/lo weight halves re-read the planes)
     int cj_in;                  // input channels / 8
     int n;                      // output channels (multiple of 64, <= 256)
     float slope;                // LeakyReLU negative slope (Keras default 0.3)

@@ -94,6 +94,36 @@ def forward(w, images, device="cpu", return_tower=False):
         return v.cpu().numpy(), logits.cpu().numpy()
 
 
+def calibrate_bn(w, images, device="cpu"):
+    """Returns a copy of `w` whose BatchNorm moving statistics are the batch statistics of `images`,
+    layer by layer (what training converges to): activations and logits become O(1), the regime the
+    2e-2 absolute tolerance of BASELINE.json's north_star is stated for.  Keras random-init BN
+    (mean 0, var 1) leaves the raw integer planes un-normalised and logits in the tens."""
+    w = {k: np.array(v, copy=True) for k, v in w.items()}
+
+    def fit(y, key):
+        c = y.shape[1]
+        m = y.mean(dim=(0, 2, 3)).cpu().numpy()
+        v = y.var(dim=(0, 2, 3), unbiased=False).cpu().numpy()
+        w[key] = np.stack([np.ones(c), np.zeros(c), m, np.maximum(v, 1e-6)]).astype(np.float32)
+
+    with torch.no_grad():
+        x = torch.as_tensor(np.asarray(images, dtype=np.float32)).to(device).permute(0, 3, 1, 2).contiguous()
+        y = _conv(x, w["stem.w"], device)
+        fit(y, "stem.bn")
+        x = F.leaky_relu(_bn(y, w["stem.bn"], device), SLOPE)
+        for i in range(num_blocks(w)):
+            y = _conv(x, w[f"res{i}.w1"], device)
+            fit(y, f"res{i}.bn1")
+            y = F.leaky_relu(_bn(y, w[f"res{i}.bn1"], device), SLOPE)
+            y = _conv(y, w[f"res{i}.w2"], device)
+            fit(y, f"res{i}.bn2")
+            x = F.leaky_relu(x + _bn(y, w[f"res{i}.bn2"], device), SLOPE)
+        fit(_conv(x, w["value.conv"], device), "value.bn")
+        fit(_conv(x, w["policy.conv"], device), "policy.bn")
+    return w
+
+
 def as_network(w, device="cpu"):
     """The reference's `network` contract (model.py:77-79): callable(f32[1,8,8,119]) -> dict."""
     def net(image):

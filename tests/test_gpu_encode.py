@@ -59,37 +59,27 @@ def test_random_playouts_against_oracle(engine):
 
 def test_long_game_move_count_beyond_bf16(engine):
     # move count > 256 is not representable in bf16: the remainder channel must make it exact
-    from gpu_util import device_board, oracle_board
+    import random
+    from gpu_util import device_board
+    from oracle import pychess_shim as ochess
     from oracle import ref_gameimage
-    shuffle = "g1f3 g8f6 f3g1 f6g8 b1c3 b8c6 c3b1 c6b8".split()
-    adv = ["a2a3", "a7a6", "a3a4", "a6a5", "b2b3", "b7b6", "b3b4", "b6b5", "c2c3", "c7c6", "c3c4", "c6c5", "d2d3", "d7d6",
-           "d3d4", "d6d5", "e2e3", "e7e6", "e3e4", "e6e5", "f2f3", "f7f6", "f3f4", "f6f5", "g2g3", "g7g6", "g3g4", "g6g5",
-           "h2h3", "h7h6", "h3h4", "h6h5"]
-    moves = []
-    k = 0
-    while len(moves) < 330 and k + 1 < len(adv):
-        moves += shuffle[:4] + shuffle[4:] + adv[k:k + 2]   # 8 reversible plies then two pawn moves
-        k += 2
-    ob = oracle_board("rnbqkbnr/pppppppp/8/8/8/8/PPPPPPPP/RNBQKBNR w KQkq - 0 1", "")
-    ok_moves = []
-    for m in moves:
-        if ob.is_game_over(claim_draw=True):
-            break
-        try:
-            ob.push_uci(m)
-        except ValueError:
-            break
-        ok_moves.append(m)
-    if ob.is_game_over(claim_draw=True):
-        ob.pop()
-        ok_moves.pop()
-    assert len(ok_moves) > 256
-    b = device_board("rnbqkbnr/pppppppp/8/8/8/8/PPPPPPPP/RNBQKBNR w KQkq - 0 1", " ".join(ok_moves))
+    rnd = random.Random(5)
+    ob, moves = None, []
+    while len(moves) < 301:
+        ob, moves = ochess.Board(), []
+        while len(moves) < 301 and not ob.is_game_over(claim_draw=False):
+            legal = list(ob.legal_moves)
+            quiet = [m for m in legal if not ob.is_zeroing(m)]
+            m = rnd.choice(quiet if quiet and len(moves) % 40 != 39 else legal)  # a pawn move / capture now and then
+            ob.push(m)
+            moves.append(m.uci())
+    b = device_board(ochess.STARTING_FEN, " ".join(moves))
     i16, planes = _encode(engine, [b])
     ref = ref_gameimage.board_to_image(ob, 8)[None]
-    assert ref[0, 0, 0, 113] == len(ok_moves)
+    assert ref[0, 0, 0, 113] == 301
     assert np.array_equal(i16, ref)
     _check_bf16_planes(planes, ref)
+    assert planes[0, 0, 0, 113] == 300 and planes[0, 0, 0, 119] == 1
 
 
 def test_fen_root_has_single_frame(engine):
