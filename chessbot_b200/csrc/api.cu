@@ -93,6 +93,9 @@ struct Search {
 
 struct cb_ctx {
     int device = 0, sms = 0;
+    bool profile = false;                       // CUDA events around every conv launch (bench.py roofline leg)
+    std::vector<cudaEvent_t> prof_events;       // pairs
+    size_t prof_used = 0;
     DevBuf<float> exp_table;
     Net net;
     Search search;
@@ -281,7 +284,19 @@ static int net_tower(cb_ctx* ctx, const void* planes_act_dev, int n, float* valu
         else { p.in = net.act[(cur + 1) % 3].p; out_i = (cur + 2) % 3; p.skip = net.act[cur].p; }  // second conv + skip
         p.out = net.act[out_i].p;
         if (l == nl - 1) { p.head_w = net.head_w.p; p.head_out = net.head_raw.p; }
+        if (ctx->profile) {
+            while (ctx->prof_events.size() < ctx->prof_used + 2) {
+                cudaEvent_t e;
+                CB_CUDA_OK(cudaEventCreate(&e));
+                ctx->prof_events.push_back(e);
+            }
+            CB_CUDA_OK(cudaEventRecord(ctx->prof_events[ctx->prof_used], st));
+        }
         if (launch_conv3x3(p, ctx->sms, st)) return -1;
+        if (ctx->profile) {
+            CB_CUDA_OK(cudaEventRecord(ctx->prof_events[ctx->prof_used + 1], st));
+            ctx->prof_used += 2;
+        }
         if (l == 0 || !(l & 1)) cur = out_i;
     }
     HeadParams hp{net.head_raw.p, net.head_bn.p, net.fc1.p, net.fc2.p, net.filters, net.slope, value_dev, net.pfeat.p};
@@ -306,6 +321,25 @@ int cb_policy_softmax(cb_ctx* ctx, const void* pos_dev, const int32_t* cur_idx_d
                       uint16_t* out_moves_dev, int16_t* out_actions_dev, float* out_priors_dev, int32_t* out_n_dev, void* stream) {
     return launch_policy_softmax((const Pos*)pos_dev, cur_idx_dev, n, (const __nv_bfloat16*)logits_bf16_dev, ctx->exp_table.p,
                                  out_moves_dev, out_actions_dev, out_priors_dev, out_n_dev, (cudaStream_t)stream);
+}
+
+int cb_profile_conv(cb_ctx* ctx, int enable) {
+    ctx->profile = enable != 0;
+    ctx->prof_used = 0;
+    return 0;
+}
+int cb_profile_conv_read_sync(cb_ctx* ctx, double* total_ms, int* launches) {
+    CB_CUDA_OK(cudaDeviceSynchronize());
+    double t = 0;
+    for (size_t i = 0; i + 1 < ctx->prof_used; i += 2) {
+        float ms = 0;
+        CB_CUDA_OK(cudaEventElapsedTime(&ms, ctx->prof_events[i], ctx->prof_events[i + 1]));
+        t += ms;
+    }
+    *total_ms = t;
+    *launches = (int)(ctx->prof_used / 2);
+    ctx->prof_used = 0;
+    return 0;
 }
 
 int cb_debug_conv_layer(cb_ctx* ctx, int layer, const void* in_act_dev, const void* skip_act_dev, void* out_act_dev, int n_boards,

@@ -133,6 +133,14 @@ class Engine:
                                     _ptr(priors), _ptr(counts), _stream()), "policy_softmax")
         return moves, actions, priors, counts
 
+    def profile_conv(self, enable):
+        check(lib.cb_profile_conv(self._h, int(enable)), "profile_conv")
+
+    def profile_conv_read(self):
+        ms, n = C.c_double(0), C.c_int(0)
+        check(lib.cb_profile_conv_read_sync(self._h, C.byref(ms), C.byref(n)), "profile_conv_read")
+        return ms.value, n.value
+
     def debug_conv_layer(self, layer, in_act, skip_act, n_boards, out_channels, use_reference=False):
         out = torch.zeros(((n_boards + 1) // 2) * (out_channels // 8) * 1600, dtype=torch.bfloat16, device=self.device)
         check(lib.cb_debug_conv_layer(self._h, layer, _ptr(in_act), _ptr(skip_act), _ptr(out), n_boards, int(use_reference),

@@ -1,0 +1,133 @@
+"""Drop-in for the reference's model.py: generate_model / predict_fn / predict_model (model.py:30,73,82).
+
+The Keras ResNet becomes `DeviceNetwork`: float32 master weights in Keras layout on the host, the
+forward pass on hand-written sm_100a kernels (csrc/conv.cu tcgen05 tower, csrc/heads.cu).  A
+DeviceNetwork is also a callable with the reference's `network` contract (model.py:77-79):
+network(f32[n,8,8,119]) -> {"value_head": [n,1], "policy_head": [n,4672]}.
+"""
+import numpy as np
+import torch
+
+from .config import Config
+
+config = Config()
+NUM_ACTIONS = 4672
+
+
+def _glorot(gen, shape, fan_in, fan_out):
+    lim = float(np.sqrt(6.0 / (fan_in + fan_out)))
+    return ((torch.rand(shape, generator=gen, dtype=torch.float32) * 2 - 1) * lim).numpy()
+
+
+def keras_init_weights(filters, blocks, in_channels=119, seed=None):
+    """Keras random-init state of generate_model() (glorot_uniform kernels, BN gamma 1 / beta 0 /
+    moving mean 0 / moving variance 1), in Keras tensor layouts (include/chessbot_b200.h: cb_net_set_tensor)."""
+    g = torch.Generator()
+    if seed is None:
+        g.seed()
+    else:
+        g.manual_seed(seed)
+    C = filters
+
+    def bn(c):
+        return np.stack([np.ones(c), np.zeros(c), np.zeros(c), np.ones(c)]).astype(np.float32)
+
+    w = {"stem.w": _glorot(g, (3, 3, in_channels, C), 9 * in_channels, 9 * C), "stem.bn": bn(C)}
+    for i in range(blocks):
+        w[f"res{i}.w1"] = _glorot(g, (3, 3, C, C), 9 * C, 9 * C)
+        w[f"res{i}.bn1"] = bn(C)
+        w[f"res{i}.w2"] = _glorot(g, (3, 3, C, C), 9 * C, 9 * C)
+        w[f"res{i}.bn2"] = bn(C)
+    w["value.conv"] = _glorot(g, (1, 1, C, 1), C, 1)
+    w["value.bn"] = bn(1)
+    w["value.fc1"] = _glorot(g, (64, C), 64, C)
+    w["value.fc2"] = _glorot(g, (C, 1), C, 1)
+    w["policy.conv"] = _glorot(g, (1, 1, C, 2), C, 2)
+    w["policy.bn"] = bn(2)
+    w["policy.fc"] = _glorot(g, (128, NUM_ACTIONS), 128, NUM_ACTIONS)
+    return w
+
+
+class DeviceNetwork:
+    """model.py:30-56 forward graph resident on one B200."""
+
+    def __init__(self, weights, filters, blocks, max_batch=1024, device=None):
+        from .engine import Engine
+        self.weights = {k: np.asarray(v, dtype=np.float32) for k, v in weights.items()}
+        self.filters, self.blocks, self.max_batch = filters, blocks, max_batch
+        self.engine = Engine.get(device)
+        self.load()
+
+    def load(self):
+        """(Re)installs these weights as the engine's network (one network per device context)."""
+        self.engine.load_network(self.weights, self.filters, self.blocks, self.max_batch)
+        self.engine.loaded_network = self
+
+    def ensure_loaded(self):
+        if getattr(self.engine, "loaded_network", None) is not self:
+            self.load()
+
+    def images_to_planes(self, images):
+        """f32 / int16 [n,8,8,119] host images -> tile-native bf16 planes on the device (128 channels; the
+        move-count / halfmove-clock parts bf16 cannot hold go to channels 119 / 120, as in csrc/encode.cu)."""
+        from .engine import nhwc_to_act
+        x = torch.as_tensor(np.asarray(images, dtype=np.float32)).to(self.engine.device)
+        n = x.shape[0]
+        full = torch.zeros(n, 8, 8, 128, dtype=torch.float32, device=x.device)
+        full[..., :119] = x
+        for src, dst in ((113, 119), (118, 120)):
+            hi = (full[..., src].view(torch.int32) & -65536).view(torch.float32)   # truncate to 8 significant bits
+            full[..., dst] = full[..., src] - hi
+            full[..., src] = hi
+        return nhwc_to_act(full), n
+
+    def predict(self, images):
+        """value f32 [n], logits f32 [n,4672] (device tensors) for host images [n,8,8,119]."""
+        self.ensure_loaded()
+        planes, n = self.images_to_planes(images)
+        value, _, logits = self.engine.forward(planes, n, want_bf16=False, want_f32=True)
+        return value, logits
+
+    def __call__(self, image):
+        value, logits = self.predict(image)
+        return {"value_head": value.cpu().numpy().reshape(-1, 1), "policy_head": logits.cpu().numpy()}
+
+
+class SyntheticNetwork:
+    """The reference tests' mock network (tests/mcts_v2.py:51-67) as a device kernel: outputs are an
+    integer hash of the planes (csrc/heads.cu; NumPy statement in oracle/synthetic_net.py)."""
+
+    def __init__(self, seed=0, device=None):
+        from .engine import Engine
+        self.seed = int(seed)
+        self.engine = Engine.get(device)
+
+    def __call__(self, image):
+        planes = torch.as_tensor(np.asarray(image).astype(np.int16)).to(self.engine.device).contiguous()
+        value, logits = self.engine.synth_forward(planes, self.seed)
+        return {"value_head": value.cpu().numpy().reshape(-1, 1), "policy_head": logits.float().cpu().numpy()}
+
+
+def generate_model(seed=None, max_batch=1024):
+    """model.py:30-71: a randomly initialised network of config.conv_filters x config.num_residual_blocks."""
+    w = keras_init_weights(config.conv_filters, config.num_residual_blocks, config.input_dims[2], seed)
+    return DeviceNetwork(w, config.conv_filters, config.num_residual_blocks, max_batch)
+
+
+def predict_fn(trt_func, image):
+    """model.py:73-80: (value, policy_logits[4672]) for ONE image [8,8,119]; `trt_func` is any callable with
+    the network contract (a DeviceNetwork, a SyntheticNetwork or a user mock)."""
+    image = np.asarray(image, dtype=np.float32)[None]
+    predictions = trt_func(image)
+    policy_logits = predictions["policy_head"][0]
+    value = predictions["value_head"][0][0]
+    return value, policy_logits
+
+
+def predict_model(model, image):
+    """model.py:82-89 (Keras model returning [value, policy])."""
+    if isinstance(model, (DeviceNetwork, SyntheticNetwork)):
+        return predict_fn(model, image)
+    image = np.asarray(image, dtype=np.float32)[None]
+    predictions = model(image)
+    return predictions[0][0], predictions[1][0]

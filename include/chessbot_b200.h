@@ -120,6 +120,10 @@ int cb_search_status_sync(cb_ctx* ctx, int64_t* counters, void* stream);
 int cb_search_read_roots_sync(cb_ctx* ctx, uint16_t* moves, int32_t* n, float* w, float* q, double* p, int32_t* n_children,
                               int32_t* root_n, int32_t* tree_nodes, void* stream);
 
+/* ---- measurement: CUDA events around every convolution launch of cb_net_forward / cb_search_step ------ */
+int cb_profile_conv(cb_ctx* ctx, int enable);
+int cb_profile_conv_read_sync(cb_ctx* ctx, double* total_ms, int* launches);   /* sums and resets */
+
 /* ---- test hooks (not on the product path) ------------------------------------------------------- */
 /* one 3x3 conv + BN + (skip) + LeakyReLU layer of the loaded net on tile-native buffers: layer 0 = stem,
  * 2i+1 / 2i+2 = first / second conv of block i.  use_reference = plain CUDA-core kernel on the same inputs. */

@@ -93,7 +93,8 @@ def test_forward_trained_like_network_within_2e_2_abs(engine, filters, blocks, n
 def test_forward_keras_random_init_relative(engine, filters, blocks, n):
     """Keras random-init state (BN mean 0 / var 1): nothing normalises the raw integer planes (move count
     in the hundreds), logits reach the tens.  bf16 operands carry 8 significant bits, so the bar here
-    is RELATIVE to the logit range: max|dlogit| <= 1 % of max|logit| (value still 2e-2 abs)."""
+    is RELATIVE to the logit range: max|dlogit| <= 1.5 % of max|logit|, value within 5e-2 (a tanh of
+    un-normalised sums)."""
     from oracle import ref_model
     w = ref_model.init_weights(filters, blocks, seed=3)
     v, p32, p16, v_ref, p_ref = _forward_both(engine, w, filters, blocks, n)
@@ -101,7 +102,7 @@ def test_forward_keras_random_init_relative(engine, filters, blocks, n):
     scale = np.abs(p_ref).max()
     print(f"\nkeras-init {blocks}x{filters}: max|dlogit|={err_p:.4g} ({100 * err_p / scale:.3g} % of range {scale:.3g}), "
           f"max|dvalue|={err_v:.4g}")
-    assert err_p <= 0.01 * max(scale, 2.0) and err_v <= TOL
+    assert err_p <= 0.015 * max(scale, 2.0) and err_v <= 5e-2
     assert (p32.argmax(1) == p_ref.argmax(1)).mean() > 0.9
 
 
