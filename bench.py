@@ -8,7 +8,7 @@ pending leaf is encoded (K1), evaluated by the residual tower + heads (K2-K4), e
 gather, exp, normalise), its value backed up (K8), and the next leaf is selected with the device chess
 rules (K6/K7).  value = NN position evaluations per second over all ranks (BASELINE.json metric: "MCTS
 sims/sec + NN position evals/sec"); sims/s (>= evals/s: terminal leaves need no network) is reported
-beside it.  Inputs: seeded random-playout positions, Keras random-init weights (no data or weights ship
+beside it.  Inputs: seeded random-playout positions, glorot random-init kernels with trained-like BN statistics (no data or weights ship
 with the reference).  Multi-GPU: games are sharded by rank, no data-path collective.
 
 `--impl reference` times the reference's CPU path (its mcts.py/gameimage.py/actionspace.py logic as
@@ -55,6 +55,30 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------------------------------ inputs
+def trained_like_bn(w, filters, blocks, in_channels=119):
+    """Overwrites the BatchNorm moving statistics of a Keras-layout weights dict (glorot kernels stay) with
+    the values a trained network would hold for them, from a closed-form variance recurrence: the stem
+    normalises the raw integer planes (move count ~80, halfmove clock ~50), every BN sees unit-variance
+    pre-activations.  Logits come out O(1) (|logit| max 1..2, checked against the torch-fp32 oracle).
+    Fresh Keras BN (mean 0 / var 1) lets a 20x256 tower reach |logit| ~ 95: np.exp overflows, priors
+    become NaN and every search degenerates — not a workload."""
+    C = filters
+
+    def bn(c, var):
+        return np.stack([np.ones(c), np.zeros(c), np.zeros(c), np.full(c, var)]).astype(np.float32)
+
+    w = dict(w)
+    w["stem.bn"] = bn(C, 0.9 * 2.0 * in_channels / (in_channels + C) * (80.0 ** 2 + 50.0 ** 2 + 30.0) / in_channels)
+    m = 0.6                                     # second moment of LeakyReLU(0.3) of a unit normal ~ 0.545 (+ mean)
+    for i in range(blocks):
+        w[f"res{i}.bn1"] = bn(C, 0.85 * m)      # 0.85: border taps of the 3x3 "same" convolution
+        w[f"res{i}.bn2"] = bn(C, 0.85 * 0.545)
+        m = 0.6 * (m / 0.6 + 1.0)               # x + BN(y): variances add
+    w["value.bn"] = bn(1, m * 2 * C / (C + 1))
+    w["policy.bn"] = bn(2, m * 2 * C / (C + 2))
+    return w
+
+
 def random_positions_device(n, seed, min_plies=8, max_plies=160):
     """seeded random playouts with the product's own host rules; full move stacks."""
     import random
@@ -126,7 +150,7 @@ class ClockSampler:
 def _oracle_setup(filters, blocks, seed):
     import torch
     from oracle import ref_model
-    w = ref_model.init_weights(filters, blocks, seed=seed)
+    w = trained_like_bn(ref_model.init_weights(filters, blocks, seed=seed), filters, blocks)
     return ref_model.as_network(w, "cpu")
 
 
@@ -242,7 +266,8 @@ def run_gpu_arm(args):
     trees = args.trees
     W, K = args.warmup, args.steps
     eng = Engine.get(local_rank)
-    net = DeviceNetwork(keras_init_weights(filters, blocks, seed=0), filters, blocks, max_batch=trees, device=local_rank)
+    net = DeviceNetwork(trained_like_bn(keras_init_weights(filters, blocks, seed=0), filters, blocks), filters, blocks,
+                        max_batch=trees, device=local_rank)
     boards = random_positions_device(trees, seed=1000 + rank)   # every rank searches its own shard of games
     records = [b.export_record() for b in boards]
     total_steps = W + 2 * K + 4
@@ -326,7 +351,7 @@ def run_gpu_arm(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {
                 "workload": f"batched MCTS leaf evaluation + tree update: {trees} concurrent games per GPU, {blocks}x{filters} "
-                            f"ResNet (Keras random init), one leaf per game per step (encode + forward + legal-move softmax + backup + select)",
+                            f"ResNet (glorot kernels, trained-like BN statistics), one leaf per game per step (encode + forward + legal-move softmax + backup + select)",
                 "net": args.net, "trees_per_gpu": trees, "parallelism": f"games sharded over {world} GPU(s), no collective",
                 "l2": "working set per step (49 MB weights + 3x52 MB activations + node pool) exceeds the 126 MB L2; no flush",
                 "fwd_gflop_per_position": flops_per_position(filters, blocks) / 1e9,

@@ -1,6 +1,7 @@
 // Device side of the C ABI (include/chessbot_b200.h): context, network weights and the batched
 // search driver.  Kernels live in encode.cu / conv.cu / heads.cu / mcts.cu.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -432,12 +433,24 @@ int cb_search_begin(cb_ctx* ctx, int n_trees, const void* records_host, const in
     return launch_mcts_begin(s.sp, st);
 }
 
+// CB_DEBUG_SYNC=1: synchronise after every stage of a search step and name the stage that faulted
+static int debug_sync(cudaStream_t st, const char* stage) {
+    static const bool on = getenv("CB_DEBUG_SYNC") != nullptr;
+    if (!on) return 0;
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+        cb_set_error(std::string("CB_DEBUG_SYNC: ") + stage + ": " + cudaGetErrorString(e));
+        return -1;
+    }
+    return 0;
+}
+
 int cb_search_step(cb_ctx* ctx, void* stream) {
     Search& s = ctx->search;
     cudaStream_t st = (cudaStream_t)stream;
     if (s.eval_mode == CB_EVAL_NET) {
-        if (launch_encode(s.pos.p, s.frame_idx.p, s.n_trees, s.planes_act.p, nullptr, st)) return -1;
-        if (net_tower(ctx, s.planes_act.p, s.n_trees, s.value.p, st)) return -1;
+        if (launch_encode(s.pos.p, s.frame_idx.p, s.n_trees, s.planes_act.p, nullptr, st) || debug_sync(st, "encode")) return -1;
+        if (net_tower(ctx, s.planes_act.p, s.n_trees, s.value.p, st) || debug_sync(st, "tower")) return -1;
     } else if (s.eval_mode == CB_EVAL_SYNTH) {
         if (launch_encode(s.pos.p, s.frame_idx.p, s.n_trees, nullptr, s.planes_i16.p, st)) return -1;
         if (launch_synth(s.planes_i16.p, s.n_trees, s.seed, s.synth_hash.p, s.value.p, nullptr, st)) return -1;
@@ -445,7 +458,8 @@ int cb_search_step(cb_ctx* ctx, void* stream) {
         cb_set_error("cb_search_step: external evaluation uses cb_search_step_external");
         return -1;
     }
-    return launch_mcts_step(s.sp, st);
+    if (launch_mcts_step(s.sp, st)) return -1;
+    return debug_sync(st, "mcts_step");
 }
 int cb_search_run(cb_ctx* ctx, int steps, void* stream) {
     for (int i = 0; i < steps; ++i)

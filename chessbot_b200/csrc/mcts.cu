@@ -161,7 +161,11 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_step_kernel(SearchParams
             const double c = cpuct_fixed < 0 ? sp.cpuct_tab[np] : cpuct_fixed;
             const double sq = sp.sqrt_tab[np];
             const bool f64 = noisy && node == ts.root_node;
-            double best_u = 0;
+            // Python's max() over (ucb, move, child) tuples (mcts.py:120-123) is a sequential scan that replaces
+            // the running best only when the candidate compares greater; a NaN ucb (overflowing logits:
+            // exp -> inf, inf/inf) never does.  So: NaN children never win, unless child 0 itself is NaN, in
+            // which case nothing ever replaces it.
+            double best_u = 0, u0 = 0;
             int best_key = -1, best_i = -1;
             for (int i = lane; i < nd.n_children; i += 32) {
                 const Node ch = sp.nodes[nd.first_child + i];
@@ -177,6 +181,8 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_step_kernel(SearchParams
                     t = __fdiv_rn(t, (float)(ch.N + 1));
                     u = (double)__fadd_rn(ch.Q, t);  // f32 value, exactly representable in f64
                 }
+                if (i == 0) u0 = u;
+                if (u != u) continue;
                 const int key = uci_sort_key(ch.move);
                 if (best_i < 0 || u > best_u || (u == best_u && key > best_key)) { best_u = u; best_key = key; best_i = i; }
             }
@@ -186,6 +192,9 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_step_kernel(SearchParams
                 const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
                 if (oi >= 0 && (best_i < 0 || ou > best_u || (ou == best_u && ok > best_key))) { best_u = ou; best_key = ok; best_i = oi; }
             }
+            u0 = __shfl_sync(0xffffffffu, u0, 0);
+            best_i = __shfl_sync(0xffffffffu, best_i, 0);   // one decision for the whole warp
+            if (u0 != u0 || best_i < 0) best_i = 0;
             node = nd.first_child + best_i;
         }
         // ---- leaf: position, outcome (mcts.py:67, game.py:49-59)
