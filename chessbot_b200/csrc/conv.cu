@@ -13,14 +13,16 @@
 //   stage (halves the L2->smem weight traffic per MMA), accumulating into two 128 x N fp32
 //   accumulators that fill TMEM (2 x 256 columns).
 // * Warp roles: warp 0 = bulk-copy producer, warp 1 = MMA issuer (one lane) + TMEM owner,
-//   warps 2..5 = epilogue (tcgen05.ld -> BN scale/shift -> +skip -> LeakyReLU -> bf16 -> HBM in the
+//   warps 2..9 = epilogue (tcgen05.ld -> BN scale/shift -> +skip -> LeakyReLU -> bf16 -> HBM in the
 //   same tile-native layout; optionally the three 1x1 head convolutions of model.py:43,52 as dot
 //   products over the fp32 row).
+#include <stdlib.h>
+
 #include "kernels.cuh"
 
 namespace cb {
 
-constexpr int CONV_THREADS = 192;
+constexpr int CONV_THREADS = 320;  // producer warp, MMA warp, 8 epilogue warps
 constexpr int A_SLOTS = 2, B_SLOTS = 3;
 constexpr int A_SLOT_BYTES = 2 * ACT_K64_BYTES;  // two board pairs x 64 channels
 constexpr int B_SLOT_BYTES = 256 * 128;          // N <= 256 rows x 64 k x bf16
@@ -60,7 +62,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tcgen05_kernel(ConvPa
         for (int i = 0; i < A_SLOTS; ++i) { ptx::mbar_init(&s->a_full[i], 1); ptx::mbar_init(&s->a_empty[i], 1); }
         for (int i = 0; i < B_SLOTS; ++i) { ptx::mbar_init(&s->b_full[i], 1); ptx::mbar_init(&s->b_empty[i], 1); }
         ptx::mbar_init(&s->acc_full, 1);
-        ptx::mbar_init(&s->acc_empty, 4);  // one arrival per epilogue warp
+        ptx::mbar_init(&s->acc_empty, 8);  // one arrival per epilogue warp
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
@@ -82,8 +84,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tcgen05_kernel(ConvPa
                 for (int kc = 0; kc < p.kc; ++kc) {
                     const int as = a_it % A_SLOTS;
                     ptx::mbar_wait(&s->a_empty[as], ((a_it / A_SLOTS) & 1) ^ 1);
-                    ptx::mbar_expect_tx(&s->a_full[as], (uint32_t)ntiles * ACT_K64_BYTES);
-                    for (int t = 0; t < ntiles; ++t) {
+                    if (p.debug & 32) ptx::mbar_arrive(&s->a_full[as]);
+                    else ptx::mbar_expect_tx(&s->a_full[as], (uint32_t)ntiles * ACT_K64_BYTES);
+                    for (int t = 0; t < ntiles && !(p.debug & 32); ++t) {
                         const uint8_t* src = reinterpret_cast<const uint8_t*>(p.in) +
                                              ((size_t)(2 * u + t) * p.cj_in + 8 * (kc % p.kc_in)) * ACT_CHUNK_BYTES;
                         ptx::bulk_g2s(a_buf + as * A_SLOT_BYTES + t * ACT_K64_BYTES, src, ACT_K64_BYTES, &s->a_full[as]);
@@ -92,6 +95,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tcgen05_kernel(ConvPa
                     for (int tap = 0; tap < 9; ++tap) {
                         const int bs = b_it % B_SLOTS;
                         ptx::mbar_wait(&s->b_empty[bs], ((b_it / B_SLOTS) & 1) ^ 1);
+                        if (p.debug & 8) { ptx::mbar_arrive(&s->b_full[bs]); ++b_it; continue; }
                         ptx::mbar_expect_tx(&s->b_full[bs], b_bytes);
                         const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wgt) + (size_t)(kc * 9 + tap) * b_bytes;
                         ptx::bulk_g2s(b_buf + bs * B_SLOT_BYTES, src, b_bytes, &s->b_full[bs]);
@@ -120,7 +124,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tcgen05_kernel(ConvPa
                         const uint32_t b_base = ptx::smem_u32(b_buf + bs * B_SLOT_BYTES);
                         const int dy = tap / 3 - 1, dx = tap % 3 - 1;
                         const uint32_t a_tap = a_base + (uint32_t)(((1 + dy) * 20 + 1 + dx) * 16);
-                        for (int t = 0; t < ntiles; ++t) {
+                        for (int t = 0; t < ntiles && !(p.debug & 4); ++t) {
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks) {
                                 const uint64_t ad = ptx::smem_desc(a_tap + t * ACT_K64_BYTES + ks * 2 * ACT_CHUNK_BYTES,
@@ -139,60 +143,78 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tcgen05_kernel(ConvPa
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        // ------------------------------------------------------------------ epilogue (warps 2..9)
+        // Two warps per TMEM lane quarter (a warp may only read lanes 32*(warp%4)..+31): one drains tile 0
+        // of the unit, the other tile 1.  The skip tile is read through a 4-deep register ring whose first
+        // loads are issued BEFORE the accumulator is ready, so the global-memory latency hides behind the MMAs.
         const int q = warp & 3;          // TMEM lane quarter this warp may read
+        const int t = (warp - 2) >> 2;   // tile of the unit this warp drains
         const int m = q * 32 + lane;     // accumulator row
         const int g = m >> 3, col = m & 7, row = g >> 1, bip = g & 1;
         const int cell = act_cell(row, bip, col);
-        const int cjo = n >> 3;
+        const int cjo = n >> 3, ncb = n >> 5;
+        const bool has_skip = p.skip != nullptr && !(p.debug & 2);
         uint32_t u_it = 0;
         for (int u = blockIdx.x; u < units; u += gridDim.x, ++u_it) {
             const int ntiles = (2 * u + 1 < p.pairs) ? 2 : 1;
+            const int pair = 2 * u + t;
+            const bool active = t < ntiles && !(p.debug & 1);
+            uint4 sk[4][4];
+            auto load_skip = [&](uint4 (&dst)[4], int cb) {
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj)
+                    dst[jj] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.skip) +
+                                                                   act_offset_bytes(pair, cjo, cb * 4 + jj, cell)));
+            };
+            if (active && has_skip) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                    if (r < ncb) load_skip(sk[r], r);
+            }
             ptx::mbar_wait(&s->acc_full, u_it & 1);
             ptx::tc_fence_after();
-            for (int t = 0; t < ntiles; ++t) {
-                const int pair = 2 * u + t;
+            if (active) {
                 float h0 = 0.f, h1 = 0.f, h2 = 0.f;
-                for (int cb = 0; cb < n / 32; ++cb) {
-                    uint4 sk[4];
-                    if (p.skip) {
+                for (int cb0 = 0; cb0 < ncb; cb0 += 4) {
 #pragma unroll
-                        for (int jj = 0; jj < 4; ++jj)
-                            sk[jj] = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.skip) +
-                                                                     act_offset_bytes(pair, cjo, cb * 4 + jj, cell));
-                    }
-                    uint32_t acc[32];
-                    ptx::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + t * 256 + cb * 32, acc);
-                    ptx::tmem_wait_ld();
+                    for (int r = 0; r < 4; ++r) {
+                        const int cb = cb0 + r;
+                        if (cb >= ncb) break;
+                        uint32_t acc[32];
+                        ptx::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + t * 256 + cb * 32, acc);
+                        ptx::tmem_wait_ld();
 #pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        float v[8];
-                        const uint32_t* skw = reinterpret_cast<const uint32_t*>(&sk[jj]);
+                        for (int jj = 0; jj < 4; ++jj) {
+                            float v[8];
+                            const uint32_t* skw = reinterpret_cast<const uint32_t*>(&sk[r][jj]);
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const int ch = cb * 32 + jj * 8 + e;
-                            float x = fmaf(__uint_as_float(acc[jj * 8 + e]), s_scale[ch], s_shift[ch]);
-                            if (p.skip) {
-                                uint32_t w = skw[e >> 1];
-                                x += __uint_as_float((e & 1) ? (w & 0xFFFF0000u) : (w << 16));
+                            for (int e = 0; e < 8; ++e) {
+                                const int ch = cb * 32 + jj * 8 + e;
+                                float x = fmaf(__uint_as_float(acc[jj * 8 + e]), s_scale[ch], s_shift[ch]);
+                                if (has_skip) {
+                                    const uint32_t w = skw[e >> 1];
+                                    x += __uint_as_float((e & 1) ? (w & 0xFFFF0000u) : (w << 16));
+                                }
+                                x = x > 0.f ? x : x * p.slope;
+                                v[e] = x;
+                                if (p.head_w) {
+                                    h0 = fmaf(x, s_head[ch], h0);
+                                    h1 = fmaf(x, s_head[256 + ch], h1);
+                                    h2 = fmaf(x, s_head[512 + ch], h2);
+                                }
                             }
-                            x = x > 0.f ? x : x * p.slope;
-                            v[e] = x;
-                            if (p.head_w) {
-                                h0 = fmaf(x, s_head[ch], h0);
-                                h1 = fmaf(x, s_head[256 + ch], h1);
-                                h2 = fmaf(x, s_head[512 + ch], h2);
-                            }
+                            uint4 o;
+                            __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]), t1 = __floats2bfloat162_rn(v[2], v[3]);
+                            __nv_bfloat162 t2 = __floats2bfloat162_rn(v[4], v[5]), t3 = __floats2bfloat162_rn(v[6], v[7]);
+                            o.x = *reinterpret_cast<uint32_t*>(&t0);
+                            o.y = *reinterpret_cast<uint32_t*>(&t1);
+                            o.z = *reinterpret_cast<uint32_t*>(&t2);
+                            o.w = *reinterpret_cast<uint32_t*>(&t3);
+                            if (!(p.debug & 16) || o.x == 0x12345678u)
+                            *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) +
+                                                      act_offset_bytes(pair, cjo, cb * 4 + jj, cell)) = o;
                         }
-                        uint4 o;
-                        __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]), t1 = __floats2bfloat162_rn(v[2], v[3]);
-                        __nv_bfloat162 t2 = __floats2bfloat162_rn(v[4], v[5]), t3 = __floats2bfloat162_rn(v[6], v[7]);
-                        o.x = *reinterpret_cast<uint32_t*>(&t0);
-                        o.y = *reinterpret_cast<uint32_t*>(&t1);
-                        o.z = *reinterpret_cast<uint32_t*>(&t2);
-                        o.w = *reinterpret_cast<uint32_t*>(&t3);
-                        *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) +
-                                                  act_offset_bytes(pair, cjo, cb * 4 + jj, cell)) = o;
+                        if (has_skip && cb + 4 < ncb) load_skip(sk[r], cb + 4);
                     }
                 }
                 if (p.head_w) {
@@ -254,6 +276,8 @@ int launch_conv3x3(const ConvParams& p, int num_sms, cudaStream_t stream) {
     }
     const int units = (p.pairs + 1) / 2;
     const int grid = units < num_sms ? units : num_sms;
+    static const int dbg = getenv("CB_CONV_DEBUG") ? atoi(getenv("CB_CONV_DEBUG")) : 0;
+    if (dbg) const_cast<ConvParams&>(p).debug = dbg;
     conv3x3_tcgen05_kernel<<<grid, CONV_THREADS, CONV_SMEM_BYTES, stream>>>(p);
     CB_CUDA_OK(cudaGetLastError());
     return 0;

@@ -21,6 +21,7 @@ struct ConvParams {
     int cj_in;                  // input channels / 8
     int n;                      // output channels (multiple of 64, <= 256)
     float slope;                // LeakyReLU negative slope (Keras default 0.3)
+    int debug;                  // experiments only (CB_CONV_DEBUG): 1 no epilogue, 2 no skip loads, 4 no MMAs, 8 no weight loads, 16 no stores
 };
 
 struct HeadParams {
