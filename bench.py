@@ -302,14 +302,30 @@ def run_gpu_arm(args):
     if c1["errors"]:
         raise RuntimeError("search pool exhausted during the bench")
 
-    # roofline leg: the same K steps again with CUDA events around every convolution launch
-    eng.profile_conv(True)
+    # roofline leg: the same K steps again with CUDA events (on the launching stream) around every kernel launch
+    nodes0 = int(eng.search_read_roots()["nodes"].sum())
+    eng.profile(True)
     eng.search_run(K)
-    conv_ms, conv_launches = eng.profile_conv_read()
-    eng.profile_conv(False)
+    prof = eng.profile_read()
+    eng.profile(False)
+    c2 = eng.search_status()
+    nodes1 = int(eng.search_read_roots()["nodes"].sum())
+    conv_ms, conv_launches = prof["conv"]
     conv_flops_launch_total = conv_flops_per_position(filters, blocks) * trees * K   # algorithmic direct-conv FLOPs
     peak_tf, peak_gbs, peak_src = measured_peaks()
     achieved_tf = conv_flops_launch_total / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    # HBM-bound kernels, algorithmic bytes as stated in DESIGN.md §4
+    enc_bytes = 17152.0 * trees * K                                             # 8 x 96 B frames read + 128 ch bf16 written
+    mcts_bytes = (nodes1 - nodes0) * (512 + 32 + 2) + (c2["sims"] - c1["sims"]) * 2700.0   # prior gather + node writes; select/backup
+    kernels = {}
+    for name, nbytes in (("encode", enc_bytes), ("mcts_step", mcts_bytes), ("heads", None)):
+        ms_k, n_k = prof["heads" if name == "heads" else name]
+        kernels[name] = {"launches": n_k, "avg_us": 1e3 * ms_k / max(n_k, 1), "share_of_step": ms_k / sum(v[0] for v in prof.values())}
+        if nbytes:
+            gbs = nbytes / (ms_k * 1e-3) / 1e9
+            kernels[name].update({"bound": "hbm", "achieved_gbs": gbs, "peak_gbs": peak_gbs, "frac": gbs / peak_gbs})
+    kernels["conv3x3"] = {"launches": conv_launches, "avg_us": 1e3 * conv_ms / max(conv_launches, 1),
+                          "share_of_step": conv_ms / sum(v[0] for v in prof.values())}
 
     # end-to-end leg: complete searches through the public API (mcts.run_mcts_batch) from host game objects:
     # host rules export the game records, H2D, e2e_sims+1 device steps, D2H of the root statistics, move choice.
@@ -366,6 +382,7 @@ def run_gpu_arm(args):
                     "d2h_bytes_per_step": d2h / steps_per_search,
                     "what": f"{reps} x mcts.run_mcts_batch({trees} games, {e2e_sims} sims): host game records -> H2D -> {steps_per_search} steps -> D2H root "
                             f"statistics -> move choice; bytes are per search / {steps_per_search} steps"},
+            "kernels": kernels,
             "gpu_launches": K * (1 + (1 + 2 * blocks) + 1 + 1),
             "clocks": clocks,
             "cpu_baseline": cpu_baseline,

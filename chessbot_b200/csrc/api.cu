@@ -94,13 +94,34 @@ struct Search {
 
 struct cb_ctx {
     int device = 0, sms = 0;
-    bool profile = false;                       // CUDA events around every conv launch (bench.py roofline leg)
+    bool profile = false;                       // CUDA events around every kernel launch (bench.py roofline legs)
     std::vector<cudaEvent_t> prof_events;       // pairs
+    std::vector<int> prof_stage;                // CB_PROF_* of each pair
     size_t prof_used = 0;
     DevBuf<float> exp_table;
     Net net;
     Search search;
 };
+
+// brackets one kernel launch with CUDA events on its stream when profiling is on
+static int prof_begin(cb_ctx* ctx, int stage, cudaStream_t st) {
+    if (!ctx->profile) return 0;
+    while (ctx->prof_events.size() < ctx->prof_used + 2) {
+        cudaEvent_t e;
+        CB_CUDA_OK(cudaEventCreate(&e));
+        ctx->prof_events.push_back(e);
+    }
+    if (ctx->prof_stage.size() < ctx->prof_used / 2 + 1) ctx->prof_stage.resize(ctx->prof_used / 2 + 1);
+    ctx->prof_stage[ctx->prof_used / 2] = stage;
+    CB_CUDA_OK(cudaEventRecord(ctx->prof_events[ctx->prof_used], st));
+    return 0;
+}
+static int prof_end(cb_ctx* ctx, cudaStream_t st) {
+    if (!ctx->profile) return 0;
+    CB_CUDA_OK(cudaEventRecord(ctx->prof_events[ctx->prof_used + 1], st));
+    ctx->prof_used += 2;
+    return 0;
+}
 
 static int upload(void* dst, const void* src, size_t bytes) {
     CB_CUDA_OK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
@@ -140,8 +161,12 @@ int cb_ctx_sm_count(const cb_ctx* ctx) { return ctx->sms; }
 int cb_set_exp_table(cb_ctx* ctx, const float* table_host) { return upload(ctx->exp_table.p, table_host, 65536 * 4); }
 
 size_t cb_planes_act_bytes(int n) { return act_bytes(n, 128); }
-int cb_encode(cb_ctx*, const void* pos_dev, const int32_t* frame_idx_dev, int n, void* planes_act_dev, int16_t* planes_i16_dev, void* stream) {
-    return launch_encode((const Pos*)pos_dev, frame_idx_dev, n, (__nv_bfloat16*)planes_act_dev, planes_i16_dev, (cudaStream_t)stream);
+int cb_encode(cb_ctx* ctx, const void* pos_dev, const int32_t* frame_idx_dev, int n, void* planes_act_dev, int16_t* planes_i16_dev, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (prof_begin(ctx, CB_PROF_ENCODE, st) ||
+        launch_encode((const Pos*)pos_dev, frame_idx_dev, n, (__nv_bfloat16*)planes_act_dev, planes_i16_dev, st) || prof_end(ctx, st))
+        return -1;
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------ network
@@ -285,30 +310,22 @@ static int net_tower(cb_ctx* ctx, const void* planes_act_dev, int n, float* valu
         else { p.in = net.act[(cur + 1) % 3].p; out_i = (cur + 2) % 3; p.skip = net.act[cur].p; }  // second conv + skip
         p.out = net.act[out_i].p;
         if (l == nl - 1) { p.head_w = net.head_w.p; p.head_out = net.head_raw.p; }
-        if (ctx->profile) {
-            while (ctx->prof_events.size() < ctx->prof_used + 2) {
-                cudaEvent_t e;
-                CB_CUDA_OK(cudaEventCreate(&e));
-                ctx->prof_events.push_back(e);
-            }
-            CB_CUDA_OK(cudaEventRecord(ctx->prof_events[ctx->prof_used], st));
-        }
-        if (launch_conv3x3(p, ctx->sms, st)) return -1;
-        if (ctx->profile) {
-            CB_CUDA_OK(cudaEventRecord(ctx->prof_events[ctx->prof_used + 1], st));
-            ctx->prof_used += 2;
-        }
+        if (prof_begin(ctx, CB_PROF_CONV, st) || launch_conv3x3(p, ctx->sms, st) || prof_end(ctx, st)) return -1;
         if (l == 0 || !(l & 1)) cur = out_i;
     }
     HeadParams hp{net.head_raw.p, net.head_bn.p, net.fc1.p, net.fc2.p, net.filters, net.slope, value_dev, net.pfeat.p};
-    return launch_head_features(hp, n, st);
+    if (prof_begin(ctx, CB_PROF_HEADS, st) || launch_head_features(hp, n, st) || prof_end(ctx, st)) return -1;
+    return 0;
 }
 
 int cb_net_forward(cb_ctx* ctx, const void* planes_act_dev, int n, float* value_dev, void* logits_bf16_dev, float* logits_f32_dev, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (net_tower(ctx, planes_act_dev, n, value_dev, st)) return -1;
-    if (logits_bf16_dev || logits_f32_dev)
-        return launch_policy_dense(ctx->net.pfeat.p, ctx->net.wp.p, n, (__nv_bfloat16*)logits_bf16_dev, logits_f32_dev, st);
+    if (logits_bf16_dev || logits_f32_dev) {
+        if (prof_begin(ctx, CB_PROF_POLICY_DENSE, st) ||
+            launch_policy_dense(ctx->net.pfeat.p, ctx->net.wp.p, n, (__nv_bfloat16*)logits_bf16_dev, logits_f32_dev, st) || prof_end(ctx, st))
+            return -1;
+    }
     return 0;
 }
 
@@ -320,25 +337,28 @@ int cb_synth_forward(cb_ctx* ctx, const int16_t* planes_i16_dev, int n, uint32_t
 
 int cb_policy_softmax(cb_ctx* ctx, const void* pos_dev, const int32_t* cur_idx_dev, int n, const void* logits_bf16_dev,
                       uint16_t* out_moves_dev, int16_t* out_actions_dev, float* out_priors_dev, int32_t* out_n_dev, void* stream) {
-    return launch_policy_softmax((const Pos*)pos_dev, cur_idx_dev, n, (const __nv_bfloat16*)logits_bf16_dev, ctx->exp_table.p,
-                                 out_moves_dev, out_actions_dev, out_priors_dev, out_n_dev, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (prof_begin(ctx, CB_PROF_POLICY_SOFTMAX, st) ||
+        launch_policy_softmax((const Pos*)pos_dev, cur_idx_dev, n, (const __nv_bfloat16*)logits_bf16_dev, ctx->exp_table.p,
+                              out_moves_dev, out_actions_dev, out_priors_dev, out_n_dev, st) || prof_end(ctx, st))
+        return -1;
+    return 0;
 }
 
-int cb_profile_conv(cb_ctx* ctx, int enable) {
+int cb_profile(cb_ctx* ctx, int enable) {
     ctx->profile = enable != 0;
     ctx->prof_used = 0;
     return 0;
 }
-int cb_profile_conv_read_sync(cb_ctx* ctx, double* total_ms, int* launches) {
+int cb_profile_read_sync(cb_ctx* ctx, double* total_ms, int* launches) {
     CB_CUDA_OK(cudaDeviceSynchronize());
-    double t = 0;
+    for (int k = 0; k < CB_PROF_STAGES; ++k) { total_ms[k] = 0; launches[k] = 0; }
     for (size_t i = 0; i + 1 < ctx->prof_used; i += 2) {
         float ms = 0;
         CB_CUDA_OK(cudaEventElapsedTime(&ms, ctx->prof_events[i], ctx->prof_events[i + 1]));
-        t += ms;
+        total_ms[ctx->prof_stage[i / 2]] += ms;
+        launches[ctx->prof_stage[i / 2]] += 1;
     }
-    *total_ms = t;
-    *launches = (int)(ctx->prof_used / 2);
     ctx->prof_used = 0;
     return 0;
 }
@@ -449,7 +469,9 @@ int cb_search_step(cb_ctx* ctx, void* stream) {
     Search& s = ctx->search;
     cudaStream_t st = (cudaStream_t)stream;
     if (s.eval_mode == CB_EVAL_NET) {
-        if (launch_encode(s.pos.p, s.frame_idx.p, s.n_trees, s.planes_act.p, nullptr, st) || debug_sync(st, "encode")) return -1;
+        if (prof_begin(ctx, CB_PROF_ENCODE, st) || launch_encode(s.pos.p, s.frame_idx.p, s.n_trees, s.planes_act.p, nullptr, st) ||
+            prof_end(ctx, st) || debug_sync(st, "encode"))
+            return -1;
         if (net_tower(ctx, s.planes_act.p, s.n_trees, s.value.p, st) || debug_sync(st, "tower")) return -1;
     } else if (s.eval_mode == CB_EVAL_SYNTH) {
         if (launch_encode(s.pos.p, s.frame_idx.p, s.n_trees, nullptr, s.planes_i16.p, st)) return -1;
@@ -458,7 +480,7 @@ int cb_search_step(cb_ctx* ctx, void* stream) {
         cb_set_error("cb_search_step: external evaluation uses cb_search_step_external");
         return -1;
     }
-    if (launch_mcts_step(s.sp, st)) return -1;
+    if (prof_begin(ctx, CB_PROF_MCTS, st) || launch_mcts_step(s.sp, st) || prof_end(ctx, st)) return -1;
     return debug_sync(st, "mcts_step");
 }
 int cb_search_run(cb_ctx* ctx, int steps, void* stream) {

@@ -133,13 +133,18 @@ class Engine:
                                     _ptr(priors), _ptr(counts), _stream()), "policy_softmax")
         return moves, actions, priors, counts
 
-    def profile_conv(self, enable):
-        check(lib.cb_profile_conv(self._h, int(enable)), "profile_conv")
+    PROF_STAGES = ("encode", "conv", "heads", "mcts_step", "policy_dense", "policy_softmax")
 
-    def profile_conv_read(self):
-        ms, n = C.c_double(0), C.c_int(0)
-        check(lib.cb_profile_conv_read_sync(self._h, C.byref(ms), C.byref(n)), "profile_conv_read")
-        return ms.value, n.value
+    def profile(self, enable):
+        """CUDA events around every kernel launch of the entry points (measurement legs of bench.py)."""
+        check(lib.cb_profile(self._h, int(enable)), "profile")
+
+    def profile_read(self):
+        """{stage: (total_ms, launches)} since profile(True) / the last read."""
+        ms = (C.c_double * len(self.PROF_STAGES))()
+        n = (C.c_int * len(self.PROF_STAGES))()
+        check(lib.cb_profile_read_sync(self._h, ms, n), "profile_read")
+        return {k: (ms[i], n[i]) for i, k in enumerate(self.PROF_STAGES)}
 
     def debug_conv_layer(self, layer, in_act, skip_act, n_boards, out_channels, use_reference=False):
         out = torch.zeros(((n_boards + 1) // 2) * (out_channels // 8) * 1600, dtype=torch.bfloat16, device=self.device)

@@ -120,9 +120,16 @@ int cb_search_status_sync(cb_ctx* ctx, int64_t* counters, void* stream);
 int cb_search_read_roots_sync(cb_ctx* ctx, uint16_t* moves, int32_t* n, float* w, float* q, double* p, int32_t* n_children,
                               int32_t* root_n, int32_t* tree_nodes, void* stream);
 
-/* ---- measurement: CUDA events around every convolution launch of cb_net_forward / cb_search_step ------ */
-int cb_profile_conv(cb_ctx* ctx, int enable);
-int cb_profile_conv_read_sync(cb_ctx* ctx, double* total_ms, int* launches);   /* sums and resets */
+/* ---- measurement: CUDA events (on the launching stream) around every kernel launch of the entry points above ---- */
+#define CB_PROF_ENCODE 0
+#define CB_PROF_CONV 1
+#define CB_PROF_HEADS 2
+#define CB_PROF_MCTS 3
+#define CB_PROF_POLICY_DENSE 4
+#define CB_PROF_POLICY_SOFTMAX 5
+#define CB_PROF_STAGES 6
+int cb_profile(cb_ctx* ctx, int enable);
+int cb_profile_read_sync(cb_ctx* ctx, double* total_ms /*[CB_PROF_STAGES]*/, int* launches /*[CB_PROF_STAGES]*/);   /* sums and resets */
 
 /* ---- test hooks (not on the product path) ------------------------------------------------------- */
 /* one 3x3 conv + BN + (skip) + LeakyReLU layer of the loaded net on tile-native buffers: layer 0 = stem,
