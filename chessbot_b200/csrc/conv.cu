@@ -1,5 +1,5 @@
 // K2 — 3x3 "same" convolution + BatchNorm + (residual add) + LeakyReLU of the residual tower
-// (model.py:19-28,35-37) as an implicit GEMM on tcgen05 tensor cores.
+// (model.py:19-28,35-37) as an implicit GEMM on tcgen05 tensor cores, two SMs per MMA.
 //
 //   D[m, co] = sum_{tap, ci} A_tap[m, ci] * W[tap][ci][co]      m = (row, board, col) of 2 boards = 128 rows
 //
@@ -8,35 +8,55 @@
 //   into shared memory, and each of the nine taps is just a different start address of the
 //   K-major / no-swizzle UMMA descriptor (LBO 3200 B between the two 8-channel core matrices,
 //   SBO 160 B between 8-pixel groups).
-// * W is pre-packed per (k-chunk, tap) as a [8][N][8] bf16 block = one bulk copy per stage.
-// * One persistent CTA per SM works on units of FOUR boards: two 128-row tiles share every weight
-//   stage (halves the L2->smem weight traffic per MMA), accumulating into two 128 x N fp32
-//   accumulators that fill TMEM (2 x 256 columns).
-// * Warp roles: warp 0 = bulk-copy producer, warp 1 = MMA issuer (one lane) + TMEM owner,
-//   warps 2..9 = epilogue (tcgen05.ld -> BN scale/shift -> +skip -> LeakyReLU -> bf16 -> HBM in the
-//   same tile-native layout; optionally the three 1x1 head convolutions of model.py:43,52 as dot
-//   products over the fp32 row).
+// * The kernel runs as clusters of two CTAs (one TPC) issuing cta_group::2 MMAs of M = 256: each CTA
+//   owns one board pair (128 accumulator rows in its own TMEM) and stages only HALF of every weight
+//   block (N/2 output channels, pre-packed per (k-chunk, tap, half) as [8][N/2][8] bf16 = one bulk
+//   copy); the tensor cores of the pair read both halves.  That halves the L2->smem weight traffic per
+//   MMA and the shared-memory operand bandwidth per SM.
+// * TMEM holds TWO accumulator stages of 256 columns: while the epilogue drains stage s, the MMAs of the
+//   next unit fill stage s^1, so BN / skip / LeakyReLU / stores overlap the tensor pipe.
+// * Warp roles per CTA: warp 0 = bulk-copy producer; warp 1 = MMA issuer (one lane, leader CTA) or
+//   relay (peer CTA: forwards "my operands have landed" to the leader's barriers); warps 2..9 =
+//   epilogue (tcgen05.ld -> BN scale/shift -> +skip -> LeakyReLU -> bf16 -> HBM in the same tile-native
+//   layout; optionally the three 1x1 head convolutions of model.py:43,52 as dot products over the
+//   fp32 row).  Two epilogue warps share a TMEM lane quarter and split the channel batches.
 #include <stdlib.h>
 
 #include "kernels.cuh"
 
 namespace cb {
 
-constexpr int CONV_THREADS = 320;  // producer warp, MMA warp, 8 epilogue warps
-constexpr int A_SLOTS = 2, B_SLOTS = 3;
-constexpr int A_SLOT_BYTES = 2 * ACT_K64_BYTES;  // two board pairs x 64 channels
-constexpr int B_SLOT_BYTES = 256 * 128;          // N <= 256 rows x 64 k x bf16
-
+constexpr int CONV_THREADS = 320;
+constexpr int A_SLOTS = 3, B_SLOTS = 8;
+constexpr int A_SLOT_BYTES = ACT_K64_BYTES;  // one board pair x 64 channels
+constexpr int B_SLOT_BYTES = 128 * 128;      // N/2 <= 128 rows x 64 k x bf16
+constexpr int EPI_WARPS = 8;
 
 struct ConvSmem {
-    uint64_t a_full[A_SLOTS], a_empty[A_SLOTS], b_full[B_SLOTS], b_empty[B_SLOTS], acc_full, acc_empty;
+    uint64_t a_full[A_SLOTS], a_peer[A_SLOTS], a_empty[A_SLOTS];
+    uint64_t b_full[B_SLOTS], b_peer[B_SLOTS], b_empty[B_SLOTS];
+    uint64_t acc_full[2], acc_empty[2];
     uint32_t tmem_base;
     uint32_t pad_;
 };
-constexpr int CONV_SMEM_PARAM_FLOATS = 256 * 2 + 256 * 3;
+static_assert(sizeof(ConvSmem) <= 1024, "barrier block");
+constexpr int CONV_SMEM_PARAM_FLOATS = 256 * 2 + 256 * 3 + 2 * 128 * 3;
 constexpr size_t CONV_SMEM_BYTES = 1024 + A_SLOTS * A_SLOT_BYTES + B_SLOTS * B_SLOT_BYTES + CONV_SMEM_PARAM_FLOATS * 4;
 
-__global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tcgen05_kernel(ConvParams p) {
+// experiments only (CB_CONV_DEBUG & 128): cycles the MMA issuer spends waiting, per barrier class, per cluster
+__device__ unsigned long long g_conv_timing[128][8];
+#define TIMED_WAIT(slot, stmt)                                   \
+    do {                                                         \
+        if (p.debug & 128) {                                     \
+            const long long t0_ = clock64();                     \
+            stmt;                                                \
+            tw[slot] += (unsigned long long)(clock64() - t0_);   \
+        } else {                                                 \
+            stmt;                                                \
+        }                                                        \
+    } while (0)
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) conv3x3_tcgen05_kernel(ConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     ConvSmem* s = reinterpret_cast<ConvSmem*>(smem);
     uint8_t* a_buf = smem + 1024;
@@ -44,10 +64,14 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tcgen05_kernel(ConvPa
     float* s_scale = reinterpret_cast<float*>(b_buf + B_SLOTS * B_SLOT_BYTES);
     float* s_shift = s_scale + 256;
     float* s_head = s_shift + 256;
+    float* s_hpart = s_head + 768;  // [2 stages][128 rows][3]
+    __shared__ long long s_tissue[B_SLOTS];  // experiments only
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int units = (p.pairs + 1) / 2;
-    const int n = p.n;
+    const uint32_t rank = ptx::cluster_ctarank();
+    const int cid = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+    const int units = (p.pairs + 1) / 2;  // one unit = two board pairs = one M=256 accumulator stage
+    const int n = p.n, nh = n >> 1;
 
     for (int i = threadIdx.x; i < n; i += CONV_THREADS) {
         s_scale[i] = p.scale[i];
@@ -59,106 +83,143 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tcgen05_kernel(ConvPa
         }
     }
     if (threadIdx.x == 0) {
-        for (int i = 0; i < A_SLOTS; ++i) { ptx::mbar_init(&s->a_full[i], 1); ptx::mbar_init(&s->a_empty[i], 1); }
-        for (int i = 0; i < B_SLOTS; ++i) { ptx::mbar_init(&s->b_full[i], 1); ptx::mbar_init(&s->b_empty[i], 1); }
-        ptx::mbar_init(&s->acc_full, 1);
-        ptx::mbar_init(&s->acc_empty, 8);  // one arrival per epilogue warp
+        for (int i = 0; i < A_SLOTS; ++i) { ptx::mbar_init(&s->a_full[i], 1); ptx::mbar_init(&s->a_peer[i], 1); ptx::mbar_init(&s->a_empty[i], 1); }
+        for (int i = 0; i < B_SLOTS; ++i) { ptx::mbar_init(&s->b_full[i], 1); ptx::mbar_init(&s->b_peer[i], 1); ptx::mbar_init(&s->b_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&s->acc_full[i], 1);
+            ptx::mbar_init(&s->acc_empty[i], 2 * EPI_WARPS);  // every epilogue warp of both CTAs
+        }
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
-        ptx::tmem_alloc(&s->tmem_base, 512);
-        ptx::tmem_relinquish();
+        ptx::tmem_alloc2(&s->tmem_base, 512);
+        ptx::tmem_relinquish2();
     }
     ptx::tc_fence_before();
     __syncthreads();
+    ptx::cluster_sync();  // barriers of both CTAs are initialised before any remote arrive / multicast commit
     ptx::tc_fence_after();
     const uint32_t tmem = s->tmem_base;
 
     if (warp == 0) {
-        // ------------------------------------------------------------------ producer
+        // ------------------------------------------------------------------ producer (both CTAs)
         if (lane == 0) {
             uint32_t a_it = 0, b_it = 0;
-            const uint32_t b_bytes = (uint32_t)n * 128;
-            for (int u = blockIdx.x; u < units; u += gridDim.x) {
-                const int ntiles = (2 * u + 1 < p.pairs) ? 2 : 1;
+            const uint32_t b_bytes = (uint32_t)nh * 128;
+            for (int u = cid; u < units; u += nclusters) {
+                const int pair = min(2 * u + (int)rank, p.pairs - 1);  // odd tail: the peer re-reads the last pair, its result is dropped
                 for (int kc = 0; kc < p.kc; ++kc) {
                     const int as = a_it % A_SLOTS;
                     ptx::mbar_wait(&s->a_empty[as], ((a_it / A_SLOTS) & 1) ^ 1);
                     if (p.debug & 32) ptx::mbar_arrive(&s->a_full[as]);
-                    else ptx::mbar_expect_tx(&s->a_full[as], (uint32_t)ntiles * ACT_K64_BYTES);
-                    for (int t = 0; t < ntiles && !(p.debug & 32); ++t) {
+                    else {
+                        ptx::mbar_expect_tx(&s->a_full[as], ACT_K64_BYTES);
                         const uint8_t* src = reinterpret_cast<const uint8_t*>(p.in) +
-                                             ((size_t)(2 * u + t) * p.cj_in + 8 * (kc % p.kc_in)) * ACT_CHUNK_BYTES;
-                        ptx::bulk_g2s(a_buf + as * A_SLOT_BYTES + t * ACT_K64_BYTES, src, ACT_K64_BYTES, &s->a_full[as]);
+                                             ((size_t)pair * p.cj_in + 8 * (kc % p.kc_in)) * ACT_CHUNK_BYTES;
+                        ptx::bulk_g2s(a_buf + as * A_SLOT_BYTES, src, ACT_K64_BYTES, &s->a_full[as]);
                     }
                     ++a_it;
                     for (int tap = 0; tap < 9; ++tap) {
                         const int bs = b_it % B_SLOTS;
                         ptx::mbar_wait(&s->b_empty[bs], ((b_it / B_SLOTS) & 1) ^ 1);
-                        if (p.debug & 8) { ptx::mbar_arrive(&s->b_full[bs]); ++b_it; continue; }
-                        ptx::mbar_expect_tx(&s->b_full[bs], b_bytes);
-                        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wgt) + (size_t)(kc * 9 + tap) * b_bytes;
-                        ptx::bulk_g2s(b_buf + bs * B_SLOT_BYTES, src, b_bytes, &s->b_full[bs]);
+                        if (p.debug & 8) ptx::mbar_arrive(&s->b_full[bs]);
+                        else {
+                            ptx::mbar_expect_tx(&s->b_full[bs], b_bytes);
+                            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wgt) + ((size_t)(kc * 9 + tap) * 2 + rank) * b_bytes;
+                            if (p.debug & 128) s_tissue[bs] = clock64();
+                            ptx::bulk_g2s(b_buf + bs * B_SLOT_BYTES, src, b_bytes, &s->b_full[bs]);
+                        }
                         ++b_it;
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            const uint32_t idesc = ptx::idesc_bf16_f32(128, n);
+        if (lane == 0 && rank == 0) {
+            // -------------------------------------------------------------- MMA issuer (leader CTA)
+            const uint32_t idesc = ptx::idesc_bf16_f32(256, n);
             uint32_t a_it = 0, b_it = 0, u_it = 0;
-            for (int u = blockIdx.x; u < units; u += gridDim.x, ++u_it) {
-                const int ntiles = (2 * u + 1 < p.pairs) ? 2 : 1;
-                ptx::mbar_wait(&s->acc_empty, (u_it & 1) ^ 1);
+            unsigned long long tw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            const long long t_start = clock64();
+            for (int u = cid; u < units; u += nclusters, ++u_it) {
+                const uint32_t st = u_it & 1;
+                TIMED_WAIT(1, ptx::mbar_wait_cluster(&s->acc_empty[st], ((u_it >> 1) & 1) ^ 1));
                 ptx::tc_fence_after();
+                const uint32_t d = tmem + st * 256;
                 for (int kc = 0; kc < p.kc; ++kc) {
                     const int as = a_it % A_SLOTS;
-                    ptx::mbar_wait(&s->a_full[as], (a_it / A_SLOTS) & 1);
+                    TIMED_WAIT(2, ptx::mbar_wait(&s->a_full[as], (a_it / A_SLOTS) & 1));
+                    if (!(p.debug & 64)) TIMED_WAIT(3, ptx::mbar_wait_cluster(&s->a_peer[as], (a_it / A_SLOTS) & 1));
                     const uint32_t a_base = ptx::smem_u32(a_buf + as * A_SLOT_BYTES);
                     for (int tap = 0; tap < 9; ++tap) {
                         const int bs = b_it % B_SLOTS;
-                        ptx::mbar_wait(&s->b_full[bs], (b_it / B_SLOTS) & 1);
+                        TIMED_WAIT(4, ptx::mbar_wait(&s->b_full[bs], (b_it / B_SLOTS) & 1));
+                        if (!(p.debug & 64)) TIMED_WAIT(5, ptx::mbar_wait_cluster(&s->b_peer[bs], (b_it / B_SLOTS) & 1));
                         ptx::tc_fence_after();
                         const uint32_t b_base = ptx::smem_u32(b_buf + bs * B_SLOT_BYTES);
                         const int dy = tap / 3 - 1, dx = tap % 3 - 1;
                         const uint32_t a_tap = a_base + (uint32_t)(((1 + dy) * 20 + 1 + dx) * 16);
-                        for (int t = 0; t < ntiles && !(p.debug & 4); ++t) {
+                        if (!(p.debug & 4)) {
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks) {
-                                const uint64_t ad = ptx::smem_desc(a_tap + t * ACT_K64_BYTES + ks * 2 * ACT_CHUNK_BYTES,
-                                                                   ACT_CHUNK_BYTES, 160);
-                                const uint64_t bd = ptx::smem_desc(b_base + ks * 2 * n * 16, (uint32_t)n * 16, 128);
-                                ptx::umma_bf16(tmem + t * 256, ad, bd, idesc, (kc | tap | ks) != 0);
+                                const uint64_t ad = ptx::smem_desc(a_tap + ks * 2 * ACT_CHUNK_BYTES, ACT_CHUNK_BYTES, 160);
+                                const uint64_t bd = ptx::smem_desc(b_base + ks * 2 * nh * 16, (uint32_t)nh * 16, 128);
+                                ptx::umma2_bf16(d, ad, bd, idesc, (kc | tap | ks) != 0);
                             }
                         }
-                        ptx::umma_commit(&s->b_empty[bs]);  // weight stage consumed when these MMAs retire
+                        ptx::umma2_commit_mc(&s->b_empty[bs]);  // weight stage of BOTH CTAs is free when these MMAs retire
                         ++b_it;
                     }
-                    ptx::umma_commit(&s->a_empty[as]);
+                    ptx::umma2_commit_mc(&s->a_empty[as]);
                     ++a_it;
                 }
-                ptx::umma_commit(&s->acc_full);
+                ptx::umma2_commit_mc(&s->acc_full[st]);
             }
+            if (p.debug & 128) {
+                tw[0] = (unsigned long long)(clock64() - t_start);
+                for (int i = 0; i < 6; ++i) g_conv_timing[cid & 127][i] = tw[i];
+            }
+        } else if (lane == 0) {
+            // -------------------------------------------------------------- relay (peer CTA)
+            uint32_t a_it = 0, b_it = 0;
+            unsigned long long lat_sum = 0, lat_n = 0;
+            const uint32_t a_peer0 = ptx::mapa(ptx::smem_u32(&s->a_peer[0]), 0), b_peer0 = ptx::mapa(ptx::smem_u32(&s->b_peer[0]), 0);
+            for (int u = cid; u < units; u += nclusters) {
+                for (int kc = 0; kc < p.kc; ++kc) {
+                    const int as = a_it % A_SLOTS;
+                    ptx::mbar_wait(&s->a_full[as], (a_it / A_SLOTS) & 1);
+                    ptx::mbar_arrive_remote(a_peer0 + as * 8);
+                    ++a_it;
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int bs = b_it % B_SLOTS;
+                        ptx::mbar_wait(&s->b_full[bs], (b_it / B_SLOTS) & 1);
+                        if (p.debug & 128) { lat_sum += (unsigned long long)(clock64() - s_tissue[bs]); ++lat_n; }
+                        ptx::mbar_arrive_remote(b_peer0 + bs * 8);
+                        ++b_it;
+                    }
+                }
+            }
+            if (p.debug & 128) { g_conv_timing[cid & 127][6] = lat_sum; g_conv_timing[cid & 127][7] = lat_n; }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue (warps 2..9)
-        // Two warps per TMEM lane quarter (a warp may only read lanes 32*(warp%4)..+31): one drains tile 0
-        // of the unit, the other tile 1.  The skip tile is read through a 4-deep register ring whose first
-        // loads are issued BEFORE the accumulator is ready, so the global-memory latency hides behind the MMAs.
+        // ------------------------------------------------------------------ epilogue (warps 2..9, both CTAs)
+        // Two warps per TMEM lane quarter (a warp may only read lanes 32*(warp%4)..+31) split the 32-channel
+        // batches of the row: warp half h takes batches h, h+2, ...  The skip tile is read through a 4-deep
+        // register ring whose first loads are issued BEFORE the accumulator is ready.
         const int q = warp & 3;          // TMEM lane quarter this warp may read
-        const int t = (warp - 2) >> 2;   // tile of the unit this warp drains
+        const int h = (warp - 2) >> 2;   // which half of the channel batches
         const int m = q * 32 + lane;     // accumulator row
         const int g = m >> 3, col = m & 7, row = g >> 1, bip = g & 1;
         const int cell = act_cell(row, bip, col);
         const int cjo = n >> 3, ncb = n >> 5;
+        const int nk = (ncb - h + 1) >> 1;  // batches of this warp: cb = h + 2k
         const bool has_skip = p.skip != nullptr && !(p.debug & 2);
+        const uint32_t acc_empty0 = ptx::mapa(ptx::smem_u32(&s->acc_empty[0]), 0);
         uint32_t u_it = 0;
-        for (int u = blockIdx.x; u < units; u += gridDim.x, ++u_it) {
-            const int ntiles = (2 * u + 1 < p.pairs) ? 2 : 1;
-            const int pair = 2 * u + t;
-            const bool active = t < ntiles && !(p.debug & 1);
+        for (int u = cid; u < units; u += nclusters, ++u_it) {
+            const uint32_t st = u_it & 1;
+            const int pair = 2 * u + (int)rank;
+            const bool active = pair < p.pairs && !(p.debug & 1);
             uint4 sk[4][4];
             auto load_skip = [&](uint4 (&dst)[4], int cb) {
 #pragma unroll
@@ -169,19 +230,20 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tcgen05_kernel(ConvPa
             if (active && has_skip) {
 #pragma unroll
                 for (int r = 0; r < 4; ++r)
-                    if (r < ncb) load_skip(sk[r], r);
+                    if (r < nk) load_skip(sk[r], h + 2 * r);
             }
-            ptx::mbar_wait(&s->acc_full, u_it & 1);
+            ptx::mbar_wait(&s->acc_full[st], (u_it >> 1) & 1);
             ptx::tc_fence_after();
+            float h0 = 0.f, h1 = 0.f, h2 = 0.f;
             if (active) {
-                float h0 = 0.f, h1 = 0.f, h2 = 0.f;
-                for (int cb0 = 0; cb0 < ncb; cb0 += 4) {
+                for (int k0 = 0; k0 < nk; k0 += 4) {
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
-                        const int cb = cb0 + r;
-                        if (cb >= ncb) break;
+                        const int k = k0 + r;
+                        if (k >= nk) break;
+                        const int cb = h + 2 * k;
                         uint32_t acc[32];
-                        ptx::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + t * 256 + cb * 32, acc);
+                        ptx::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + st * 256 + cb * 32, acc);
                         ptx::tmem_wait_ld();
 #pragma unroll
                         for (int jj = 0; jj < 4; ++jj) {
@@ -210,26 +272,33 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tcgen05_kernel(ConvPa
                             o.y = *reinterpret_cast<uint32_t*>(&t1);
                             o.z = *reinterpret_cast<uint32_t*>(&t2);
                             o.w = *reinterpret_cast<uint32_t*>(&t3);
-                            if (!(p.debug & 16) || o.x == 0x12345678u)
                             *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) +
                                                       act_offset_bytes(pair, cjo, cb * 4 + jj, cell)) = o;
                         }
-                        if (has_skip && cb + 4 < ncb) load_skip(sk[r], cb + 4);
+                        if (has_skip && k + 4 < nk) load_skip(sk[r], h + 2 * (k + 4));
                     }
                 }
-                if (p.head_w) {
-                    float* ho = p.head_out + ((size_t)(pair * 2 + bip) * 64 + row * 8 + col) * 3;
-                    ho[0] = h0; ho[1] = h1; ho[2] = h2;
-                }
             }
+            // the accumulator stage is drained: hand it back to the MMA issuer before the head bookkeeping
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&s->acc_empty);
+            if (lane == 0) ptx::mbar_arrive_remote(acc_empty0 + st * 8);
+            if (p.head_w) {
+                // the two warps of a lane quarter hold partial dot products over their channel batches
+                float* hp = s_hpart + ((size_t)st * 128 + m) * 3;
+                if (h == 1) { hp[0] = h0; hp[1] = h1; hp[2] = h2; }
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+                if (h == 0 && active) {
+                    float* ho = p.head_out + ((size_t)(pair * 2 + bip) * 64 + row * 8 + col) * 3;
+                    ho[0] = h0 + hp[0]; ho[1] = h1 + hp[1]; ho[2] = h2 + hp[2];
+                }
+            }
         }
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 1) ptx::tmem_dealloc(tmem, 512);
+    ptx::cluster_sync();  // the peer may still be reading this CTA's shared memory / signalling its barriers
+    if (warp == 1) ptx::tmem_dealloc2(tmem, 512);
 }
 
 // Plain CUDA-core restatement of the same layer on the same bf16 inputs (fp32 accumulate).  Test
@@ -237,7 +306,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv3x3_tcgen05_kernel(ConvPa
 __global__ void conv3x3_reference_kernel(ConvParams p) {
     const int boards = p.pairs * 2;
     const size_t total = (size_t)boards * 64 * p.n;
-    const int cjo = p.n >> 3;
+    const int cjo = p.n >> 3, nh = p.n >> 1;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const int co = (int)(idx % p.n);
         const int sq = (int)((idx / p.n) % 64);
@@ -252,7 +321,7 @@ __global__ void conv3x3_reference_kernel(ConvParams p) {
                 const __nv_bfloat16 a = *reinterpret_cast<const __nv_bfloat16*>(
                     reinterpret_cast<const uint8_t*>(p.in) + act_offset_bytes(pair, p.cj_in, cin >> 3, cell) + (cin & 7) * 2);
                 const int kc = ci >> 6, k = ci & 63;
-                const __nv_bfloat16 w = p.wgt[((size_t)(kc * 9 + tap) * p.n * 64) + ((size_t)(k >> 3) * p.n + co) * 8 + (k & 7)];
+                const __nv_bfloat16 w = p.wgt[conv_weight_index(kc, tap, k, co, nh)];
                 acc = fmaf(__bfloat162float(a), __bfloat162float(w), acc);
             }
         }
@@ -264,22 +333,30 @@ __global__ void conv3x3_reference_kernel(ConvParams p) {
     }
 }
 
-int launch_conv3x3(const ConvParams& p, int num_sms, cudaStream_t stream) {
+int launch_conv3x3(const ConvParams& p_in, int num_sms, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
         CB_CUDA_OK(cudaFuncSetAttribute(conv3x3_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV_SMEM_BYTES));
         attr_set = true;
     }
+    ConvParams p = p_in;
     if (p.n % 64 != 0 || p.n > 256 || p.n < 64 || p.kc < 1 || p.kc_in < 1 || p.pairs < 1) {
         cb_set_error("conv3x3: unsupported shape");
         return -1;
     }
+    static const int dbg = getenv("CB_CONV_DEBUG") ? atoi(getenv("CB_CONV_DEBUG")) : 0;  // experiments only
+    if (dbg) p.debug = dbg;
     const int units = (p.pairs + 1) / 2;
-    const int grid = units < num_sms ? units : num_sms;
-    static const int dbg = getenv("CB_CONV_DEBUG") ? atoi(getenv("CB_CONV_DEBUG")) : 0;
-    if (dbg) const_cast<ConvParams&>(p).debug = dbg;
-    conv3x3_tcgen05_kernel<<<grid, CONV_THREADS, CONV_SMEM_BYTES, stream>>>(p);
+    const int max_clusters = num_sms / 2;
+    const int clusters = units < max_clusters ? units : max_clusters;
+    conv3x3_tcgen05_kernel<<<2 * clusters, CONV_THREADS, CONV_SMEM_BYTES, stream>>>(p);
     CB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int conv_timing_read(unsigned long long* out /*[128][8]*/) {
+    CB_CUDA_OK(cudaDeviceSynchronize());
+    CB_CUDA_OK(cudaMemcpyFromSymbol(out, g_conv_timing, sizeof(unsigned long long) * 128 * 8));
     return 0;
 }
 
