@@ -59,7 +59,6 @@ _SIGS = {
     "cb_search_read_roots_sync": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "cb_profile": (i32, [vp, i32]),
     "cb_profile_read_sync": (i32, [vp, vp, vp]),
-    "cb_debug_conv_timing_sync": (i32, [vp, vp]),
     "cb_debug_conv_layer": (i32, [vp, i32, vp, vp, vp, i32, i32, vp]),
 }
 for _name, (_res, _args) in _SIGS.items():

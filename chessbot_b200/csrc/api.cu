@@ -212,7 +212,7 @@ static int pack_conv(Net& net, ConvLayer& L, const std::vector<float>& w, int ci
                 const __nv_bfloat16 hi = __float2bfloat16(wf);
                 for (int h = 0; h < halves; ++h) {
                     const int kc = (ci >> 6) + h * L.kc_in;
-                    packed[conv_weight_index(kc, tap, k, co, N / 2)] =
+                    packed[conv_weight_index(kc, tap, k, co, N)] =
                         h == 0 ? hi : __float2bfloat16(wf - __bfloat162float(hi));
                 }
             }
@@ -362,8 +362,6 @@ int cb_profile_read_sync(cb_ctx* ctx, double* total_ms, int* launches) {
     ctx->prof_used = 0;
     return 0;
 }
-
-int cb_debug_conv_timing_sync(cb_ctx*, uint64_t* out) { return conv_timing_read((unsigned long long*)out); }
 
 int cb_debug_conv_layer(cb_ctx* ctx, int layer, const void* in_act_dev, const void* skip_act_dev, void* out_act_dev, int n_boards,
                         int use_reference, void* stream) {

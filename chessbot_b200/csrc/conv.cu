@@ -1,5 +1,5 @@
 // K2 — 3x3 "same" convolution + BatchNorm + (residual add) + LeakyReLU of the residual tower
-// (model.py:19-28,35-37) as an implicit GEMM on tcgen05 tensor cores, two SMs per MMA.
+// (model.py:19-28,35-37) as an implicit GEMM on tcgen05 tensor cores.
 //
 //   D[m, co] = sum_{tap, ci} A_tap[m, ci] * W[tap][ci][co]      m = (row, board, col) of 2 boards = 128 rows
 //
@@ -8,18 +8,18 @@
 //   into shared memory, and each of the nine taps is just a different start address of the
 //   K-major / no-swizzle UMMA descriptor (LBO 3200 B between the two 8-channel core matrices,
 //   SBO 160 B between 8-pixel groups).
-// * The kernel runs as clusters of two CTAs (one TPC) issuing cta_group::2 MMAs of M = 256: each CTA
-//   owns one board pair (128 accumulator rows in its own TMEM) and stages only HALF of every weight
-//   block (N/2 output channels, pre-packed per (k-chunk, tap, half) as [8][N/2][8] bf16 = one bulk
-//   copy); the tensor cores of the pair read both halves.  That halves the L2->smem weight traffic per
-//   MMA and the shared-memory operand bandwidth per SM.
-// * TMEM holds TWO accumulator stages of 256 columns: while the epilogue drains stage s, the MMAs of the
-//   next unit fill stage s^1, so BN / skip / LeakyReLU / stores overlap the tensor pipe.
-// * Warp roles per CTA: warp 0 = bulk-copy producer; warp 1 = MMA issuer (one lane, leader CTA) or
-//   relay (peer CTA: forwards "my operands have landed" to the leader's barriers); warps 2..9 =
-//   epilogue (tcgen05.ld -> BN scale/shift -> +skip -> LeakyReLU -> bf16 -> HBM in the same tile-native
-//   layout; optionally the three 1x1 head convolutions of model.py:43,52 as dot products over the
-//   fp32 row).  Two epilogue warps share a TMEM lane quarter and split the channel batches.
+// * The kernel runs as clusters of two CTAs that SHARE the weight stream: every (k-chunk, tap) weight
+//   block is pre-packed K-major as [8][N][8] bf16; CTA r fetches its K half (input channels 32r..32r+31,
+//   one contiguous N x 64 B piece) with one bulk copy MULTICAST to both CTAs, so each weight byte leaves
+//   L2 once per cluster.  A slot
+//   is refilled when the MMAs of BOTH CTAs that read it have retired (multicast tcgen05.commit).
+// * Each CTA owns one board pair per accumulator stage (128 x N fp32 in TMEM) and TMEM holds TWO stages:
+//   while the epilogue drains stage s the MMAs of the next board pair fill stage s^1, so BN / skip /
+//   LeakyReLU / stores overlap the tensor pipe.
+// * Warp roles per CTA: warp 0 = bulk-copy producer, warp 1 = MMA issuer (one lane) + TMEM owner,
+//   warps 2..9 = epilogue (tcgen05.ld -> BN scale/shift -> +skip -> LeakyReLU -> bf16 -> HBM in the same
+//   tile-native layout; optionally the three 1x1 head convolutions of model.py:43,52 as dot products
+//   over the fp32 row).  Two epilogue warps share a TMEM lane quarter and split the channel batches.
 #include <stdlib.h>
 
 #include "kernels.cuh"
@@ -27,14 +27,14 @@
 namespace cb {
 
 constexpr int CONV_THREADS = 320;
-constexpr int A_SLOTS = 3, B_SLOTS = 8;
+constexpr int A_SLOTS = 3, B_SLOTS = 4;
 constexpr int A_SLOT_BYTES = ACT_K64_BYTES;  // one board pair x 64 channels
-constexpr int B_SLOT_BYTES = 128 * 128;      // N/2 <= 128 rows x 64 k x bf16
+constexpr int B_SLOT_BYTES = 256 * 128;      // N <= 256 rows x 64 k x bf16 (two K halves)
 constexpr int EPI_WARPS = 8;
 
 struct ConvSmem {
-    uint64_t a_full[A_SLOTS], a_peer[A_SLOTS], a_empty[A_SLOTS];
-    uint64_t b_full[B_SLOTS], b_peer[B_SLOTS], b_empty[B_SLOTS];
+    uint64_t a_full[A_SLOTS], a_empty[A_SLOTS];
+    uint64_t b_full[B_SLOTS], b_empty[B_SLOTS];
     uint64_t acc_full[2], acc_empty[2];
     uint32_t tmem_base;
     uint32_t pad_;
@@ -42,19 +42,6 @@ struct ConvSmem {
 static_assert(sizeof(ConvSmem) <= 1024, "barrier block");
 constexpr int CONV_SMEM_PARAM_FLOATS = 256 * 2 + 256 * 3 + 2 * 128 * 3;
 constexpr size_t CONV_SMEM_BYTES = 1024 + A_SLOTS * A_SLOT_BYTES + B_SLOTS * B_SLOT_BYTES + CONV_SMEM_PARAM_FLOATS * 4;
-
-// experiments only (CB_CONV_DEBUG & 128): cycles the MMA issuer spends waiting, per barrier class, per cluster
-__device__ unsigned long long g_conv_timing[128][8];
-#define TIMED_WAIT(slot, stmt)                                   \
-    do {                                                         \
-        if (p.debug & 128) {                                     \
-            const long long t0_ = clock64();                     \
-            stmt;                                                \
-            tw[slot] += (unsigned long long)(clock64() - t0_);   \
-        } else {                                                 \
-            stmt;                                                \
-        }                                                        \
-    } while (0)
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) conv3x3_tcgen05_kernel(ConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -65,13 +52,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) con
     float* s_shift = s_scale + 256;
     float* s_head = s_shift + 256;
     float* s_hpart = s_head + 768;  // [2 stages][128 rows][3]
-    __shared__ long long s_tissue[B_SLOTS];  // experiments only
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = ptx::cluster_ctarank();
     const int cid = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
     const int units = (p.pairs + 1) / 2;  // one unit = two board pairs = one M=256 accumulator stage
-    const int n = p.n, nh = n >> 1;
+    const int n = p.n;
 
     for (int i = threadIdx.x; i < n; i += CONV_THREADS) {
         s_scale[i] = p.scale[i];
@@ -83,21 +69,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) con
         }
     }
     if (threadIdx.x == 0) {
-        for (int i = 0; i < A_SLOTS; ++i) { ptx::mbar_init(&s->a_full[i], 1); ptx::mbar_init(&s->a_peer[i], 1); ptx::mbar_init(&s->a_empty[i], 1); }
-        for (int i = 0; i < B_SLOTS; ++i) { ptx::mbar_init(&s->b_full[i], 1); ptx::mbar_init(&s->b_peer[i], 1); ptx::mbar_init(&s->b_empty[i], 1); }
+        for (int i = 0; i < A_SLOTS; ++i) { ptx::mbar_init(&s->a_full[i], 1); ptx::mbar_init(&s->a_empty[i], 1); }
+        for (int i = 0; i < B_SLOTS; ++i) { ptx::mbar_init(&s->b_full[i], 1); ptx::mbar_init(&s->b_empty[i], 2); }  // freed by both CTAs' MMAs
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&s->acc_full[i], 1);
-            ptx::mbar_init(&s->acc_empty[i], 2 * EPI_WARPS);  // every epilogue warp of both CTAs
+            ptx::mbar_init(&s->acc_empty[i], EPI_WARPS);
         }
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
-        ptx::tmem_alloc2(&s->tmem_base, 512);
-        ptx::tmem_relinquish2();
+        ptx::tmem_alloc(&s->tmem_base, 512);
+        ptx::tmem_relinquish();
     }
     ptx::tc_fence_before();
     __syncthreads();
-    ptx::cluster_sync();  // barriers of both CTAs are initialised before any remote arrive / multicast commit
+    ptx::cluster_sync();  // barriers of both CTAs are initialised before any multicast copy / commit reaches them
     ptx::tc_fence_after();
     const uint32_t tmem = s->tmem_base;
 
@@ -105,9 +91,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) con
         // ------------------------------------------------------------------ producer (both CTAs)
         if (lane == 0) {
             uint32_t a_it = 0, b_it = 0;
-            const uint32_t b_bytes = (uint32_t)nh * 128;
+            const uint32_t h_bytes = (uint32_t)n * 64;  // one K-half (32 of the 64 input channels) of a weight block
             for (int u = cid; u < units; u += nclusters) {
-                const int pair = min(2 * u + (int)rank, p.pairs - 1);  // odd tail: the peer re-reads the last pair, its result is dropped
+                const int pair = min(2 * u + (int)rank, p.pairs - 1);  // odd tail: this CTA re-reads the last pair, its result is dropped
                 for (int kc = 0; kc < p.kc; ++kc) {
                     const int as = a_it % A_SLOTS;
                     ptx::mbar_wait(&s->a_empty[as], ((a_it / A_SLOTS) & 1) ^ 1);
@@ -124,10 +110,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) con
                         ptx::mbar_wait(&s->b_empty[bs], ((b_it / B_SLOTS) & 1) ^ 1);
                         if (p.debug & 8) ptx::mbar_arrive(&s->b_full[bs]);
                         else {
-                            ptx::mbar_expect_tx(&s->b_full[bs], b_bytes);
-                            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wgt) + ((size_t)(kc * 9 + tap) * 2 + rank) * b_bytes;
-                            if (p.debug & 128) s_tissue[bs] = clock64();
-                            ptx::bulk_g2s(b_buf + bs * B_SLOT_BYTES, src, b_bytes, &s->b_full[bs]);
+                            // this CTA will receive both halves (its own copy + the peer's multicast)
+                            ptx::mbar_expect_tx(&s->b_full[bs], 2 * h_bytes);
+                            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wgt) + ((size_t)(kc * 9 + tap) * 2 + rank) * h_bytes;  // [kc][tap][8][N][8]: K halves are contiguous
+                            ptx::bulk_g2s_multicast(b_buf + bs * B_SLOT_BYTES + rank * h_bytes, src, h_bytes, &s->b_full[bs], 3);
                         }
                         ++b_it;
                     }
@@ -135,26 +121,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) con
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {
-            // -------------------------------------------------------------- MMA issuer (leader CTA)
-            const uint32_t idesc = ptx::idesc_bf16_f32(256, n);
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = ptx::idesc_bf16_f32(128, n);
             uint32_t a_it = 0, b_it = 0, u_it = 0;
-            unsigned long long tw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            const long long t_start = clock64();
             for (int u = cid; u < units; u += nclusters, ++u_it) {
                 const uint32_t st = u_it & 1;
-                TIMED_WAIT(1, ptx::mbar_wait_cluster(&s->acc_empty[st], ((u_it >> 1) & 1) ^ 1));
+                ptx::mbar_wait(&s->acc_empty[st], ((u_it >> 1) & 1) ^ 1);
                 ptx::tc_fence_after();
                 const uint32_t d = tmem + st * 256;
                 for (int kc = 0; kc < p.kc; ++kc) {
                     const int as = a_it % A_SLOTS;
-                    TIMED_WAIT(2, ptx::mbar_wait(&s->a_full[as], (a_it / A_SLOTS) & 1));
-                    if (!(p.debug & 64)) TIMED_WAIT(3, ptx::mbar_wait_cluster(&s->a_peer[as], (a_it / A_SLOTS) & 1));
+                    ptx::mbar_wait(&s->a_full[as], (a_it / A_SLOTS) & 1);
                     const uint32_t a_base = ptx::smem_u32(a_buf + as * A_SLOT_BYTES);
                     for (int tap = 0; tap < 9; ++tap) {
                         const int bs = b_it % B_SLOTS;
-                        TIMED_WAIT(4, ptx::mbar_wait(&s->b_full[bs], (b_it / B_SLOTS) & 1));
-                        if (!(p.debug & 64)) TIMED_WAIT(5, ptx::mbar_wait_cluster(&s->b_peer[bs], (b_it / B_SLOTS) & 1));
+                        ptx::mbar_wait(&s->b_full[bs], (b_it / B_SLOTS) & 1);
                         ptx::tc_fence_after();
                         const uint32_t b_base = ptx::smem_u32(b_buf + bs * B_SLOT_BYTES);
                         const int dy = tap / 3 - 1, dx = tap % 3 - 1;
@@ -163,43 +145,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) con
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks) {
                                 const uint64_t ad = ptx::smem_desc(a_tap + ks * 2 * ACT_CHUNK_BYTES, ACT_CHUNK_BYTES, 160);
-                                const uint64_t bd = ptx::smem_desc(b_base + ks * 2 * nh * 16, (uint32_t)nh * 16, 128);
-                                ptx::umma2_bf16(d, ad, bd, idesc, (kc | tap | ks) != 0);
+                                const uint64_t bd = ptx::smem_desc(b_base + ks * 2 * n * 16, (uint32_t)n * 16, 128);
+                                ptx::umma_bf16(d, ad, bd, idesc, (kc | tap | ks) != 0);
                             }
                         }
-                        ptx::umma2_commit_mc(&s->b_empty[bs]);  // weight stage of BOTH CTAs is free when these MMAs retire
+                        ptx::umma_commit_mc(&s->b_empty[bs], 3);  // tell BOTH producers: this CTA is done with the slot
                         ++b_it;
                     }
-                    ptx::umma2_commit_mc(&s->a_empty[as]);
+                    ptx::umma_commit(&s->a_empty[as]);
                     ++a_it;
                 }
-                ptx::umma2_commit_mc(&s->acc_full[st]);
+                ptx::umma_commit(&s->acc_full[st]);
             }
-            if (p.debug & 128) {
-                tw[0] = (unsigned long long)(clock64() - t_start);
-                for (int i = 0; i < 6; ++i) g_conv_timing[cid & 127][i] = tw[i];
-            }
-        } else if (lane == 0) {
-            // -------------------------------------------------------------- relay (peer CTA)
-            uint32_t a_it = 0, b_it = 0;
-            unsigned long long lat_sum = 0, lat_n = 0;
-            const uint32_t a_peer0 = ptx::mapa(ptx::smem_u32(&s->a_peer[0]), 0), b_peer0 = ptx::mapa(ptx::smem_u32(&s->b_peer[0]), 0);
-            for (int u = cid; u < units; u += nclusters) {
-                for (int kc = 0; kc < p.kc; ++kc) {
-                    const int as = a_it % A_SLOTS;
-                    ptx::mbar_wait(&s->a_full[as], (a_it / A_SLOTS) & 1);
-                    ptx::mbar_arrive_remote(a_peer0 + as * 8);
-                    ++a_it;
-                    for (int tap = 0; tap < 9; ++tap) {
-                        const int bs = b_it % B_SLOTS;
-                        ptx::mbar_wait(&s->b_full[bs], (b_it / B_SLOTS) & 1);
-                        if (p.debug & 128) { lat_sum += (unsigned long long)(clock64() - s_tissue[bs]); ++lat_n; }
-                        ptx::mbar_arrive_remote(b_peer0 + bs * 8);
-                        ++b_it;
-                    }
-                }
-            }
-            if (p.debug & 128) { g_conv_timing[cid & 127][6] = lat_sum; g_conv_timing[cid & 127][7] = lat_n; }
         }
     } else {
         // ------------------------------------------------------------------ epilogue (warps 2..9, both CTAs)
@@ -214,7 +171,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) con
         const int cjo = n >> 3, ncb = n >> 5;
         const int nk = (ncb - h + 1) >> 1;  // batches of this warp: cb = h + 2k
         const bool has_skip = p.skip != nullptr && !(p.debug & 2);
-        const uint32_t acc_empty0 = ptx::mapa(ptx::smem_u32(&s->acc_empty[0]), 0);
         uint32_t u_it = 0;
         for (int u = cid; u < units; u += nclusters, ++u_it) {
             const uint32_t st = u_it & 1;
@@ -282,7 +238,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) con
             // the accumulator stage is drained: hand it back to the MMA issuer before the head bookkeeping
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive_remote(acc_empty0 + st * 8);
+            if (lane == 0) ptx::mbar_arrive(&s->acc_empty[st]);
             if (p.head_w) {
                 // the two warps of a lane quarter hold partial dot products over their channel batches
                 float* hp = s_hpart + ((size_t)st * 128 + m) * 3;
@@ -297,8 +253,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) con
     }
     ptx::tc_fence_before();
     __syncthreads();
-    ptx::cluster_sync();  // the peer may still be reading this CTA's shared memory / signalling its barriers
-    if (warp == 1) ptx::tmem_dealloc2(tmem, 512);
+    ptx::cluster_sync();  // the peer's multicast copies / commits may still target this CTA
+    if (warp == 1) ptx::tmem_dealloc(tmem, 512);
 }
 
 // Plain CUDA-core restatement of the same layer on the same bf16 inputs (fp32 accumulate).  Test
@@ -306,7 +262,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) con
 __global__ void conv3x3_reference_kernel(ConvParams p) {
     const int boards = p.pairs * 2;
     const size_t total = (size_t)boards * 64 * p.n;
-    const int cjo = p.n >> 3, nh = p.n >> 1;
+    const int cjo = p.n >> 3;
     for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const int co = (int)(idx % p.n);
         const int sq = (int)((idx / p.n) % 64);
@@ -321,7 +277,7 @@ __global__ void conv3x3_reference_kernel(ConvParams p) {
                 const __nv_bfloat16 a = *reinterpret_cast<const __nv_bfloat16*>(
                     reinterpret_cast<const uint8_t*>(p.in) + act_offset_bytes(pair, p.cj_in, cin >> 3, cell) + (cin & 7) * 2);
                 const int kc = ci >> 6, k = ci & 63;
-                const __nv_bfloat16 w = p.wgt[conv_weight_index(kc, tap, k, co, nh)];
+                const __nv_bfloat16 w = p.wgt[conv_weight_index(kc, tap, k, co, p.n)];
                 acc = fmaf(__bfloat162float(a), __bfloat162float(w), acc);
             }
         }
@@ -351,12 +307,6 @@ int launch_conv3x3(const ConvParams& p_in, int num_sms, cudaStream_t stream) {
     const int clusters = units < max_clusters ? units : max_clusters;
     conv3x3_tcgen05_kernel<<<2 * clusters, CONV_THREADS, CONV_SMEM_BYTES, stream>>>(p);
     CB_CUDA_OK(cudaGetLastError());
-    return 0;
-}
-
-int conv_timing_read(unsigned long long* out /*[128][8]*/) {
-    CB_CUDA_OK(cudaDeviceSynchronize());
-    CB_CUDA_OK(cudaMemcpyFromSymbol(out, g_conv_timing, sizeof(unsigned long long) * 128 * 8));
     return 0;
 }
 

@@ -10,7 +10,7 @@ struct ConvParams {
     const __nv_bfloat16* in;    // tile-native, cj_in chunks
     __nv_bfloat16* out;         // tile-native, n/8 chunks
     const __nv_bfloat16* skip;  // tile-native like out, or nullptr
-    const __nv_bfloat16* wgt;   // [kc][tap][half][8][n/2][8], see conv_weight_index
+    const __nv_bfloat16* wgt;   // [kc][tap][8][n][8], see conv_weight_index
     const float* scale;         // [n] gamma / sqrt(var + eps)
     const float* shift;         // [n] beta - mean * scale
     const float* head_w;        // [3][n] 1x1 head conv weights (value, policy0, policy1) or nullptr
@@ -24,11 +24,10 @@ struct ConvParams {
     int debug;                  // experiments only (CB_CONV_DEBUG): 1 no epilogue, 2 no skip loads, 4 no MMAs, 8 no weight loads, 16 no stores
 };
 
-// Packed weight layout: per (k-chunk of 64 input channels, tap) two halves of N/2 output channels, each a
-// K-major / no-swizzle block [k/8][N/2][k%8] = the B operand one CTA of the pair stages with one bulk copy.
-__host__ __device__ inline size_t conv_weight_index(int kc, int tap, int k /*0..63*/, int co, int nh /*N/2*/) {
-    const int half = co >= nh, c = co - half * nh;
-    return ((size_t)((kc * 9 + tap) * 2 + half) * 8 + (k >> 3)) * nh * 8 + (size_t)c * 8 + (k & 7);
+// Packed weight layout [kc][tap][k/8][N][k%8]: per (k-chunk of 64 input channels, tap) one K-major / no-swizzle
+// block = the B operand of four K=16 MMAs; its two K halves (k < 32, k >= 32) are contiguous N x 64 B pieces.
+__host__ __device__ inline size_t conv_weight_index(int kc, int tap, int k /*0..63*/, int co, int n) {
+    return ((size_t)(kc * 9 + tap) * 8 + (k >> 3)) * n * 8 + (size_t)co * 8 + (k & 7);
 }
 
 struct HeadParams {
@@ -92,7 +91,6 @@ struct SearchParams {
 };
 
 int launch_conv3x3(const ConvParams& p, int num_sms, cudaStream_t stream);
-int conv_timing_read(unsigned long long* out);
 int launch_conv3x3_reference(const ConvParams& p, cudaStream_t stream);
 int launch_encode(const Pos* pos_base, const int32_t* frame_idx, int n, __nv_bfloat16* planes_act, int16_t* planes_i16, cudaStream_t stream);
 int launch_head_features(const HeadParams& p, int boards, cudaStream_t stream);

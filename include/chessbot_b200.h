@@ -137,10 +137,6 @@ int cb_profile_read_sync(cb_ctx* ctx, double* total_ms /*[CB_PROF_STAGES]*/, int
 int cb_debug_conv_layer(cb_ctx* ctx, int layer, const void* in_act_dev, const void* skip_act_dev, void* out_act_dev,
                         int n_boards, int use_reference, void* stream);
 
-/* experiments only: with CB_CONV_DEBUG & 128, cycles the MMA issuer of each cluster spent per barrier class:
- * out[128][8] = {total, acc_empty, a_full, a_peer, b_full, b_peer, 0, 0} */
-int cb_debug_conv_timing_sync(cb_ctx* ctx, uint64_t* out);
-
 #ifdef __cplusplus
 }
 #endif

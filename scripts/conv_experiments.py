@@ -26,10 +26,3 @@ for name, layer, skip in (("conv", 1, None), ("conv+skip", 2, sk)):
     us = e0.elapsed_time(e1) / reps * 1e3
     fl = 2 * 64 * 9 * filters * filters * boards
     print(f"CB_CONV_DEBUG={os.environ.get('CB_CONV_DEBUG','0'):>3s} {name:10s} {us:8.1f} us  {fl / us / 1e6:8.1f} TFLOP/s")
-    if int(os.environ.get("CB_CONV_DEBUG", "0")) & 128:
-        t = np.zeros((128, 8), dtype=np.uint64)
-        lib.cb_debug_conv_timing_sync(eng._h, t.ctypes.data)
-        t = t[:74].astype(np.float64)
-        names = ["total", "acc_empty", "a_full", "a_peer", "b_full", "b_peer"]
-        print("   MMA-issuer cycles per launch (mean over clusters): " + ", ".join(f"{k}={t[:, i].mean():.0f}" for i, k in enumerate(names))
-              + f"; issue+other={(t[:,0]-t[:,1:6].sum(1)).mean():.0f}; max total={t[:,0].max():.0f}; peer B copy issue->landed(relay sees) = {(t[:,6]/np.maximum(t[:,7],1)).mean():.0f} cycles")
