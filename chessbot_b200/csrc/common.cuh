@@ -42,6 +42,13 @@ inline size_t act_bytes(int boards, int channels) { return (size_t)((boards + 1)
 #if defined(__CUDACC__)
 namespace ptx {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// one lane of a fully converged warp (always the same one): the warp runs the role's control flow together
+// so that addresses and descriptors stay in uniform registers, and only the async instruction is predicated
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -120,6 +127,18 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask)
                      smem_u32(bar)),
                  "h"(cta_mask)
                  : "memory");
+}
+// TMA tile load (2-D tensor map, rows of 128 B) into this CTA's shared memory; with .cta_group::2 the
+// transaction bytes may complete on a barrier of the PEER CTA, given by its shared::cluster address
+__device__ __forceinline__ void tma_load_2d_pair(void* dst_smem, const void* tensor_map, int c0, int c1, uint32_t bar_cluster_addr) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(tensor_map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tensor_map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tensor_map) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)

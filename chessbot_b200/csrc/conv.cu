@@ -1,5 +1,5 @@
 // K2 — 3x3 "same" convolution + BatchNorm + (residual add) + LeakyReLU of the residual tower
-// (model.py:19-28,35-37) as an implicit GEMM on tcgen05 tensor cores.
+// (model.py:19-28,35-37) as an implicit GEMM on tcgen05 tensor cores, two SMs per MMA.
 //
 //   D[m, co] = sum_{tap, ci} A_tap[m, ci] * W[tap][ci][co]      m = (row, board, col) of 2 boards = 128 rows
 //
@@ -8,18 +8,18 @@
 //   into shared memory, and each of the nine taps is just a different start address of the
 //   K-major / no-swizzle UMMA descriptor (LBO 3200 B between the two 8-channel core matrices,
 //   SBO 160 B between 8-pixel groups).
-// * The kernel runs as clusters of two CTAs that SHARE the weight stream: every (k-chunk, tap) weight
-//   block is pre-packed K-major as [8][N][8] bf16; CTA r fetches its K half (input channels 32r..32r+31,
-//   one contiguous N x 64 B piece) with one bulk copy MULTICAST to both CTAs, so each weight byte leaves
-//   L2 once per cluster.  A slot
-//   is refilled when the MMAs of BOTH CTAs that read it have retired (multicast tcgen05.commit).
-// * Each CTA owns one board pair per accumulator stage (128 x N fp32 in TMEM) and TMEM holds TWO stages:
-//   while the epilogue drains stage s the MMAs of the next board pair fill stage s^1, so BN / skip /
-//   LeakyReLU / stores overlap the tensor pipe.
-// * Warp roles per CTA: warp 0 = bulk-copy producer, warp 1 = MMA issuer (one lane) + TMEM owner,
-//   warps 2..9 = epilogue (tcgen05.ld -> BN scale/shift -> +skip -> LeakyReLU -> bf16 -> HBM in the same
-//   tile-native layout; optionally the three 1x1 head convolutions of model.py:43,52 as dot products
-//   over the fp32 row).  Two epilogue warps share a TMEM lane quarter and split the channel batches.
+// * The kernel runs as clusters of two CTAs (one TPC) issuing cta_group::2 MMAs of M = 256: each CTA
+//   owns one board pair (128 accumulator rows in its own TMEM) and stages only HALF of every weight
+//   block (N/2 output channels, pre-packed per (k-chunk, tap, half) as [8][N/2][8] bf16 = one bulk
+//   copy); the tensor cores of the pair read both halves.  That halves the L2->smem weight traffic per
+//   MMA and the shared-memory operand bandwidth per SM.
+// * TMEM holds TWO accumulator stages of 256 columns: while the epilogue drains stage s, the MMAs of the
+//   next unit fill stage s^1, so BN / skip / LeakyReLU / stores overlap the tensor pipe.
+// * Warp roles per CTA: warp 0 = bulk-copy producer; warp 1 = MMA issuer (one lane of the leader
+//   CTA; the bulk copies of both CTAs complete on the leader's barriers); warps 2..9 =
+//   epilogue (tcgen05.ld -> BN scale/shift -> +skip -> LeakyReLU -> bf16 -> HBM in the same tile-native
+//   layout; optionally the three 1x1 head convolutions of model.py:43,52 as dot products over the
+//   fp32 row).  Two epilogue warps share a TMEM lane quarter and split the channel batches.
 #include <stdlib.h>
 
 #include "kernels.cuh"
@@ -27,9 +27,9 @@
 namespace cb {
 
 constexpr int CONV_THREADS = 320;
-constexpr int A_SLOTS = 3, B_SLOTS = 4;
+constexpr int A_SLOTS = 3, B_SLOTS = 8;
 constexpr int A_SLOT_BYTES = ACT_K64_BYTES;  // one board pair x 64 channels
-constexpr int B_SLOT_BYTES = 256 * 128;      // N <= 256 rows x 64 k x bf16 (two K halves)
+constexpr int B_SLOT_BYTES = 128 * 128;      // N/2 <= 128 rows x 64 k x bf16
 constexpr int EPI_WARPS = 8;
 
 struct ConvSmem {
@@ -43,7 +43,7 @@ static_assert(sizeof(ConvSmem) <= 1024, "barrier block");
 constexpr int CONV_SMEM_PARAM_FLOATS = 256 * 2 + 256 * 3 + 2 * 128 * 3;
 constexpr size_t CONV_SMEM_BYTES = 1024 + A_SLOTS * A_SLOT_BYTES + B_SLOTS * B_SLOT_BYTES + CONV_SMEM_PARAM_FLOATS * 4;
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) conv3x3_tcgen05_kernel(ConvParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) conv3x3_tcgen05_kernel(const __grid_constant__ ConvParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     ConvSmem* s = reinterpret_cast<ConvSmem*>(smem);
     uint8_t* a_buf = smem + 1024;
@@ -57,7 +57,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) con
     const uint32_t rank = ptx::cluster_ctarank();
     const int cid = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
     const int units = (p.pairs + 1) / 2;  // one unit = two board pairs = one M=256 accumulator stage
-    const int n = p.n;
+    const int n = p.n, nh = n >> 1;
 
     for (int i = threadIdx.x; i < n; i += CONV_THREADS) {
         s_scale[i] = p.scale[i];
@@ -70,60 +70,71 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) con
     }
     if (threadIdx.x == 0) {
         for (int i = 0; i < A_SLOTS; ++i) { ptx::mbar_init(&s->a_full[i], 1); ptx::mbar_init(&s->a_empty[i], 1); }
-        for (int i = 0; i < B_SLOTS; ++i) { ptx::mbar_init(&s->b_full[i], 1); ptx::mbar_init(&s->b_empty[i], 2); }  // freed by both CTAs' MMAs
+        for (int i = 0; i < B_SLOTS; ++i) { ptx::mbar_init(&s->b_full[i], 1); ptx::mbar_init(&s->b_empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&s->acc_full[i], 1);
-            ptx::mbar_init(&s->acc_empty[i], EPI_WARPS);
+            ptx::mbar_init(&s->acc_empty[i], 2 * EPI_WARPS);  // every epilogue warp of both CTAs
         }
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
-        ptx::tmem_alloc(&s->tmem_base, 512);
-        ptx::tmem_relinquish();
+        ptx::tmem_alloc2(&s->tmem_base, 512);
+        ptx::tmem_relinquish2();
     }
     ptx::tc_fence_before();
     __syncthreads();
-    ptx::cluster_sync();  // barriers of both CTAs are initialised before any multicast copy / commit reaches them
+    ptx::cluster_sync();  // barriers of both CTAs are initialised before any remote arrive / multicast commit
     ptx::tc_fence_after();
     const uint32_t tmem = s->tmem_base;
 
     if (warp == 0) {
-        // ------------------------------------------------------------------ producer (both CTAs)
-        if (lane == 0) {
-            uint32_t a_it = 0, b_it = 0;
-            const uint32_t h_bytes = (uint32_t)n * 64;  // one K-half (32 of the 64 input channels) of a weight block
-            for (int u = cid; u < units; u += nclusters) {
-                const int pair = min(2 * u + (int)rank, p.pairs - 1);  // odd tail: this CTA re-reads the last pair, its result is dropped
-                for (int kc = 0; kc < p.kc; ++kc) {
-                    const int as = a_it % A_SLOTS;
-                    ptx::mbar_wait(&s->a_empty[as], ((a_it / A_SLOTS) & 1) ^ 1);
-                    if (p.debug & 32) ptx::mbar_arrive(&s->a_full[as]);
+        // ------------------------------------------------------------------ producer (both CTAs; whole warp, one elected lane issues)
+        uint32_t a_it = 0, b_it = 0;
+        const uint32_t b_bytes = (uint32_t)nh * 128;
+        // operands of BOTH CTAs complete on the leader's "full" barriers (the MMA issuer lives there)
+        const uint32_t a_full0 = ptx::mapa(ptx::smem_u32(&s->a_full[0]), 0), b_full0 = ptx::mapa(ptx::smem_u32(&s->b_full[0]), 0);
+        if (ptx::elect_one()) {
+            ptx::tma_prefetch_desc(&p.tm_in);
+            ptx::tma_prefetch_desc(&p.tm_w);
+        }
+        for (int u = cid; u < units; u += nclusters) {
+            const int pair = min(2 * u + (int)rank, p.pairs - 1);  // odd tail: the peer re-reads the last pair, its result is dropped
+            for (int kc = 0; kc < p.kc; ++kc) {
+                const int as = a_it % A_SLOTS;
+                ptx::mbar_wait(&s->a_empty[as], ((a_it / A_SLOTS) & 1) ^ 1);
+                if (ptx::elect_one()) {
+                    if (p.debug & 32) { if (rank == 0) ptx::mbar_arrive(&s->a_full[as]); }
                     else {
-                        ptx::mbar_expect_tx(&s->a_full[as], ACT_K64_BYTES);
-                        const uint8_t* src = reinterpret_cast<const uint8_t*>(p.in) +
-                                             ((size_t)pair * p.cj_in + 8 * (kc % p.kc_in)) * ACT_CHUNK_BYTES;
-                        ptx::bulk_g2s(a_buf + as * A_SLOT_BYTES, src, ACT_K64_BYTES, &s->a_full[as]);
+                        if (rank == 0) ptx::mbar_expect_tx(&s->a_full[as], 2 * ACT_K64_BYTES);
+                        ptx::tma_load_2d_pair(a_buf + as * A_SLOT_BYTES, &p.tm_in, 0, (pair * p.cj_in + 8 * (kc % p.kc_in)) * (ACT_CHUNK_BYTES / 128),
+                                              a_full0 + as * 8);
                     }
-                    ++a_it;
-                    for (int tap = 0; tap < 9; ++tap) {
-                        const int bs = b_it % B_SLOTS;
-                        ptx::mbar_wait(&s->b_empty[bs], ((b_it / B_SLOTS) & 1) ^ 1);
-                        if (p.debug & 8) ptx::mbar_arrive(&s->b_full[bs]);
+                }
+                ++a_it;
+                const int wrow = (kc * 9 * 2 + (int)rank) * nh;
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int bs = b_it % B_SLOTS;
+                    ptx::mbar_wait(&s->b_empty[bs], ((b_it / B_SLOTS) & 1) ^ 1);
+                    if (ptx::elect_one()) {
+                        if (p.debug & 8) { if (rank == 0) ptx::mbar_arrive(&s->b_full[bs]); }
                         else {
-                            // this CTA will receive both halves (its own copy + the peer's multicast)
-                            ptx::mbar_expect_tx(&s->b_full[bs], 2 * h_bytes);
-                            const uint8_t* src = reinterpret_cast<const uint8_t*>(p.wgt) + ((size_t)(kc * 9 + tap) * 2 + rank) * h_bytes;  // [kc][tap][8][N][8]: K halves are contiguous
-                            ptx::bulk_g2s_multicast(b_buf + bs * B_SLOT_BYTES + rank * h_bytes, src, h_bytes, &s->b_full[bs], 3);
+                            if (rank == 0) ptx::mbar_expect_tx(&s->b_full[bs], 2 * b_bytes);
+                            ptx::tma_load_2d_pair(b_buf + bs * B_SLOT_BYTES, &p.tm_w, 0, wrow + tap * 2 * nh, b_full0 + bs * 8);
                         }
-                        ++b_it;
                     }
+                    ++b_it;
                 }
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            const uint32_t idesc = ptx::idesc_bf16_f32(128, n);
+        if (rank == 0) {
+            // -------------------------------------------------------------- MMA issuer (leader CTA; whole warp, one elected lane issues)
+            const uint32_t idesc = ptx::idesc_bf16_f32(256, n);
+            // K-major / no-swizzle descriptors: hi word = SBO | version, lo word = address | LBO; a K=16 step adds to the address field only
+            const uint64_t a_desc0 = ptx::smem_desc(ptx::smem_u32(a_buf), ACT_CHUNK_BYTES, 160);
+            const uint64_t b_desc0 = ptx::smem_desc(ptx::smem_u32(b_buf), (uint32_t)nh * 16, 128);
+            const uint32_t a_ks = 2 * ACT_CHUNK_BYTES / 16, b_ks = 2 * nh;  // descriptor address units of 16 B
             uint32_t a_it = 0, b_it = 0, u_it = 0;
             for (int u = cid; u < units; u += nclusters, ++u_it) {
                 const uint32_t st = u_it & 1;
@@ -133,29 +144,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) con
                 for (int kc = 0; kc < p.kc; ++kc) {
                     const int as = a_it % A_SLOTS;
                     ptx::mbar_wait(&s->a_full[as], (a_it / A_SLOTS) & 1);
-                    const uint32_t a_base = ptx::smem_u32(a_buf + as * A_SLOT_BYTES);
+                    const uint64_t a_desc = a_desc0 + (uint64_t)(as * (A_SLOT_BYTES / 16));
+#pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
                         const int bs = b_it % B_SLOTS;
                         ptx::mbar_wait(&s->b_full[bs], (b_it / B_SLOTS) & 1);
                         ptx::tc_fence_after();
-                        const uint32_t b_base = ptx::smem_u32(b_buf + bs * B_SLOT_BYTES);
-                        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-                        const uint32_t a_tap = a_base + (uint32_t)(((1 + dy) * 20 + 1 + dx) * 16);
-                        if (!(p.debug & 4)) {
+                        const uint64_t bd0 = b_desc0 + (uint64_t)(bs * (B_SLOT_BYTES / 16));
+                        const uint64_t ad0 = a_desc + (uint64_t)((tap / 3) * 20 + (tap % 3));  // tap (dy, dx): start cell (1+dy)*20 + 1+dx
+                        if (ptx::elect_one()) {
+                            if (!(p.debug & 4)) {
 #pragma unroll
-                            for (int ks = 0; ks < 4; ++ks) {
-                                const uint64_t ad = ptx::smem_desc(a_tap + ks * 2 * ACT_CHUNK_BYTES, ACT_CHUNK_BYTES, 160);
-                                const uint64_t bd = ptx::smem_desc(b_base + ks * 2 * n * 16, (uint32_t)n * 16, 128);
-                                ptx::umma_bf16(d, ad, bd, idesc, (kc | tap | ks) != 0);
+                                for (int ks = 0; ks < 4; ++ks)
+                                    ptx::umma2_bf16(d, ad0 + ks * a_ks, bd0 + ks * b_ks, idesc, (kc | tap | ks) != 0);
                             }
+                            ptx::umma2_commit_mc(&s->b_empty[bs]);  // weight stage of BOTH CTAs is free when these MMAs retire
                         }
-                        ptx::umma_commit_mc(&s->b_empty[bs], 3);  // tell BOTH producers: this CTA is done with the slot
+                        __syncwarp();
                         ++b_it;
                     }
-                    ptx::umma_commit(&s->a_empty[as]);
+                    if (ptx::elect_one()) ptx::umma2_commit_mc(&s->a_empty[as]);
+                    __syncwarp();
                     ++a_it;
                 }
-                ptx::umma_commit(&s->acc_full[st]);
+                if (ptx::elect_one()) ptx::umma2_commit_mc(&s->acc_full[st]);
+                __syncwarp();
             }
         }
     } else {
@@ -171,6 +184,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) con
         const int cjo = n >> 3, ncb = n >> 5;
         const int nk = (ncb - h + 1) >> 1;  // batches of this warp: cb = h + 2k
         const bool has_skip = p.skip != nullptr && !(p.debug & 2);
+        const uint32_t acc_empty0 = ptx::mapa(ptx::smem_u32(&s->acc_empty[0]), 0);
         uint32_t u_it = 0;
         for (int u = cid; u < units; u += nclusters, ++u_it) {
             const uint32_t st = u_it & 1;
@@ -238,7 +252,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) con
             // the accumulator stage is drained: hand it back to the MMA issuer before the head bookkeeping
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&s->acc_empty[st]);
+            if (lane == 0) ptx::mbar_arrive_remote(acc_empty0 + st * 8);
             if (p.head_w) {
                 // the two warps of a lane quarter hold partial dot products over their channel batches
                 float* hp = s_hpart + ((size_t)st * 128 + m) * 3;
@@ -253,8 +267,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) con
     }
     ptx::tc_fence_before();
     __syncthreads();
-    ptx::cluster_sync();  // the peer's multicast copies / commits may still target this CTA
-    if (warp == 1) ptx::tmem_dealloc(tmem, 512);
+    ptx::cluster_sync();  // the peer may still be reading this CTA's shared memory / signalling its barriers
+    if (warp == 1) ptx::tmem_dealloc2(tmem, 512);
 }
 
 // Plain CUDA-core restatement of the same layer on the same bf16 inputs (fp32 accumulate).  Test
@@ -289,6 +303,29 @@ __global__ void conv3x3_reference_kernel(ConvParams p) {
     }
 }
 
+// 2-D tensor map over a buffer seen as `rows` rows of 128 B (64 bf16), box = box_rows whole rows, no swizzle:
+// the tile lands in shared memory byte for byte as it lies in HBM.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int make_row_map(CUtensorMap* tm, const void* base, uint64_t rows, uint32_t box_rows) {
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CB_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) { cb_set_error("cuTensorMapEncodeTiled not available"); return -1; }
+        encode = (EncodeTiledFn)fn;
+    }
+    const cuuint64_t dims[2] = {64, rows};
+    const cuuint64_t strides[1] = {128};
+    const cuuint32_t box[2] = {64, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { cb_set_error("cuTensorMapEncodeTiled failed: " + std::to_string((int)r)); return -1; }
+    return 0;
+}
+
 int launch_conv3x3(const ConvParams& p_in, int num_sms, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
@@ -302,6 +339,9 @@ int launch_conv3x3(const ConvParams& p_in, int num_sms, cudaStream_t stream) {
     }
     static const int dbg = getenv("CB_CONV_DEBUG") ? atoi(getenv("CB_CONV_DEBUG")) : 0;  // experiments only
     if (dbg) p.debug = dbg;
+    if (make_row_map(&p.tm_in, p.in, (uint64_t)p.pairs * p.cj_in * (ACT_CHUNK_BYTES / 128), ACT_K64_BYTES / 128) ||
+        make_row_map(&p.tm_w, p.wgt, (uint64_t)p.kc * 9 * p.n, p.n / 2))
+        return -1;
     const int units = (p.pairs + 1) / 2;
     const int max_clusters = num_sms / 2;
     const int clusters = units < max_clusters ? units : max_clusters;

@@ -1,6 +1,8 @@
 // Parameter blocks and launchers shared by the kernels (conv.cu, encode.cu, heads.cu, mcts.cu) and
 // the C ABI (api.cu).
 #pragma once
+#include <cuda.h>
+
 #include "common.cuh"
 #include "rules.cuh"
 
@@ -10,7 +12,7 @@ struct ConvParams {
     const __nv_bfloat16* in;    // tile-native, cj_in chunks
     __nv_bfloat16* out;         // tile-native, n/8 chunks
     const __nv_bfloat16* skip;  // tile-native like out, or nullptr
-    const __nv_bfloat16* wgt;   // [kc][tap][8][n][8], see conv_weight_index
+    const __nv_bfloat16* wgt;   // [kc][tap][half][8][n/2][8], see conv_weight_index
     const float* scale;         // [n] gamma / sqrt(var + eps)
     const float* shift;         // [n] beta - mean * scale
     const float* head_w;        // [3][n] 1x1 head conv weights (value, policy0, policy1) or nullptr
@@ -21,13 +23,16 @@ struct ConvParams {
     int cj_in;                  // input channels / 8
     int n;                      // output channels (multiple of 64, <= 256)
     float slope;                // LeakyReLU negative slope (Keras default 0.3)
+    CUtensorMap tm_in;          // filled by launch_conv3x3: `in` as rows of 128 B, box = one 64-channel chunk of a board pair (200 rows)
+    CUtensorMap tm_w;           // `wgt` as rows of 128 B, box = one half weight block (n/2 rows)
     int debug;                  // experiments only (CB_CONV_DEBUG): 1 no epilogue, 2 no skip loads, 4 no MMAs, 8 no weight loads, 16 no stores
 };
 
-// Packed weight layout [kc][tap][k/8][N][k%8]: per (k-chunk of 64 input channels, tap) one K-major / no-swizzle
-// block = the B operand of four K=16 MMAs; its two K halves (k < 32, k >= 32) are contiguous N x 64 B pieces.
+// Packed weight layout: per (k-chunk of 64 input channels, tap) two halves of N/2 output channels, each a
+// K-major / no-swizzle block [k/8][N/2][k%8] = the B operand one CTA of the pair stages with one bulk copy.
 __host__ __device__ inline size_t conv_weight_index(int kc, int tap, int k /*0..63*/, int co, int n) {
-    return ((size_t)(kc * 9 + tap) * 8 + (k >> 3)) * n * 8 + (size_t)co * 8 + (k & 7);
+    const int nh = n >> 1, half = co >= nh, c = co - half * nh;
+    return ((size_t)((kc * 9 + tap) * 2 + half) * 8 + (k >> 3)) * nh * 8 + (size_t)c * 8 + (k & 7);
 }
 
 struct HeadParams {
