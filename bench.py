@@ -324,7 +324,7 @@ def run_gpu_arm(args):
         if nbytes:
             gbs = nbytes / (ms_k * 1e-3) / 1e9
             kernels[name].update({"bound": "hbm", "achieved_gbs": gbs, "peak_gbs": peak_gbs, "frac": gbs / peak_gbs})
-    kernels["conv3x3"] = {"launches": conv_launches, "avg_us": 1e3 * conv_ms / max(conv_launches, 1),
+    kernels["tower"] = {"launches": conv_launches, "avg_us": 1e3 * conv_ms / max(conv_launches, 1),
                           "share_of_step": conv_ms / sum(v[0] for v in prof.values())}
 
     # end-to-end leg: complete searches through the public API (mcts.run_mcts_batch) from host game objects:
@@ -373,7 +373,7 @@ def run_gpu_arm(args):
                 "fwd_gflop_per_position": flops_per_position(filters, blocks) / 1e9,
             },
             "roofline": {
-                "bound": "tensor", "kernel": "conv3x3_tcgen05_kernel", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                "bound": "tensor", "kernel": "tower_tcgen05_kernel (all 1+2R conv layers, one persistent launch)", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved_tf / peak_tf, "traffic": None, "peak_source": peak_src,
                 "how": f"algorithmic direct-conv FLOPs of {conv_launches} launches / their CUDA-event durations ({conv_ms:.2f} ms), second pass of the same {K} steps",
                 "conv_share_of_step": conv_ms / ms if ms > 0 else None,
@@ -383,7 +383,7 @@ def run_gpu_arm(args):
                     "what": f"{reps} x mcts.run_mcts_batch({trees} games, {e2e_sims} sims): host game records -> H2D -> {steps_per_search} steps -> D2H root "
                             f"statistics -> move choice; bytes are per search / {steps_per_search} steps"},
             "kernels": kernels,
-            "gpu_launches": K * (1 + (1 + 2 * blocks) + 1 + 1),
+            "gpu_launches": K * 4,   # encode, tower, heads, mcts_step
             "clocks": clocks,
             "cpu_baseline": cpu_baseline,
         }

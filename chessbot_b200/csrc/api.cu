@@ -69,6 +69,14 @@ struct Net {
     DevBuf<float> head_w, head_bn, fc1, fc2, wp, wpt;
     DevBuf<__nv_bfloat16> act[3];
     DevBuf<float> head_raw, pfeat;
+    DevBuf<LayerDesc> layer_desc, dbg_desc;          // tower kernel: per-layer descriptors (dbg_desc: cb_debug_conv_layer)
+    DevBuf<CUtensorMap> wmaps;                       // tensor maps of the packed weights, one per layer
+    DevBuf<int> flags;                               // per board pair progress flags of the tower kernel
+    CUtensorMap act_maps[3];                         // tensor maps of act[0..2]
+    CUtensorMap planes_map;                          // tensor map of the last planes buffer seen
+    const void* planes_ptr = nullptr;
+    int planes_pairs = 0;
+    int epoch = 0;
     bool ready = false;
 };
 
@@ -285,8 +293,39 @@ int cb_net_finalize(cb_ctx* ctx) {
         if (net.act[i].alloc(act_elems)) return -1;  // zeroed: border cells stay zero forever
     const size_t mb = (size_t)(net.max_batch + 3) / 4 * 4;
     if (net.head_raw.alloc(mb * 192) || net.pfeat.alloc(mb * 128)) return -1;
+    // tower kernel: weight tensor maps, layer descriptors (buffer 0 = input planes, 1..3 = act[0..2]), progress flags
+    const int nl = (int)net.layers.size();
+    std::vector<CUtensorMap> wm(nl);
+    std::vector<LayerDesc> ld(nl);
+    int cur = 0;
+    for (int l = 0; l < nl; ++l) {
+        ConvLayer& L = net.layers[l];
+        if (conv_make_row_map(&wm[l], L.w.p, (uint64_t)L.kc * 9 * N, N / 2)) return -1;
+        LayerDesc& d = ld[l];
+        d.scale = L.scale.p; d.shift = L.shift.p; d.kc = L.kc; d.kc_in = L.kc_in; d.cj_in = L.cj_in; d.w_map = l; d.pad_ = 0;
+        if (l == 0) { d.in_buf = 0; d.out_buf = 1; d.skip_buf = -1; }
+        else if (l & 1) { d.in_buf = 1 + cur; d.out_buf = 1 + (cur + 1) % 3; d.skip_buf = -1; }                    // first conv of a block
+        else { d.in_buf = 1 + (cur + 1) % 3; d.out_buf = 1 + (cur + 2) % 3; d.skip_buf = 1 + cur; cur = (cur + 2) % 3; }  // second conv + skip
+    }
+    if (net.wmaps.alloc(nl, false) || net.layer_desc.alloc(nl, false) || net.dbg_desc.alloc(1, false) ||
+        net.flags.alloc(2 * ((size_t)net.max_batch / 4 + 2)))
+        return -1;
+    if (upload(net.wmaps.p, wm.data(), nl * sizeof(CUtensorMap)) || upload(net.layer_desc.p, ld.data(), nl * sizeof(LayerDesc))) return -1;
+    for (int i = 0; i < 3; ++i)
+        if (conv_make_row_map(&net.act_maps[i], net.act[i].p, (uint64_t)act_bytes(net.max_batch, N) / 128, ACT_K64_BYTES / 128)) return -1;
+    net.planes_ptr = nullptr;
+    net.epoch = 0;
     net.host.clear();
     net.ready = true;
+    return 0;
+}
+
+// progress flags hold epoch * 256 + layers finished; start a new epoch per launch, clear before it can overflow
+static int next_epoch(Net& net, cudaStream_t st) {
+    if (++net.epoch >= (1 << 22)) {
+        CB_CUDA_OK(cudaMemsetAsync(net.flags.p, 0, net.flags.n * sizeof(int), st));
+        net.epoch = 1;
+    }
     return 0;
 }
 
@@ -296,23 +335,27 @@ static int net_tower(cb_ctx* ctx, const void* planes_act_dev, int n, float* valu
     if (!net.ready) { cb_set_error("network not finalized"); return -1; }
     if (n > net.max_batch) { cb_set_error("batch larger than max_batch"); return -1; }
     const int pairs = (n + 1) / 2;
-    const __nv_bfloat16* in = (const __nv_bfloat16*)planes_act_dev;
-    int cur = -1;  // index of the act buffer holding the block input
-    const int nl = (int)net.layers.size();
-    for (int l = 0; l < nl; ++l) {
-        ConvLayer& L = net.layers[l];
-        ConvParams p{};
-        p.wgt = L.w.p; p.scale = L.scale.p; p.shift = L.shift.p;
-        p.pairs = pairs; p.kc = L.kc; p.kc_in = L.kc_in; p.cj_in = L.cj_in; p.n = net.cpad; p.slope = net.slope;
-        int out_i;
-        if (l == 0) { p.in = in; out_i = 0; p.skip = nullptr; }
-        else if (l & 1) { p.in = net.act[cur].p; out_i = (cur + 1) % 3; p.skip = nullptr; }       // first conv of a block
-        else { p.in = net.act[(cur + 1) % 3].p; out_i = (cur + 2) % 3; p.skip = net.act[cur].p; }  // second conv + skip
-        p.out = net.act[out_i].p;
-        if (l == nl - 1) { p.head_w = net.head_w.p; p.head_out = net.head_raw.p; }
-        if (prof_begin(ctx, CB_PROF_CONV, st) || launch_conv3x3(p, ctx->sms, st) || prof_end(ctx, st)) return -1;
-        if (l == 0 || !(l & 1)) cur = out_i;
+    if (net.planes_ptr != planes_act_dev || net.planes_pairs != pairs) {
+        if (conv_make_row_map(&net.planes_map, planes_act_dev, (uint64_t)act_bytes(n, 128) / 128, ACT_K64_BYTES / 128)) return -1;
+        net.planes_ptr = planes_act_dev;
+        net.planes_pairs = pairs;
     }
+    if (next_epoch(net, st)) return -1;
+    TowerParams tp{};
+    tp.tm_act[0] = net.planes_map;
+    tp.bufs[0] = (uint8_t*)const_cast<void*>(planes_act_dev);
+    for (int i = 0; i < 3; ++i) { tp.tm_act[1 + i] = net.act_maps[i]; tp.bufs[1 + i] = (uint8_t*)net.act[i].p; }
+    tp.maps = net.wmaps.p;
+    tp.layers = net.layer_desc.p;
+    tp.head_w = net.head_w.p;
+    tp.head_out = net.head_raw.p;
+    tp.flags = net.flags.p;
+    tp.epoch = net.epoch;
+    tp.nl = (int)net.layers.size();
+    tp.pairs = pairs;
+    tp.n = net.cpad;
+    tp.slope = net.slope;
+    if (prof_begin(ctx, CB_PROF_CONV, st) || launch_tower(tp, ctx->sms, st) || prof_end(ctx, st)) return -1;
     HeadParams hp{net.head_raw.p, net.head_bn.p, net.fc1.p, net.fc2.p, net.filters, net.slope, value_dev, net.pfeat.p};
     if (prof_begin(ctx, CB_PROF_HEADS, st) || launch_head_features(hp, n, st) || prof_end(ctx, st)) return -1;
     return 0;
@@ -366,13 +409,39 @@ int cb_profile_read_sync(cb_ctx* ctx, double* total_ms, int* launches) {
 int cb_debug_conv_layer(cb_ctx* ctx, int layer, const void* in_act_dev, const void* skip_act_dev, void* out_act_dev, int n_boards,
                         int use_reference, void* stream) {
     Net& net = ctx->net;
+    cudaStream_t st = (cudaStream_t)stream;
     if (!net.ready || layer < 0 || layer >= (int)net.layers.size()) { cb_set_error("bad layer"); return -1; }
+    if (n_boards > net.max_batch) { cb_set_error("batch larger than max_batch"); return -1; }
     ConvLayer& L = net.layers[layer];
-    ConvParams p{};
-    p.in = (const __nv_bfloat16*)in_act_dev; p.out = (__nv_bfloat16*)out_act_dev; p.skip = (const __nv_bfloat16*)skip_act_dev;
-    p.wgt = L.w.p; p.scale = L.scale.p; p.shift = L.shift.p;
-    p.pairs = (n_boards + 1) / 2; p.kc = L.kc; p.kc_in = L.kc_in; p.cj_in = L.cj_in; p.n = net.cpad; p.slope = net.slope;
-    return use_reference ? launch_conv3x3_reference(p, (cudaStream_t)stream) : launch_conv3x3(p, ctx->sms, (cudaStream_t)stream);
+    const int pairs = (n_boards + 1) / 2;
+    if (use_reference) {
+        ConvParams p{};
+        p.in = (const __nv_bfloat16*)in_act_dev; p.out = (__nv_bfloat16*)out_act_dev; p.skip = (const __nv_bfloat16*)skip_act_dev;
+        p.wgt = L.w.p; p.scale = L.scale.p; p.shift = L.shift.p;
+        p.pairs = pairs; p.kc = L.kc; p.kc_in = L.kc_in; p.cj_in = L.cj_in; p.n = net.cpad; p.slope = net.slope;
+        return launch_conv3x3_reference(p, st);
+    }
+    // the tower kernel with a one-layer plan: buffer 0 = in, 1 = out, 2 = skip
+    LayerDesc d{};
+    d.scale = L.scale.p; d.shift = L.shift.p; d.kc = L.kc; d.kc_in = L.kc_in; d.cj_in = L.cj_in; d.w_map = layer;
+    d.in_buf = 0; d.out_buf = 1; d.skip_buf = skip_act_dev ? 2 : -1;
+    CB_CUDA_OK(cudaMemcpyAsync(net.dbg_desc.p, &d, sizeof(d), cudaMemcpyHostToDevice, st));
+    CB_CUDA_OK(cudaStreamSynchronize(st));  // `d` is on this stack frame
+    if (next_epoch(net, st)) return -1;
+    TowerParams tp{};
+    if (conv_make_row_map(&tp.tm_act[0], in_act_dev, (uint64_t)pairs * L.cj_in * (ACT_CHUNK_BYTES / 128), ACT_K64_BYTES / 128)) return -1;
+    tp.bufs[0] = (uint8_t*)const_cast<void*>(in_act_dev);
+    tp.bufs[1] = (uint8_t*)out_act_dev;
+    tp.bufs[2] = (uint8_t*)const_cast<void*>(skip_act_dev);
+    tp.maps = net.wmaps.p;
+    tp.layers = net.dbg_desc.p;
+    tp.flags = net.flags.p;
+    tp.epoch = net.epoch;
+    tp.nl = 1;
+    tp.pairs = pairs;
+    tp.n = net.cpad;
+    tp.slope = net.slope;
+    return launch_tower(tp, ctx->sms, st);
 }
 
 // ------------------------------------------------------------------------------------ search

@@ -1,25 +1,30 @@
-// K2 — 3x3 "same" convolution + BatchNorm + (residual add) + LeakyReLU of the residual tower
-// (model.py:19-28,35-37) as an implicit GEMM on tcgen05 tensor cores, two SMs per MMA.
+// K2 — the residual tower of model.py:19-28,35-37 (3x3 "same" convolution + BatchNorm + (residual add) +
+// LeakyReLU, layer after layer) as ONE persistent kernel of implicit GEMMs on tcgen05 tensor cores.
 //
 //   D[m, co] = sum_{tap, ci} A_tap[m, ci] * W[tap][ci][co]      m = (row, board, col) of 2 boards = 128 rows
 //
 // * A is never materialised: the activations of a board pair sit in HBM in the tile-native layout
-//   (common.cuh) with a zero border, one bulk async copy (UBLKCP) brings 64 channels of the pair
-//   into shared memory, and each of the nine taps is just a different start address of the
-//   K-major / no-swizzle UMMA descriptor (LBO 3200 B between the two 8-channel core matrices,
-//   SBO 160 B between 8-pixel groups).
-// * The kernel runs as clusters of two CTAs (one TPC) issuing cta_group::2 MMAs of M = 256: each CTA
-//   owns one board pair (128 accumulator rows in its own TMEM) and stages only HALF of every weight
-//   block (N/2 output channels, pre-packed per (k-chunk, tap, half) as [8][N/2][8] bf16 = one bulk
-//   copy); the tensor cores of the pair read both halves.  That halves the L2->smem weight traffic per
-//   MMA and the shared-memory operand bandwidth per SM.
+//   (common.cuh) with a zero border, one TMA tile load brings 64 channels of the pair into shared memory
+//   byte for byte, and each of the nine taps is just a different start address of the K-major /
+//   no-swizzle UMMA descriptor (LBO 3200 B between the two 8-channel core matrices, SBO 160 B between
+//   8-pixel groups).
+// * Clusters of two CTAs (one TPC) issue cta_group::2 MMAs of M = 256: each CTA owns one board pair (128
+//   accumulator rows in its own TMEM) and stages only HALF of every weight block (N/2 output channels,
+//   pre-packed per (k-chunk, tap, half) as [8][N/2][8] bf16); the TMA loads of both CTAs complete on the
+//   leader's barriers, the leader's single elected lane issues the MMAs, tcgen05.commit multicasts the
+//   "slot free" / "accumulator ready" signals back to both CTAs.
 // * TMEM holds TWO accumulator stages of 256 columns: while the epilogue drains stage s, the MMAs of the
-//   next unit fill stage s^1, so BN / skip / LeakyReLU / stores overlap the tensor pipe.
-// * Warp roles per CTA: warp 0 = bulk-copy producer; warp 1 = MMA issuer (one lane of the leader
-//   CTA; the bulk copies of both CTAs complete on the leader's barriers); warps 2..9 =
-//   epilogue (tcgen05.ld -> BN scale/shift -> +skip -> LeakyReLU -> bf16 -> HBM in the same tile-native
-//   layout; optionally the three 1x1 head convolutions of model.py:43,52 as dot products over the
-//   fp32 row).  Two epilogue warps share a TMEM lane quarter and split the channel batches.
+//   next work item fill stage s^1, so BN / skip / LeakyReLU / stores overlap the tensor pipe.
+// * A 3x3 convolution never mixes boards, so a board pair can run through ALL layers without any
+//   grid-wide synchronisation.  The (unit = 4 boards, layer) items are cut into equal contiguous ranges
+//   per cluster (perfect balance over the whole tower instead of a ragged last wave per layer); a
+//   cluster walks its range layer by layer over its units, and a unit shared between two neighbouring
+//   clusters is handed over through a per-board-pair progress flag in global memory.  The same flag
+//   orders "epilogue wrote layer l" before "TMA reads layer l as the input of layer l+1".
+// * Warp roles per CTA: warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA), warps 2..9 = epilogue
+//   (tcgen05.ld -> BN scale/shift -> +skip -> LeakyReLU -> bf16 -> HBM in the same tile-native layout; on
+//   the last layer also the three 1x1 head convolutions of model.py:43,52 as dot products over the fp32
+//   row).  Two epilogue warps share a TMEM lane quarter and split the channel batches.
 #include <stdlib.h>
 
 #include "kernels.cuh"
@@ -37,37 +42,58 @@ struct ConvSmem {
     uint64_t b_full[B_SLOTS], b_empty[B_SLOTS];
     uint64_t acc_full[2], acc_empty[2];
     uint32_t tmem_base;
-    uint32_t pad_;
+    int item_cnt[4];  // epilogue warps that finished item j (slot j & 3)
 };
 static_assert(sizeof(ConvSmem) <= 1024, "barrier block");
-constexpr int CONV_SMEM_PARAM_FLOATS = 256 * 2 + 256 * 3 + 2 * 128 * 3;
+constexpr int CONV_SMEM_PARAM_FLOATS = 256 * 3 + 2 * 128 * 3;
 constexpr size_t CONV_SMEM_BYTES = 1024 + A_SLOTS * A_SLOT_BYTES + B_SLOTS * B_SLOT_BYTES + CONV_SMEM_PARAM_FLOATS * 4;
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) conv3x3_tcgen05_kernel(const __grid_constant__ ConvParams p) {
+// This cluster's share of the flattened (unit, layer) items i = unit * nl + layer: the range [lo, hi).
+struct WorkRange {
+    int lo, hi, u_first, nu, nl;
+    __device__ WorkRange(int cid, int nclusters, int units, int nl_) : nl(nl_) {
+        const long long total = (long long)units * nl_;
+        lo = (int)(total * cid / nclusters);
+        hi = (int)(total * (cid + 1) / nclusters);
+        u_first = lo / nl_;
+        nu = (hi - 1) / nl_ - u_first + 1;
+    }
+    // k-th unit of a layer round: the unit the NEXT cluster continues goes first (its flag is published early),
+    // the unit the PREVIOUS cluster began goes last (its flag has had a whole round to arrive)
+    __device__ int unit(int k) const { return nu == 1 ? u_first : (k == 0 ? u_first + nu - 1 : (k == nu - 1 ? u_first : u_first + k)); }
+    __device__ bool mine(int u, int l) const { const int i = u * nl + l; return i >= lo && i < hi; }
+};
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tower_tcgen05_kernel(const __grid_constant__ TowerParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     ConvSmem* s = reinterpret_cast<ConvSmem*>(smem);
     uint8_t* a_buf = smem + 1024;
     uint8_t* b_buf = a_buf + A_SLOTS * A_SLOT_BYTES;
-    float* s_scale = reinterpret_cast<float*>(b_buf + B_SLOTS * B_SLOT_BYTES);
-    float* s_shift = s_scale + 256;
-    float* s_head = s_shift + 256;
+    float* s_head = reinterpret_cast<float*>(b_buf + B_SLOTS * B_SLOT_BYTES);
     float* s_hpart = s_head + 768;  // [2 stages][128 rows][3]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = ptx::cluster_ctarank();
     const int cid = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
     const int units = (p.pairs + 1) / 2;  // one unit = two board pairs = one M=256 accumulator stage
-    const int n = p.n, nh = n >> 1;
+    const int n = p.n, nh = n >> 1, nl = p.nl;
+    const WorkRange w(cid, nclusters, units, nl);
+    const int flag_base = p.epoch << 8;
 
-    for (int i = threadIdx.x; i < n; i += CONV_THREADS) {
-        s_scale[i] = p.scale[i];
-        s_shift[i] = p.shift[i];
-        if (p.head_w) {
+    if (p.head_w)
+        for (int i = threadIdx.x; i < n; i += CONV_THREADS) {
             s_head[i] = p.head_w[i];
             s_head[256 + i] = p.head_w[n + i];
             s_head[512 + i] = p.head_w[2 * n + i];
         }
-    }
     if (threadIdx.x == 0) {
         for (int i = 0; i < A_SLOTS; ++i) { ptx::mbar_init(&s->a_full[i], 1); ptx::mbar_init(&s->a_empty[i], 1); }
         for (int i = 0; i < B_SLOTS; ++i) { ptx::mbar_init(&s->b_full[i], 1); ptx::mbar_init(&s->b_empty[i], 1); }
@@ -75,6 +101,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) con
             ptx::mbar_init(&s->acc_full[i], 1);
             ptx::mbar_init(&s->acc_empty[i], 2 * EPI_WARPS);  // every epilogue warp of both CTAs
         }
+        for (int i = 0; i < 4; ++i) s->item_cnt[i] = 0;
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
@@ -93,37 +120,43 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) con
         const uint32_t b_bytes = (uint32_t)nh * 128;
         // operands of BOTH CTAs complete on the leader's "full" barriers (the MMA issuer lives there)
         const uint32_t a_full0 = ptx::mapa(ptx::smem_u32(&s->a_full[0]), 0), b_full0 = ptx::mapa(ptx::smem_u32(&s->b_full[0]), 0);
-        if (ptx::elect_one()) {
-            ptx::tma_prefetch_desc(&p.tm_in);
-            ptx::tma_prefetch_desc(&p.tm_w);
-        }
-        for (int u = cid; u < units; u += nclusters) {
-            const int pair = min(2 * u + (int)rank, p.pairs - 1);  // odd tail: the peer re-reads the last pair, its result is dropped
-            for (int kc = 0; kc < p.kc; ++kc) {
-                const int as = a_it % A_SLOTS;
-                ptx::mbar_wait(&s->a_empty[as], ((a_it / A_SLOTS) & 1) ^ 1);
-                if (ptx::elect_one()) {
-                    if (p.debug & 32) { if (rank == 0) ptx::mbar_arrive(&s->a_full[as]); }
-                    else {
+        for (int l = 0; l < nl; ++l) {
+            const LayerDesc L = p.layers[l];
+            const CUtensorMap* tm_in = &p.tm_act[L.in_buf];
+            const CUtensorMap* tm_w = &p.maps[L.w_map];
+            if (ptx::elect_one()) ptx::tma_prefetch_desc(tm_w);
+            for (int k = 0; k < w.nu; ++k) {
+                const int u = w.unit(k);
+                if (!w.mine(u, l)) continue;
+                const int pair = min(2 * u + (int)rank, p.pairs - 1);  // odd tail: the peer re-reads the last pair, its result is dropped
+                if (l > 0) {
+                    // the input of this item is the output of (unit, layer - 1): written by this CTA's epilogue warps, or by
+                    // the same-rank CTA of the previous cluster; either way its progress flag says when it is in L2
+                    const int* flag = p.flags + 2 * u + rank;
+                    while (ld_acquire_gpu(flag) < flag_base + l) {
+                    }
+                    fence_proxy_async();
+                }
+                for (int kc = 0; kc < L.kc; ++kc) {
+                    const int as = a_it % A_SLOTS;
+                    ptx::mbar_wait(&s->a_empty[as], ((a_it / A_SLOTS) & 1) ^ 1);
+                    if (ptx::elect_one()) {
                         if (rank == 0) ptx::mbar_expect_tx(&s->a_full[as], 2 * ACT_K64_BYTES);
-                        ptx::tma_load_2d_pair(a_buf + as * A_SLOT_BYTES, &p.tm_in, 0, (pair * p.cj_in + 8 * (kc % p.kc_in)) * (ACT_CHUNK_BYTES / 128),
+                        ptx::tma_load_2d_pair(a_buf + as * A_SLOT_BYTES, tm_in, 0, (pair * L.cj_in + 8 * (kc % L.kc_in)) * (ACT_CHUNK_BYTES / 128),
                                               a_full0 + as * 8);
                     }
-                }
-                ++a_it;
-                const int wrow = (kc * 9 * 2 + (int)rank) * nh;
+                    ++a_it;
+                    const int wrow = (kc * 9 * 2 + (int)rank) * nh;
 #pragma unroll
-                for (int tap = 0; tap < 9; ++tap) {
-                    const int bs = b_it % B_SLOTS;
-                    ptx::mbar_wait(&s->b_empty[bs], ((b_it / B_SLOTS) & 1) ^ 1);
-                    if (ptx::elect_one()) {
-                        if (p.debug & 8) { if (rank == 0) ptx::mbar_arrive(&s->b_full[bs]); }
-                        else {
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int bs = b_it % B_SLOTS;
+                        ptx::mbar_wait(&s->b_empty[bs], ((b_it / B_SLOTS) & 1) ^ 1);
+                        if (ptx::elect_one()) {
                             if (rank == 0) ptx::mbar_expect_tx(&s->b_full[bs], 2 * b_bytes);
-                            ptx::tma_load_2d_pair(b_buf + bs * B_SLOT_BYTES, &p.tm_w, 0, wrow + tap * 2 * nh, b_full0 + bs * 8);
+                            ptx::tma_load_2d_pair(b_buf + bs * B_SLOT_BYTES, tm_w, 0, wrow + tap * 2 * nh, b_full0 + bs * 8);
                         }
+                        ++b_it;
                     }
-                    ++b_it;
                 }
             }
         }
@@ -135,40 +168,43 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) con
             const uint64_t a_desc0 = ptx::smem_desc(ptx::smem_u32(a_buf), ACT_CHUNK_BYTES, 160);
             const uint64_t b_desc0 = ptx::smem_desc(ptx::smem_u32(b_buf), (uint32_t)nh * 16, 128);
             const uint32_t a_ks = 2 * ACT_CHUNK_BYTES / 16, b_ks = 2 * nh;  // descriptor address units of 16 B
-            uint32_t a_it = 0, b_it = 0, u_it = 0;
-            for (int u = cid; u < units; u += nclusters, ++u_it) {
-                const uint32_t st = u_it & 1;
-                ptx::mbar_wait(&s->acc_empty[st], ((u_it >> 1) & 1) ^ 1);
-                ptx::tc_fence_after();
-                const uint32_t d = tmem + st * 256;
-                for (int kc = 0; kc < p.kc; ++kc) {
-                    const int as = a_it % A_SLOTS;
-                    ptx::mbar_wait(&s->a_full[as], (a_it / A_SLOTS) & 1);
-                    const uint64_t a_desc = a_desc0 + (uint64_t)(as * (A_SLOT_BYTES / 16));
+            uint32_t a_it = 0, b_it = 0, j = 0;
+            for (int l = 0; l < nl; ++l) {
+                const int kcs = p.layers[l].kc;
+                for (int k = 0; k < w.nu; ++k) {
+                    if (!w.mine(w.unit(k), l)) continue;
+                    const uint32_t st = j & 1;
+                    ptx::mbar_wait(&s->acc_empty[st], ((j >> 1) & 1) ^ 1);
+                    ptx::tc_fence_after();
+                    const uint32_t d = tmem + st * 256;
+                    for (int kc = 0; kc < kcs; ++kc) {
+                        const int as = a_it % A_SLOTS;
+                        ptx::mbar_wait(&s->a_full[as], (a_it / A_SLOTS) & 1);
+                        const uint64_t a_desc = a_desc0 + (uint64_t)(as * (A_SLOT_BYTES / 16));
 #pragma unroll
-                    for (int tap = 0; tap < 9; ++tap) {
-                        const int bs = b_it % B_SLOTS;
-                        ptx::mbar_wait(&s->b_full[bs], (b_it / B_SLOTS) & 1);
-                        ptx::tc_fence_after();
-                        const uint64_t bd0 = b_desc0 + (uint64_t)(bs * (B_SLOT_BYTES / 16));
-                        const uint64_t ad0 = a_desc + (uint64_t)((tap / 3) * 20 + (tap % 3));  // tap (dy, dx): start cell (1+dy)*20 + 1+dx
-                        if (ptx::elect_one()) {
-                            if (!(p.debug & 4)) {
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const int bs = b_it % B_SLOTS;
+                            ptx::mbar_wait(&s->b_full[bs], (b_it / B_SLOTS) & 1);
+                            ptx::tc_fence_after();
+                            const uint64_t bd0 = b_desc0 + (uint64_t)(bs * (B_SLOT_BYTES / 16));
+                            const uint64_t ad0 = a_desc + (uint64_t)((tap / 3) * 20 + (tap % 3));  // tap (dy, dx): start cell (1+dy)*20 + 1+dx
+                            if (ptx::elect_one()) {
 #pragma unroll
                                 for (int ks = 0; ks < 4; ++ks)
                                     ptx::umma2_bf16(d, ad0 + ks * a_ks, bd0 + ks * b_ks, idesc, (kc | tap | ks) != 0);
+                                ptx::umma2_commit_mc(&s->b_empty[bs]);  // weight stage of BOTH CTAs is free when these MMAs retire
                             }
-                            ptx::umma2_commit_mc(&s->b_empty[bs]);  // weight stage of BOTH CTAs is free when these MMAs retire
+                            __syncwarp();
+                            ++b_it;
                         }
+                        if (ptx::elect_one()) ptx::umma2_commit_mc(&s->a_empty[as]);
                         __syncwarp();
-                        ++b_it;
+                        ++a_it;
                     }
-                    if (ptx::elect_one()) ptx::umma2_commit_mc(&s->a_empty[as]);
+                    if (ptx::elect_one()) ptx::umma2_commit_mc(&s->acc_full[st]);
                     __syncwarp();
-                    ++a_it;
+                    ++j;
                 }
-                if (ptx::elect_one()) ptx::umma2_commit_mc(&s->acc_full[st]);
-                __syncwarp();
             }
         }
     } else {
@@ -183,85 +219,119 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) con
         const int cell = act_cell(row, bip, col);
         const int cjo = n >> 3, ncb = n >> 5;
         const int nk = (ncb - h + 1) >> 1;  // batches of this warp: cb = h + 2k
-        const bool has_skip = p.skip != nullptr && !(p.debug & 2);
         const uint32_t acc_empty0 = ptx::mapa(ptx::smem_u32(&s->acc_empty[0]), 0);
-        uint32_t u_it = 0;
-        for (int u = cid; u < units; u += nclusters, ++u_it) {
-            const uint32_t st = u_it & 1;
-            const int pair = 2 * u + (int)rank;
-            const bool active = pair < p.pairs && !(p.debug & 1);
-            uint4 sk[4][4];
-            auto load_skip = [&](uint4 (&dst)[4], int cb) {
+        uint32_t j = 0;
+        for (int l = 0; l < nl; ++l) {
+            const LayerDesc L = p.layers[l];
+            const uint8_t* skip_buf = L.skip_buf >= 0 ? p.bufs[L.skip_buf] : nullptr;
+            uint8_t* out_buf = p.bufs[L.out_buf];
+            const bool has_skip = skip_buf != nullptr;
+            const bool heads = p.head_w != nullptr && l == nl - 1;
+            for (int k = 0; k < w.nu; ++k) {
+                const int u = w.unit(k);
+                if (!w.mine(u, l)) continue;
+                const uint32_t st = j & 1;
+                const int pair = 2 * u + (int)rank;
+                const bool active = pair < p.pairs;
+                // the skip tile is the output of (unit, layer - 2): if another cluster wrote it, it is only known to be
+                // complete once this item's own operands have been loaded (the producer waited for the flag)
+                const bool skip_early = has_skip && w.mine(u, l - 2);
+                uint4 sk[4][4];
+                auto load_skip = [&](uint4 (&dst)[4], int cb) {
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj)
-                    dst[jj] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.skip) +
-                                                                   act_offset_bytes(pair, cjo, cb * 4 + jj, cell)));
-            };
-            if (active && has_skip) {
+                    for (int jj = 0; jj < 4; ++jj)
+                        dst[jj] = __ldcg(reinterpret_cast<const uint4*>(skip_buf + act_offset_bytes(pair, cjo, cb * 4 + jj, cell)));
+                };
+                if (active && skip_early) {
 #pragma unroll
-                for (int r = 0; r < 4; ++r)
-                    if (r < nk) load_skip(sk[r], h + 2 * r);
-            }
-            ptx::mbar_wait(&s->acc_full[st], (u_it >> 1) & 1);
-            ptx::tc_fence_after();
-            float h0 = 0.f, h1 = 0.f, h2 = 0.f;
-            if (active) {
-                for (int k0 = 0; k0 < nk; k0 += 4) {
+                    for (int r = 0; r < 4; ++r)
+                        if (r < nk) load_skip(sk[r], h + 2 * r);
+                }
+                ptx::mbar_wait(&s->acc_full[st], (j >> 1) & 1);
+                ptx::tc_fence_after();
+                if (active && has_skip && !skip_early) {
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        const int k = k0 + r;
-                        if (k >= nk) break;
-                        const int cb = h + 2 * k;
-                        uint32_t acc[32];
-                        ptx::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + st * 256 + cb * 32, acc);
-                        ptx::tmem_wait_ld();
+                    for (int r = 0; r < 4; ++r)
+                        if (r < nk) load_skip(sk[r], h + 2 * r);
+                }
+                float h0 = 0.f, h1 = 0.f, h2 = 0.f;
+                if (active) {
+                    for (int k0 = 0; k0 < nk; k0 += 4) {
 #pragma unroll
-                        for (int jj = 0; jj < 4; ++jj) {
-                            float v[8];
-                            const uint32_t* skw = reinterpret_cast<const uint32_t*>(&sk[r][jj]);
+                        for (int r = 0; r < 4; ++r) {
+                            const int kk = k0 + r;
+                            if (kk >= nk) break;
+                            const int cb = h + 2 * kk;
+                            uint32_t acc[32];
+                            ptx::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + st * 256 + cb * 32, acc);
+                            const float4* sc4 = reinterpret_cast<const float4*>(L.scale + cb * 32);
+                            const float4* sh4 = reinterpret_cast<const float4*>(L.shift + cb * 32);
+                            ptx::tmem_wait_ld();
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) {
-                                const int ch = cb * 32 + jj * 8 + e;
-                                float x = fmaf(__uint_as_float(acc[jj * 8 + e]), s_scale[ch], s_shift[ch]);
-                                if (has_skip) {
-                                    const uint32_t w = skw[e >> 1];
-                                    x += __uint_as_float((e & 1) ? (w & 0xFFFF0000u) : (w << 16));
+                            for (int jj = 0; jj < 4; ++jj) {
+                                float v[8];
+                                const uint32_t* skw = reinterpret_cast<const uint32_t*>(&sk[r][jj]);
+                                const float4 sa = __ldg(sc4 + jj * 2), sb = __ldg(sc4 + jj * 2 + 1);
+                                const float4 ha = __ldg(sh4 + jj * 2), hb = __ldg(sh4 + jj * 2 + 1);
+                                const float scl[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+                                const float shf[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+#pragma unroll
+                                for (int e = 0; e < 8; ++e) {
+                                    const int ch = cb * 32 + jj * 8 + e;
+                                    float x = fmaf(__uint_as_float(acc[jj * 8 + e]), scl[e], shf[e]);
+                                    if (has_skip) {
+                                        const uint32_t wv = skw[e >> 1];
+                                        x += __uint_as_float((e & 1) ? (wv & 0xFFFF0000u) : (wv << 16));
+                                    }
+                                    x = x > 0.f ? x : x * p.slope;
+                                    v[e] = x;
+                                    if (heads) {
+                                        h0 = fmaf(x, s_head[ch], h0);
+                                        h1 = fmaf(x, s_head[256 + ch], h1);
+                                        h2 = fmaf(x, s_head[512 + ch], h2);
+                                    }
                                 }
-                                x = x > 0.f ? x : x * p.slope;
-                                v[e] = x;
-                                if (p.head_w) {
-                                    h0 = fmaf(x, s_head[ch], h0);
-                                    h1 = fmaf(x, s_head[256 + ch], h1);
-                                    h2 = fmaf(x, s_head[512 + ch], h2);
-                                }
+                                uint4 o;
+                                __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]), t1 = __floats2bfloat162_rn(v[2], v[3]);
+                                __nv_bfloat162 t2 = __floats2bfloat162_rn(v[4], v[5]), t3 = __floats2bfloat162_rn(v[6], v[7]);
+                                o.x = *reinterpret_cast<uint32_t*>(&t0);
+                                o.y = *reinterpret_cast<uint32_t*>(&t1);
+                                o.z = *reinterpret_cast<uint32_t*>(&t2);
+                                o.w = *reinterpret_cast<uint32_t*>(&t3);
+                                *reinterpret_cast<uint4*>(out_buf + act_offset_bytes(pair, cjo, cb * 4 + jj, cell)) = o;
                             }
-                            uint4 o;
-                            __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]), t1 = __floats2bfloat162_rn(v[2], v[3]);
-                            __nv_bfloat162 t2 = __floats2bfloat162_rn(v[4], v[5]), t3 = __floats2bfloat162_rn(v[6], v[7]);
-                            o.x = *reinterpret_cast<uint32_t*>(&t0);
-                            o.y = *reinterpret_cast<uint32_t*>(&t1);
-                            o.z = *reinterpret_cast<uint32_t*>(&t2);
-                            o.w = *reinterpret_cast<uint32_t*>(&t3);
-                            *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) +
-                                                      act_offset_bytes(pair, cjo, cb * 4 + jj, cell)) = o;
+                            if (has_skip && kk + 4 < nk) load_skip(sk[r], h + 2 * (kk + 4));
                         }
-                        if (has_skip && k + 4 < nk) load_skip(sk[r], h + 2 * (k + 4));
                     }
                 }
-            }
-            // the accumulator stage is drained: hand it back to the MMA issuer before the head bookkeeping
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive_remote(acc_empty0 + st * 8);
-            if (p.head_w) {
-                // the two warps of a lane quarter hold partial dot products over their channel batches
-                float* hp = s_hpart + ((size_t)st * 128 + m) * 3;
-                if (h == 1) { hp[0] = h0; hp[1] = h1; hp[2] = h2; }
-                asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
-                if (h == 0 && active) {
-                    float* ho = p.head_out + ((size_t)(pair * 2 + bip) * 64 + row * 8 + col) * 3;
-                    ho[0] = h0 + hp[0]; ho[1] = h1 + hp[1]; ho[2] = h2 + hp[2];
+                // the accumulator stage is drained: hand it back to the MMA issuer
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive_remote(acc_empty0 + st * 8);
+                if (heads) {
+                    // the two warps of a lane quarter hold partial dot products over their channel batches
+                    float* hp = s_hpart + ((size_t)st * 128 + m) * 3;
+                    if (h == 1) { hp[0] = h0; hp[1] = h1; hp[2] = h2; }
+                    asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory");
+                    if (h == 0 && active) {
+                        float* ho = p.head_out + ((size_t)(pair * 2 + bip) * 64 + row * 8 + col) * 3;
+                        ho[0] = h0 + hp[0]; ho[1] = h1 + hp[1]; ho[2] = h2 + hp[2];
+                    }
                 }
+                // publish "layer l of this board pair is in memory": the last of the eight warps sets the progress flag
+                // that the TMA producer of (unit, l + 1) — here or in the next cluster — waits for
+                __threadfence();
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    const int old = atomicAdd(&s->item_cnt[j & 3], 1);
+                    if (old == EPI_WARPS - 1) {
+                        s->item_cnt[j & 3] = 0;
+                        __threadfence();
+                        st_release_gpu(p.flags + 2 * u + rank, flag_base + l + 1);
+                    }
+                }
+                ++j;
             }
         }
     }
@@ -326,26 +396,22 @@ static int make_row_map(CUtensorMap* tm, const void* base, uint64_t rows, uint32
     return 0;
 }
 
-int launch_conv3x3(const ConvParams& p_in, int num_sms, cudaStream_t stream) {
+int conv_make_row_map(CUtensorMap* tm, const void* base, uint64_t rows, uint32_t box_rows) { return make_row_map(tm, base, rows, box_rows); }
+
+int launch_tower(const TowerParams& p, int num_sms, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        CB_CUDA_OK(cudaFuncSetAttribute(conv3x3_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV_SMEM_BYTES));
+        CB_CUDA_OK(cudaFuncSetAttribute(tower_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV_SMEM_BYTES));
         attr_set = true;
     }
-    ConvParams p = p_in;
-    if (p.n % 64 != 0 || p.n > 256 || p.n < 64 || p.kc < 1 || p.kc_in < 1 || p.pairs < 1) {
-        cb_set_error("conv3x3: unsupported shape");
+    if (p.n % 64 != 0 || p.n > 256 || p.n < 64 || p.nl < 1 || p.nl > 255 || p.pairs < 1) {
+        cb_set_error("tower: unsupported shape");
         return -1;
     }
-    static const int dbg = getenv("CB_CONV_DEBUG") ? atoi(getenv("CB_CONV_DEBUG")) : 0;  // experiments only
-    if (dbg) p.debug = dbg;
-    if (make_row_map(&p.tm_in, p.in, (uint64_t)p.pairs * p.cj_in * (ACT_CHUNK_BYTES / 128), ACT_K64_BYTES / 128) ||
-        make_row_map(&p.tm_w, p.wgt, (uint64_t)p.kc * 9 * p.n, p.n / 2))
-        return -1;
     const int units = (p.pairs + 1) / 2;
     const int max_clusters = num_sms / 2;
     const int clusters = units < max_clusters ? units : max_clusters;
-    conv3x3_tcgen05_kernel<<<2 * clusters, CONV_THREADS, CONV_SMEM_BYTES, stream>>>(p);
+    tower_tcgen05_kernel<<<2 * clusters, CONV_THREADS, CONV_SMEM_BYTES, stream>>>(p);
     CB_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -23,9 +23,31 @@ struct ConvParams {
     int cj_in;                  // input channels / 8
     int n;                      // output channels (multiple of 64, <= 256)
     float slope;                // LeakyReLU negative slope (Keras default 0.3)
-    CUtensorMap tm_in;          // filled by launch_conv3x3: `in` as rows of 128 B, box = one 64-channel chunk of a board pair (200 rows)
-    CUtensorMap tm_w;           // `wgt` as rows of 128 B, box = one half weight block (n/2 rows)
-    int debug;                  // experiments only (CB_CONV_DEBUG): 1 no epilogue, 2 no skip loads, 4 no MMAs, 8 no weight loads, 16 no stores
+};
+
+// One layer of the tower kernel (device array, read by every role)
+struct LayerDesc {
+    const float* scale;         // [n] gamma / sqrt(var + eps)
+    const float* shift;         // [n] beta - mean * scale
+    int kc, kc_in, cj_in;       // as in ConvParams
+    int in_buf, out_buf, skip_buf;  // indices into TowerParams::bufs / tm_act; skip_buf = -1: no residual add
+    int w_map;                  // index into TowerParams::maps
+    int pad_;
+};
+
+struct TowerParams {
+    CUtensorMap tm_act[4];      // the activation buffers as rows of 128 B, box = one 64-channel chunk of a board pair (200 rows)
+    const CUtensorMap* maps;    // device array: packed weights of each layer as rows of 128 B, box = one half weight block (n/2 rows)
+    const LayerDesc* layers;    // device array [nl]
+    uint8_t* bufs[4];           // raw pointers of the same four buffers (epilogue stores, skip reads)
+    const float* head_w;        // [3][n] 1x1 head conv weights fused into the LAST layer, or nullptr
+    float* head_out;            // [boards][64][3]
+    int* flags;                 // [2 * units] progress of every board pair: epoch * 256 + layers finished
+    int epoch;                  // increases with every launch, so flags never need clearing
+    int nl;                     // layers to run
+    int pairs;                  // board pairs in the batch
+    int n;                      // channels of every layer output (multiple of 64, <= 256)
+    float slope;
 };
 
 // Packed weight layout: per (k-chunk of 64 input channels, tap) two halves of N/2 output channels, each a
@@ -95,7 +117,8 @@ struct SearchParams {
     int32_t* counters;         // [0] evals, [1] sims, [2] errors
 };
 
-int launch_conv3x3(const ConvParams& p, int num_sms, cudaStream_t stream);
+int launch_tower(const TowerParams& p, int num_sms, cudaStream_t stream);
+int conv_make_row_map(CUtensorMap* tm, const void* base, uint64_t rows, uint32_t box_rows);
 int launch_conv3x3_reference(const ConvParams& p, cudaStream_t stream);
 int launch_encode(const Pos* pos_base, const int32_t* frame_idx, int n, __nv_bfloat16* planes_act, int16_t* planes_i16, cudaStream_t stream);
 int launch_head_features(const HeadParams& p, int boards, cudaStream_t stream);
