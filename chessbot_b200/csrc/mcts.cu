@@ -63,6 +63,7 @@ constexpr int MCTS_WARPS = 4;
 
 __global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_step_kernel(SearchParams sp) {
     __shared__ float s_p[MCTS_WARPS][MAX_MOVES];
+    __shared__ uint16_t s_m[MCTS_WARPS][MAX_MOVES];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tree = blockIdx.x * MCTS_WARPS + warp;
     if (tree >= sp.n_trees) return;
@@ -198,7 +199,10 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_step_kernel(SearchParams
             node = nd.first_child + best_i;
         }
         // ---- leaf: position, outcome (mcts.py:67, game.py:49-59)
-        int term = 0, n_moves = 0, leaf_pos = -1, err = 0;
+        // lane 0 makes the move and generates the legal moves; the threefold claim-ahead scan (one make-move +
+        // history walk per legal move, the expensive part of outcome(claim_draw=True)) runs one move per lane
+        int term = 0, n_moves = 0, leaf_pos = -1, err = 0, scan = 0;
+        uint16_t* sm = s_m[warp];
         if (lane == 0) {
             Node& lf = sp.nodes[node];
             term = lf.term;
@@ -216,23 +220,36 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_step_kernel(SearchParams
                     lf.pos_id = leaf_pos;
                     MoveList ml;
                     generate_legal(np_, ml);
-                    const int out = outcome_claim_draw(np_, ml, &pp, PoolPrev{sp.pos}, ts.max_len);
-                    if (out != OUT_NONE) {
-                        term = terminal_value_to_play(out) < 0 ? 2 : 1;
-                        lf.term = (int8_t)term;
-                    } else {
-                        n_moves = ml.n;
-                        uint16_t* pm = sp.pend_moves + (size_t)tree * MAX_MOVES;
-                        for (int i = 0; i < ml.n; ++i) pm[i] = ml.m[i];
-                    }
+                    bool need_scan = false;
+                    const int out = outcome_before_scan(np_, ml, &pp, PoolPrev{sp.pos}, ts.max_len, &need_scan);
+                    if (out != OUT_NONE) term = terminal_value_to_play(out) < 0 ? 2 : 1;
+                    n_moves = ml.n;
+                    scan = need_scan;
+                    for (int i = 0; i < ml.n; ++i) sm[i] = ml.m[i];
+                    __threadfence_block();
                 }
             }
+        }
+        __syncwarp();
+        scan = __shfl_sync(0xffffffffu, scan, 0);
+        if (scan) {
+            n_moves = __shfl_sync(0xffffffffu, n_moves, 0);
+            leaf_pos = __shfl_sync(0xffffffffu, leaf_pos, 0);
+            const Pos& cur = sp.pos[leaf_pos];
+            bool found = false;
+            for (int i = lane; i < n_moves && !found; i += 32) found = move_claims_threefold(cur, sm[i], &sp.pos[parent_pos], PoolPrev{sp.pos});
+            if (__any_sync(0xffffffffu, found)) term = 1;  // draw by threefold claim
+        }
+        if (lane == 0) {
             if (!err && term) {
+                sp.nodes[node].term = (int8_t)term;
                 // evaluate() returned (value, True): update(node, -value) with value = -1 or 0
                 backup(sp.nodes, node, term == 2 ? 1.0f : -0.0f);
                 ts.sims_done += 1;
                 atomicAdd(&sp.counters[1], 1);
             } else if (!err) {
+                uint16_t* pm = sp.pend_moves + (size_t)tree * MAX_MOVES;
+                for (int i = 0; i < n_moves; ++i) pm[i] = sm[i];
                 ts.leaf_node = node;
                 ts.leaf_pos = leaf_pos;
                 ts.n_moves = n_moves;

@@ -572,10 +572,34 @@ CB_HDN int count_occurrences(const Pos& cur, const Pos* before, PrevFn prev) {
     return n;
 }
 
-// outcome(claim_draw=True) (game.py:57-58) for a position whose `occur` is filled in.
+// Threefold claim-ahead for ONE legal move of `cur`: does it reach a position that already occurred twice since
+// the last irreversible move?  (python-chess can_claim_threefold_repetition, the "any legal move" part.)
+template <class PrevFn>
+CB_HDN bool move_claims_threefold(const Pos& cur, Move m, const Pos* before, PrevFn prev) {
+    if (is_zeroing(cur, m)) return false;  // only reversible moves can repeat (others change material, pawns or castling rights)
+    Pos nxt = push_move(cur, m);
+    if (nxt.irrev_in) return false;
+    int n = 0, k = 1;
+    const Pos* walk = &cur;
+    const Pos* q = before;
+    while (!walk->irrev_in && q) {  // same side to move as nxt: 1, 3, 5, ... plies back
+        if ((k & 1) && key_equal(*q, nxt)) {
+            if (++n >= 2) return true;
+        }
+        walk = q;
+        q = prev(q);
+        ++k;
+    }
+    return false;
+}
+
+// outcome(claim_draw=True) (game.py:57-58) for a position whose `occur` is filled in, EXCEPT the threefold
+// claim-ahead scan over the legal moves: *scan is set when that scan (move_claims_threefold for every legal
+// move, any order) still has to decide between OUT_THREEFOLD_REPETITION and the returned OUT_NONE.
 // `legal` must hold generate_legal(cur).  max_len: config.max_game_length (game.py:55), 0 to disable.
 template <class PrevFn>
-CB_HDN int outcome_claim_draw(const Pos& cur, const MoveList& legal, const Pos* before, PrevFn prev, int max_len) {
+CB_HDN int outcome_before_scan(const Pos& cur, const MoveList& legal, const Pos* before, PrevFn prev, int max_len, bool* scan) {
+    *scan = false;
     if (max_len > 0 && cur.ply == max_len) return OUT_MAX_LENGTH;
     if (legal.n == 0 && checkers_mask(cur)) return OUT_CHECKMATE;
     if (is_insufficient_material(cur)) return OUT_INSUFFICIENT_MATERIAL;
@@ -593,29 +617,21 @@ CB_HDN int outcome_claim_draw(const Pos& cur, const MoveList& legal, const Pos* 
     }
     // can_claim_threefold_repetition
     if (cur.occur >= 3) return OUT_THREEFOLD_REPETITION;
-    // claim-ahead: a legal move reaches a position already seen twice since the last irreversible
-    // move.  Only reversible moves can (others change material, pawns or castling rights), and the
-    // record must reach at least three plies back without crossing an irreversible move.
+    // claim-ahead needs a record that reaches at least three plies back without crossing an irreversible move
     if (cur.irrev_in || !before || before->irrev_in) return OUT_NONE;
     const Pos* b2 = prev(before);
     if (!b2 || b2->irrev_in || !prev(b2)) return OUT_NONE;
-    for (int i = 0; i < legal.n; ++i) {
-        Move m = legal.m[i];
-        if (is_zeroing(cur, m)) continue;
-        Pos nxt = push_move(cur, m);
-        if (nxt.irrev_in) continue;
-        int n = 0, k = 1;
-        const Pos* walk = &cur;
-        const Pos* q = before;
-        while (!walk->irrev_in && q) {  // same side to move as nxt: 1, 3, 5, ... plies back
-            if ((k & 1) && key_equal(*q, nxt)) {
-                if (++n >= 2) return OUT_THREEFOLD_REPETITION;
-            }
-            walk = q;
-            q = prev(q);
-            ++k;
-        }
-    }
+    *scan = true;
+    return OUT_NONE;
+}
+
+template <class PrevFn>
+CB_HDN int outcome_claim_draw(const Pos& cur, const MoveList& legal, const Pos* before, PrevFn prev, int max_len) {
+    bool scan;
+    const int out = outcome_before_scan(cur, legal, before, prev, max_len, &scan);
+    if (!scan) return out;
+    for (int i = 0; i < legal.n; ++i)
+        if (move_claims_threefold(cur, legal.m[i], before, prev)) return OUT_THREEFOLD_REPETITION;
     return OUT_NONE;
 }
 // terminal_value(to_play) of game.py:61-77 for the side to move at a terminal position
