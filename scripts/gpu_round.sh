@@ -9,10 +9,10 @@ python bench.py > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err; echo 
 if [ "$2" != "skip-ncu" ]; then
   CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-sims 2"
   $CMD > gpurun_out/plain_$tag.log 2>&1 &&
-  ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches_$tag.csv $CMD > gpurun_out/ncu_launches_$tag.log 2>&1
+  ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_$tag.csv $CMD > gpurun_out/ncu_launches_$tag.log 2>&1
   echo "ncu launches rc=$?"
   $CMD > gpurun_out/plain_$tag.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:conv3x3_tcgen05 -s 60 -c 2 -f -o gpurun_out/prof_conv_$tag $CMD > gpurun_out/ncu_full_$tag.log 2>&1
+  ncu --set full --clock-control none --import-source on -k "regex:tower_tcgen05|mcts_step|encode_planes" -s 9 -c 3 -f -o gpurun_out/prof_$tag $CMD > gpurun_out/ncu_full_$tag.log 2>&1
   echo "ncu full rc=$?"; tail -n 3 gpurun_out/ncu_full_$tag.log
 fi
 exit $trc
