@@ -284,11 +284,11 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)               # started before the warm-up: nvidia-smi needs ~0.2 s to deliver its first sample
+    sampler.start()
     eng.search_run(W)                                # warm-up steps (incl. the root expansion)
     barrier()
     c0 = eng.search_status()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record(stream)
@@ -393,6 +393,81 @@ def run_gpu_arm(args):
         dist.destroy_process_group()
 
 
+def run_leaf_eval_arm(args):
+    """BASELINE config 2: batched leaf evaluation of `trees` synthetic positions outside a tree — encode + forward
+    (dense 4672 logits) + legal-move mask / softmax — on one GPU per rank.  A step = one pass over the batch."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from chessbot_b200.engine import Engine
+    from chessbot_b200.model import DeviceNetwork, keras_init_weights
+    filters, blocks = parse_net(args.net)
+    n, W, K = args.trees, args.warmup, args.steps
+    eng = Engine.get(local_rank)
+    DeviceNetwork(trained_like_bn(keras_init_weights(filters, blocks, seed=0), filters, blocks), filters, blocks, max_batch=n, device=local_rank)
+    records = [b.export_record() for b in random_positions_device(n, seed=1000 + rank)]
+    pos, fi = eng.upload_records(records)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for _ in range(max(W, 50)):
+        eng.evaluate_positions(None, pos, fi)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(K):
+        eng.evaluate_positions(None, pos, fi)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    eng.profile(True)
+    for _ in range(K):
+        eng.evaluate_positions(None, pos, fi)
+    prof = eng.profile_read()
+    eng.profile(False)
+    t0 = time.perf_counter()
+    reps = max(3, K // 10)
+    for _ in range(reps):                                    # end to end: host records -> H2D -> kernels -> priors D2H
+        out = eng.evaluate_positions(records)
+        host = [t.cpu() for t in out]
+    e2e_dt = time.perf_counter() - t0
+    h2d = sum(r.nbytes for r in records) + n * 32
+    d2h = sum(t.numel() * t.element_size() for t in host)
+    if world > 1:
+        t = torch.tensor([ms, e2e_dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_dt = t.tolist()
+    if rank == 0:
+        peak_tf, peak_gbs, peak_src = measured_peaks()
+        conv_ms = prof["conv"][0]
+        tf = conv_flops_per_position(filters, blocks) * n * K / (conv_ms * 1e-3) / 1e12
+        tot = sum(v[0] for v in prof.values())
+        print(json.dumps({
+            "metric": METRIC, "value": world * n * K / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"batched leaf eval: {blocks}x{filters} ResNet, {n} synthetic positions per GPU, encode + forward + legal-move mask/softmax",
+                       "net": args.net, "positions_per_gpu": n, "l2": "inputs resident; activations 3 x %.0f MB per pass" % (n * 32 * filters * 1.6 / 1e6)},
+            "roofline": {"bound": "tensor", "kernel": "tower_tcgen05_kernel", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
+                         "traffic": None, "peak_source": peak_src},
+            "kernels": {k: {"launches": v[1], "avg_us": 1e3 * v[0] / max(v[1], 1), "share_of_step": v[0] / tot} for k, v in prof.items() if v[1]},
+            "e2e": {"value": world * n * reps / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": K * 6, "clocks": clocks, "cpu_baseline": None}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -400,13 +475,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--net", default="20x256", help="blocks x filters (BASELINE north_star: 20x256 at batch 1024)")
     ap.add_argument("--trees", type=int, default=1024, help="concurrent games per GPU = batch of leaves per step")
-    ap.add_argument("--e2e-sims", type=int, default=16)
+    ap.add_argument("--e2e-sims", type=int, default=100, help="simulations per search of the end-to-end leg (run_mcts default, mcts.py:38)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="search", choices=["search", "leaf_eval"],
+                    help="search = the headline (batched MCTS, BASELINE north_star); leaf_eval = BASELINE config 2 (use --net 6x128)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.workload == "leaf_eval":
+        run_leaf_eval_arm(args)
     else:
         run_gpu_arm(args)
 

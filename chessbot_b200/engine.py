@@ -133,6 +133,19 @@ class Engine:
                                     _ptr(priors), _ptr(counts), _stream()), "policy_softmax")
         return moves, actions, priors, counts
 
+    def evaluate_positions(self, records, pos=None, frame_idx=None):
+        """BASELINE config 2 — batched leaf evaluation outside a tree: encode (K1) -> tower + heads (K2-K4, dense
+        bf16 logits) -> legal-move gather / exp / normalise (K5).  records: game records of the positions (host),
+        or pos / frame_idx already on the device.  Returns device tensors (value [n], moves [n,224] uint16 codes as
+        int16, actions [n,224], priors [n,224] f32, n_moves [n])."""
+        if pos is None:
+            pos, frame_idx = self.upload_records(records)
+        n = frame_idx.shape[0]
+        act, _ = self.encode(pos, frame_idx)
+        value, lb, _ = self.forward(act, n, want_bf16=True, want_f32=False)
+        moves, actions, priors, counts = self.policy_softmax(pos, frame_idx[:, 0].contiguous(), lb)
+        return value, moves, actions, priors, counts
+
     PROF_STAGES = ("encode", "conv", "heads", "mcts_step", "policy_dense", "policy_softmax")
 
     def profile(self, enable):

@@ -39,21 +39,32 @@ class Node:
 
 
 # ------------------------------------------------------------------------------ device search
+_UCI = {}
+
+
+def _uci(code):
+    """uci string of a packed move (from | to << 6 | promo << 12), memoised: 1792 x 5 distinct values at most."""
+    u = _UCI.get(code)
+    if u is None:
+        from .board import code_to_uci
+        u = _UCI[code] = code_to_uci(code)
+    return u
+
+
 def _root_from_device(out, i):
-    from .board import code_to_uci
+    """Root Node with its children dict (legal-move order) from the read-back root statistics of tree i."""
     root = Node()
     root.N = int(out["root_N"][i])
     k = int(out["n_children"][i])
+    moves = out["moves"][i, :k].tolist()
+    ns = out["N"][i, :k].tolist()
+    ws, qs = list(out["W"][i, :k]), list(out["Q"][i, :k])                 # np.float32 scalars, like the reference's nodes
+    ps = list(out["P"][i, :k]) if out["noisy"][i] else list(out["P"][i, :k].astype(np.float32))
+    children = root.children
     for j in range(k):
-        c = Node()
-        c.parent = root
-        c.N = int(out["N"][i, j])
-        c.W = out["W"][i, j]
-        c.Q = out["Q"][i, j]
-        p = out["P"][i, j]
-        c.P = p if out["noisy"][i] else np.float32(p)
-        root.children[code_to_uci(out["moves"][i, j])] = c
-    # root.W / root.Q: sum over children with the sign flip of the backup
+        c = Node.__new__(Node)
+        c.parent, c.children, c.N, c.W, c.P, c.Q = root, {}, ns[j], ws[j], ps[j], qs[j]
+        children[_uci(moves[j])] = c
     return root
 
 
@@ -81,20 +92,19 @@ def _external_search(engine, network, records, sims, cpuct, noise, max_len):
     return out
 
 
-def run_mcts_batch(games, network, num_simulations=100, num_sampling_moves=30, add_noise=True, CPUCT=None,
-                   rng=None, noise=None):
-    """run_mcts for a list of games in one device batch.  num_simulations / add_noise / CPUCT may be
-    scalars or per-game lists.  `noise`: optional per-game pre-drawn Gamma(0.3, 1) samples (else drawn
-    from `rng` like mcts.py:158).  Returns [(move_uci, root Node), ...]."""
+def search_batch(games, network, num_simulations=100, add_noise=True, CPUCT=None, rng=None, noise=None):
+    """The search of run_mcts (mcts.py:50-74) for a list of games in one device batch, without the final move
+    choice.  num_simulations / add_noise / CPUCT may be scalars or per-game lists.  `noise`: optional per-game
+    pre-drawn Gamma(0.3, 1) samples (else drawn from `rng` like mcts.py:158).  Returns the root Nodes."""
     from .engine import EVAL_NET, EVAL_SYNTH, Engine
     from .gameimage import as_device_board
     n = len(games)
-    rng = np.random.default_rng() if rng is None else rng
     sims = [num_simulations] * n if np.isscalar(num_simulations) else list(num_simulations)
     noisy = [bool(add_noise)] * n if isinstance(add_noise, (bool, np.bool_)) else [bool(a) for a in add_noise]
     cpuct = [CPUCT] * n if (CPUCT is None or np.isscalar(CPUCT)) else list(CPUCT)
     boards = [as_device_board(g.board) for g in games]
     if noise is None:
+        rng = np.random.default_rng() if rng is None else rng
         noise = [rng.gamma(ROOT_DIRICHLET_ALPHA, 1, len(b.legal_moves)) if z else None for b, z in zip(boards, noisy)]
     else:
         noise = [z if f else None for z, f in zip(noise, noisy)]
@@ -120,9 +130,16 @@ def run_mcts_batch(games, network, num_simulations=100, num_sampling_moves=30, a
     else:
         out = _external_search(engine, network, records, sims, cpuct, noise if has_noise else None, max_len)
     out["noisy"] = [z is not None for z in noise]
+    return [_root_from_device(out, i) for i in range(n)]
+
+
+def run_mcts_batch(games, network, num_simulations=100, num_sampling_moves=30, add_noise=True, CPUCT=None,
+                   rng=None, noise=None):
+    """run_mcts for a list of games in one device batch (one tree per game).  Returns [(move_uci, root Node), ...]."""
+    rng = np.random.default_rng() if rng is None else rng
+    roots = search_batch(games, network, num_simulations, add_noise, CPUCT, rng=rng, noise=noise)
     results = []
-    for i, g in enumerate(games):
-        root = _root_from_device(out, i)
+    for g, root in zip(games, roots):
         temp = TEMP if g.history_len < num_sampling_moves else 0
         results.append((select_move(root, rng, temp), root))
     return results

@@ -1,0 +1,109 @@
+"""Callers of the hot path: the self-play game loop and replay format of train.py
+(train.py:13-52,77-78,104-110) and the puzzle bot of eval_trt.py (eval_trt.py:31-39), over the batched
+device search.  Many games advance together: every move of every live game is one tree of one
+`mcts.search_batch` call."""
+import numpy as np
+
+from . import actionspace as asp
+from . import gameimage, mcts
+from .config import Config
+from .game import Game
+
+
+def calc_search_statistics(config: Config, root, to_play):
+    """train.py:13-19: visit distribution over the 4672 actions, float64."""
+    sum_visits = sum([child.N for child in root.children.values()])
+    child_visits = np.zeros(config.num_actions)
+    for uci_move, child in root.children.items():
+        child_visits[asp.uci_to_action(uci_move, to_play)] = child.N / sum_visits
+    return child_visits
+
+
+def playout_cap(config: Config, u: float):
+    """train.py:29-31 for one uniform draw u: (do_full_search, num_simulations, CPUCT).  The reference compares
+    the BOOL with the probability (`do_full_search < num_mcts_sims_p`), so a full search gets num_mcts_sims[1]
+    (300) simulations and a quick one num_mcts_sims[0] (50)."""
+    do_full_search = True if u < config.num_mcts_sims_p else False
+    num_simulations = config.num_mcts_sims[0] if do_full_search < config.num_mcts_sims_p else config.num_mcts_sims[1]
+    return do_full_search, num_simulations, (None if do_full_search else 1.0)
+
+
+def play_games(network, n_games=1, config: Config = None, rngs=None, games=None):
+    """train.py:21-52 for n_games games at once.  rngs: one np.random.Generator per game (default: unseeded,
+    like the reference); game i consumes its own stream in the reference's order — playout-cap draw, root noise
+    (full searches), move choice — so a game does not depend on which other games share its batch.
+    Returns, per game, the reference's play_game tuple:
+    (images, (terminal_values, search_statistics), outcome_str, history_len)."""
+    config = Config() if config is None else config
+    games = [Game(config) for _ in range(n_games)] if games is None else list(games)
+    n_games = len(games)
+    rngs = [np.random.default_rng() for _ in range(n_games)] if rngs is None else list(rngs)
+    stats = [[] for _ in range(n_games)]
+    images = [[] for _ in range(n_games)]
+    on_turn = [[] for _ in range(n_games)]
+    live = [i for i in range(n_games) if not games[i].terminal()]
+    while live:
+        full, sims, cpuct, noise = [], [], [], []
+        for i in live:
+            f, s, c = playout_cap(config, rngs[i].random())
+            full.append(f); sims.append(s); cpuct.append(c)
+            noise.append(rngs[i].gamma(mcts.ROOT_DIRICHLET_ALPHA, 1, len(games[i].board.legal_moves)) if f else None)
+        roots = mcts.search_batch([games[i] for i in live], network, sims, full, cpuct, noise=noise)
+        rec = [k for k, f in enumerate(full) if f]          # only full-search moves are training samples (train.py:43-47)
+        if rec:
+            imgs = gameimage.boards_to_images([games[live[k]].board for k in rec], config.T).astype(np.int16)
+            for img, k in zip(imgs, rec):
+                g = games[live[k]]
+                stats[live[k]].append(calc_search_statistics(config, roots[k], g.to_play()))
+                images[live[k]].append(img)
+                on_turn[live[k]].append(g.to_play())
+        for k, i in enumerate(live):
+            temp = mcts.TEMP if games[i].history_len < config.num_mcts_sampling_moves else 0
+            games[i].make_move(mcts.select_move(roots[k], rngs[i], temp))
+        live = [i for i in live if not games[i].terminal()]
+    out = []
+    for i, g in enumerate(games):
+        terminal_values = [g.terminal_value(player) for player in on_turn[i]]
+        out.append((images[i], (terminal_values, stats[i]), g.outcome_str, g.history_len))
+    return out
+
+
+def play_game(network, config: Config = None, rng=None):
+    """train.py:21-52, one game."""
+    return play_games(network, 1, config, None if rng is None else [rng])[0]
+
+
+def buffer_entries(game_result):
+    """train.py:77-78: the (image, (terminal_value, search_statistic)) samples a finished game appends to the buffer."""
+    images, (terminal_values, search_statistics), _, _ = game_result
+    return [(img, (z, pi)) for img, z, pi in zip(images, terminal_values, search_statistics)]
+
+
+def sample_buffer(buffer, batch_size: int, rng=None):
+    """train.py:104-110: uniform sampling without replacement."""
+    rng = np.random.default_rng() if rng is None else rng
+    batch = rng.choice(len(buffer), size=batch_size, replace=False)
+    images = np.array([buffer[b][0] for b in batch])
+    terminal_values = np.array([buffer[b][1][0] for b in batch])
+    search_statistics = np.array([buffer[b][1][1] for b in batch])
+    return images, (terminal_values, search_statistics)
+
+
+class Bot:
+    """eval_trt.py:31-39 (`bot.get_move(board)` is all puzzles.Puzzle.solve needs, puzzles.py:83-86), plus
+    get_moves for many boards in one device batch.  Deterministic by default: no root noise, arg-max visits."""
+
+    def __init__(self, model, config: Config = None, num_simulations=None, add_noise=False, rng=None):
+        self.model = model
+        self.config = Config() if config is None else config
+        self.num_simulations = self.config.num_mcts_sims[1] if num_simulations is None else num_simulations
+        self.add_noise = add_noise
+        self.rng = np.random.default_rng() if rng is None else rng
+
+    def get_moves(self, boards):
+        games = [Game(self.config, board=b) for b in boards]
+        res = mcts.run_mcts_batch(games, self.model, self.num_simulations, 0, self.add_noise, None, rng=self.rng)
+        return [move for move, _ in res]
+
+    def get_move(self, board):
+        return self.get_moves([board])[0]

@@ -210,3 +210,67 @@ def test_game_make_image_and_gameimage_helpers(golden_dir):
     game = _game(None, "e2e4 e7e5 g1f3".split())
     assert np.array_equal(game.make_image(-1), gi.board_to_image(game.board, 8))
     assert np.array_equal(game.make_image(1), gi.board_to_image(_game(None, ["e2e4"]).board, 8))
+
+
+def test_self_play_games_match_oracle_move_for_move():
+    """§8(f) row 2: train.py:21-52 (playout-cap randomisation, per-move search, sample format) for several
+    concurrent device games against the oracle playing the same games one by one with the same per-game
+    random streams: identical move sequences, samples, outcomes."""
+    from chessbot_b200 import selfplay
+    from chessbot_b200.config import Config
+    from chessbot_b200.model import SyntheticNetwork
+    from oracle import pychess_shim as ochess
+    from oracle import ref_actionspace, ref_mcts, synthetic_net
+    from oracle.ref_game import Game as OGame
+    from oracle.ref_game import OracleConfig
+    cfg = Config()
+    cfg.num_mcts_sims, cfg.num_mcts_sampling_moves, cfg.max_game_length = (6, 20), 8, 30
+    n = 5
+    res = selfplay.play_games(SyntheticNetwork(seed=11), n, cfg, rngs=[np.random.default_rng(100 + i) for i in range(n)])
+    for i in range(n):
+        ocfg = OracleConfig(max_game_length=30)
+        ocfg.num_mcts_sims, ocfg.num_mcts_sampling_moves = (6, 20), 8
+        game, rng = OGame(ocfg), np.random.default_rng(100 + i)
+        images, stats, turns = [], [], []
+        while not game.terminal():
+            full, sims, cpuct = selfplay.playout_cap(ocfg, rng.random())
+            move, tree = ref_mcts.run_mcts(game, synthetic_net.as_network(11), sims, 8, full, cpuct, rng=rng)
+            if full:
+                kids = list(tree.children(0))
+                total = sum(tree.N[c] for c in kids)
+                pi = np.zeros(4672)
+                for c in kids:
+                    pi[ref_actionspace.uci_to_action(tree.move[c], game.to_play())] = tree.N[c] / total
+                stats.append(pi)
+                images.append(game.make_image(-1))
+                turns.append(game.to_play())
+            game.make_move(move)
+        got_images, (got_z, got_pi), outcome_str, history_len = res[i]
+        assert history_len == game.history_len and outcome_str == game.outcome_str
+        assert len(got_images) == len(images) and all(np.array_equal(a, b) and a.dtype == np.int16 for a, b in zip(got_images, images))
+        assert all(np.array_equal(a, b) and a.dtype == np.float64 for a, b in zip(got_pi, stats))
+        assert got_z == [game.terminal_value(p) for p in turns]
+    entries = [e for r in res for e in selfplay.buffer_entries(r)]
+    if len(entries) >= 2:
+        imgs, (z, pi) = selfplay.sample_buffer(entries, 2, np.random.default_rng(0))
+        assert imgs.shape == (2, 8, 8, 119) and pi.shape == (2, 4672) and z.shape == (2,)
+
+
+def test_puzzle_bot_matches_oracle_search():
+    """§8(f) row 3: eval_trt.Bot.get_move(board) over the batched search (puzzles.Puzzle.solve calls nothing else)."""
+    from chessbot_b200 import selfplay
+    from chessbot_b200.board import Board
+    from chessbot_b200.model import SyntheticNetwork
+    from oracle import pychess_shim as ochess
+    from oracle import ref_mcts, synthetic_net
+    from oracle.ref_game import Game as OGame
+    from oracle.ref_game import OracleConfig
+    fens = ["r1bqkb1r/pppp1ppp/2n2n2/4p2Q/2B1P3/8/PPPP1PPP/RNB1K1NR w KQkq - 4 4",      # mate in one
+            "6k1/5ppp/8/8/8/8/5PPP/3R2K1 w - - 0 1", "7k/6p1/8/8/8/8/1P6/K7 w - - 1 1"]
+    bot = selfplay.Bot(SyntheticNetwork(seed=2), num_simulations=40)
+    moves = bot.get_moves([Board(f) for f in fens])
+    assert bot.get_move(Board(fens[0])) == moves[0]
+    for f, mv in zip(fens, moves):
+        omove, _ = ref_mcts.run_mcts(OGame(OracleConfig(), board=ochess.Board(f)), synthetic_net.as_network(2), 40, 0, False, None,
+                                     rng=_Rng())
+        assert mv == omove

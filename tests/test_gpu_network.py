@@ -121,3 +121,34 @@ def test_forward_is_batch_invariant(engine):
     v1, lb1, _ = engine.forward(act1, 1)
     torch.cuda.synchronize()
     assert torch.equal(v_all[17:18], v1) and torch.equal(lb_all[17:18], lb1)
+
+
+def test_batched_leaf_eval_pipeline_6x128(engine):
+    """BASELINE config 2: encode + forward + legal-move mask/softmax for a batch of positions, against the oracle
+    (torch-fp32 network, NumPy softmax over the legal moves).  Moves / action indices exact; priors follow the
+    2e-2 logit tolerance: |dP| <= 6 % of P (exp of a 2.5e-2 logit difference, twice for the normalisation)."""
+    from gpu_util import oracle_board, random_games
+    from chessbot_b200.board import code_to_uci
+    from oracle import ref_actionspace, ref_gameimage, ref_model
+    n = 96
+    games = random_games(n, seed=61, max_plies=140)
+    obs = [oracle_board(f, m) for f, m in games]
+    images = np.stack([ref_gameimage.board_to_image(ob, 8) for ob in obs])
+    w = ref_model.calibrate_bn(ref_model.init_weights(128, 6, seed=9), images, device="cuda")
+    engine.load_network(w, 128, 6, max_batch=n)
+    from gpu_util import device_board
+    value, moves, actions, priors, counts = engine.evaluate_positions([device_board(f, m).export_record() for f, m in games])
+    torch.cuda.synchronize()
+    value, moves, actions, priors, counts = (t.cpu().numpy() for t in (value, moves, actions, priors, counts))
+    v_ref, p_ref = ref_model.forward(w, images, device="cuda")
+    assert np.abs(value - v_ref).max() <= TOL
+    for i, ob in enumerate(obs):
+        legal = [mv.uci() for mv in ob.legal_moves]
+        k = counts[i]
+        assert [code_to_uci(c) for c in moves[i, :k].astype(np.uint16)] == legal
+        acts = [ref_actionspace.uci_to_action(u, ob.turn) for u in legal]
+        assert list(actions[i, :k]) == acts
+        e = np.exp(p_ref[i, acts], dtype=np.float32)
+        ref = e / np.sum(e, dtype=np.float32)
+        assert np.abs(priors[i, :k] - ref).max() <= 0.06 * ref.max() and abs(float(priors[i, :k].sum()) - 1) < 1e-5
+        assert np.all(np.abs(priors[i, :k] - ref) <= 0.06 * ref + 1e-6)

@@ -175,3 +175,79 @@ def test_device_network_search_matches_oracle_on_same_outputs(engine):
 
         _, tree = run_with_device_outputs()
         _compare_tree(out, i, tree)
+
+
+def test_config1_single_game_start_position_100_sims_default_net(engine):
+    """BASELINE config 1: single game from the start position, 100 sims, the repo-default 4x48 net, batch 1 —
+    the device tree against the oracle fed with the device network's own outputs (visit counts identical)."""
+    from chessbot_b200.board import Board
+    from chessbot_b200.engine import EVAL_NET
+    from oracle import pychess_shim as ochess
+    from oracle import ref_mcts, ref_model
+    from oracle.ref_game import Game, OracleConfig
+    w = ref_model.init_weights(48, 4, seed=1)
+    engine.load_network(w, 48, 4, max_batch=64)
+    noise = np.random.default_rng(5).gamma(0.3, 1, 256)
+    out = engine.search([Board().export_record()], 100, noise=[noise], eval_mode=EVAL_NET)
+
+    def expand_with_device_outputs(tree, node, g, network, exp_fn=ref_mcts.default_exp):
+        db = Board()
+        for mv in g.board.move_stack:
+            db.push_uci(mv.uci())
+        pos, fi = engine.upload_records([db.export_record()])
+        act, _ = engine.encode(pos, fi)
+        v, lb, _ = engine.forward(act, 1)
+        torch.cuda.synchronize()
+        logits = lb.float().cpu().numpy()[0]
+        moves, actions = ref_mcts.legal_actions(g)
+        p = exp_fn(logits[np.asarray(actions, dtype=np.int64)])
+        s = np.sum(p, dtype=np.float32)
+        tree.add_children(node, moves, [np.float32(x / s) for x in p])
+        return np.float32(v.cpu().numpy()[0])
+
+    orig = ref_mcts.expand
+    ref_mcts.expand = expand_with_device_outputs
+    try:
+        _, tree = ref_mcts.run_mcts(Game(OracleConfig(), board=ochess.Board()), None, 100, 30, True, None, rng=_FixedRng(noise), noise=noise)
+    finally:
+        ref_mcts.expand = orig
+    _compare_tree(out, 0, tree)
+    assert out["root_N"][0] == 101 and out["sims"] == 100
+
+
+def test_config3_512_games_800_sims_20x256_properties():
+    """BASELINE config 3 at full size (512 concurrent games x 800 simulations, 20x256 net) through size-independent
+    properties: every tree finishes with exactly 800 visits below the root, Q == W / N bit for bit, priors sum to
+    one, and a tree's statistics do not depend on the batch it was searched in (re-searched alone: identical)."""
+    import random
+    from chessbot_b200.board import Board
+    from chessbot_b200.engine import EVAL_NET, Engine
+    from chessbot_b200.model import keras_init_weights
+    import bench
+    eng = Engine.get()
+    eng.load_network(bench.trained_like_bn(keras_init_weights(256, 20, seed=0), 256, 20), 256, 20, max_batch=512)
+    eng.search_create(max_trees=512, max_nodes=512 * 802 * 40, max_positions=512 * 1100, max_sims=800)
+    rnd = random.Random(3)
+    recs = []
+    for _ in range(512):                                  # self-play openings: 0..11 random plies from the start position
+        b = Board()
+        for _ in range(rnd.randint(0, 11)):
+            b.push(rnd.choice(list(b.legal_moves)))
+        recs.append(b.export_record())
+    noise = [np.random.default_rng(i).gamma(0.3, 1, 256) for i in range(512)]
+    out = eng.search(recs, 800, noise=noise, eval_mode=EVAL_NET)
+    assert out["unfinished"] == 0 and out["errors"] == 0 and out["sims"] == 512 * 800 and out["evals"] <= 512 * 801
+    for i in range(512):
+        k = out["n_children"][i]
+        n, w, q, p = out["N"][i, :k], out["W"][i, :k], out["Q"][i, :k], out["P"][i, :k]
+        assert out["root_N"][i] == 801 and n.sum() == 800 and (n >= 0).all()
+        vis = n > 0
+        assert np.array_equal(q[vis], (w[vis] / n[vis].astype(np.float32)).astype(np.float32)) and not q[~vis].any()
+        assert np.isfinite(p).all() and (np.abs(w) <= n + 1e-3).all()
+    for i in (0, 137, 511):
+        alone = eng.search([recs[i]], 800, noise=[noise[i]], eval_mode=EVAL_NET)
+        k = out["n_children"][i]
+        assert alone["n_children"][0] == k and np.array_equal(alone["moves"][0, :k], out["moves"][i, :k])
+        for key in ("N", "W", "Q", "P"):
+            assert np.array_equal(alone[key][0, :k], out[key][i, :k]), (i, key)
+        assert alone["nodes"][0] == out["nodes"][i]
