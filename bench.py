@@ -469,6 +469,9 @@ def run_leaf_eval_arm(args):
 
 
 def main():
+    # NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION; the bench prints exactly one JSON line there
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
