@@ -86,7 +86,7 @@ struct Search {
     DevBuf<Node> nodes;
     DevBuf<Pos> pos;
     DevBuf<TreeState> trees;
-    DevBuf<int32_t> node_count, pos_count, frame_idx, counters, scratch_i32;
+    DevBuf<int32_t> node_count, pos_count, frame_idx, counters, scratch_i32, path;
     DevBuf<uint16_t> pend_moves;
     DevBuf<double> root_p64, noise, cpuct_tab, sqrt_tab;
     DevBuf<float> value, expvals;
@@ -449,9 +449,12 @@ int cb_search_create(cb_ctx* ctx, int max_trees, int max_nodes, int max_position
     Search& s = ctx->search;
     s.max_trees = max_trees;
     s.max_sims = max_sims;
+    // every tree allocates from the pools in chunks: the last chunk of each tree may stay partly unused
+    max_nodes += max_trees * NODE_CHUNK;
+    max_positions += max_trees * POS_CHUNK;
     const size_t mt = max_trees, mm = (size_t)max_trees * MAX_MOVES;
     if (s.nodes.alloc(max_nodes, false) || s.pos.alloc(max_positions, false) || s.trees.alloc(mt) || s.node_count.alloc(1) ||
-        s.pos_count.alloc(1) || s.frame_idx.alloc(mt * 8) || s.counters.alloc(4) || s.scratch_i32.alloc(4) || s.pend_moves.alloc(mm) ||
+        s.pos_count.alloc(1) || s.frame_idx.alloc(mt * 8) || s.path.alloc(mt * MCTS_MAX_PATH) || s.counters.alloc(4) || s.scratch_i32.alloc(4) || s.pend_moves.alloc(mm) ||
         s.root_p64.alloc(mm) || s.noise.alloc(mm) || s.value.alloc(mt) || s.synth_hash.alloc(mt) ||
         s.planes_act.alloc(act_bytes(max_trees, 128) / 2) || s.planes_i16.alloc(mt * 7616) || s.flags.alloc(mt) ||
         s.r_moves.alloc(mm) || s.r_n.alloc(mm) || s.r_w.alloc(mm) || s.r_q.alloc(mm) || s.r_p.alloc(mm) || s.r_nc.alloc(mt) ||
@@ -470,7 +473,7 @@ int cb_search_create(cb_ctx* ctx, int max_trees, int max_nodes, int max_position
     SearchParams& sp = s.sp;
     sp.nodes = s.nodes.p; sp.node_count = s.node_count.p; sp.max_nodes = max_nodes;
     sp.pos = s.pos.p; sp.pos_count = s.pos_count.p; sp.max_pos = max_positions;
-    sp.trees = s.trees.p; sp.pend_moves = s.pend_moves.p; sp.frame_idx = s.frame_idx.p; sp.root_p64 = s.root_p64.p;
+    sp.trees = s.trees.p; sp.path = s.path.p; sp.pend_moves = s.pend_moves.p; sp.frame_idx = s.frame_idx.p; sp.root_p64 = s.root_p64.p;
     sp.noise = s.noise.p; sp.cpuct_tab = s.cpuct_tab.p; sp.sqrt_tab = s.sqrt_tab.p; sp.tab_len = tl;
     sp.value = s.value.p; sp.synth_hash = s.synth_hash.p; sp.exp_table = ctx->exp_table.p; sp.counters = s.counters.p;
     return 0;

@@ -80,10 +80,13 @@ struct Node {  // 32 bytes; children of a node are contiguous, in legal-move ord
 };
 static_assert(sizeof(Node) == 32, "Node must be 32 bytes");
 
+constexpr int MCTS_MAX_PATH = 128;  // deeper paths fall back to walking parent links
 enum { TREE_IDLE = 0, TREE_WAIT_ROOT = 1, TREE_WAIT_LEAF = 2, TREE_DONE = 3 };
 enum { EVAL_NET = 0, EVAL_SYNTH = 1, EVAL_EXTERNAL = 2 };
 
-struct TreeState {  // 64 bytes
+constexpr int NODE_CHUNK = 4096;  // nodes a tree takes from the global pool at a time (one contended atomic per ~100 expansions)
+constexpr int POS_CHUNK = 128;    // positions likewise
+struct TreeState {  // 80 bytes
     int32_t root_node, root_pos;
     int32_t sims_done, sims_target;
     int32_t leaf_node, leaf_pos;
@@ -92,9 +95,12 @@ struct TreeState {  // 64 bytes
     int32_t noisy;       // add_exploration_noise applied at the root (P held in f64)
     int32_t max_len;     // config.max_game_length
     double cpuct;        // < 0: AlphaZero schedule log((N+19653)/19652)+1.25, else fixed (mcts.py:135-139)
-    int32_t error, pad_;
+    int32_t error;
+    int32_t path_len;    // nodes on the root..leaf path of the pending leaf (SearchParams::path), 0 = not recorded (too deep)
+    int32_t node_next, node_end;  // this tree's current chunk of the node pool: [node_next, node_end) is free
+    int32_t pos_next, pos_end;    // and of the position pool
 };
-static_assert(sizeof(TreeState) == 64, "TreeState must be 64 bytes");
+static_assert(sizeof(TreeState) == 80, "TreeState must be 80 bytes");
 
 struct SearchParams {
     Node* nodes; int32_t* node_count; int32_t max_nodes;
@@ -115,6 +121,7 @@ struct SearchParams {
     const float* expvals;      // EVAL_EXTERNAL: [n_trees][4672] exp(logit) from the host
     const float* exp_table;    // [65536] f32 exp indexed by bf16 bits
     int32_t* counters;         // [0] evals, [1] sims, [2] errors
+    int32_t* path;             // [n_trees][MCTS_MAX_PATH] node ids root..leaf of every pending leaf
 };
 
 int launch_tower(const TowerParams& p, int num_sms, cudaStream_t stream);

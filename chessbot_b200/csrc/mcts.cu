@@ -59,11 +59,41 @@ __device__ void backup(Node* nodes, int node, float v) {
     }
 }
 
+// the same update for a recorded root..leaf path: one node per lane (every node of a path is distinct, each
+// receives exactly one f32 add, so the result does not depend on the order); `v` is the value for the LEAF
+__device__ __forceinline__ void backup_path(Node* nodes, const int32_t* path, int len, float v, int lane) {
+    for (int d = lane; d < len; d += 32) {
+        Node& nd = nodes[path[d]];
+        const int n = nd.N + 1;
+        const float w = __fadd_rn(nd.W, ((len - 1 - d) & 1) ? -v : v);
+        nd.N = n;
+        nd.W = w;
+        nd.Q = __fdiv_rn(w, (float)n);
+    }
+}
+
+// Bump allocation inside a per-tree chunk; only a new chunk touches the global counter (every warp hammering one
+// address costs ~30 cycles per warp at the L2 atomic unit: 1024 trees -> tens of microseconds per step).
+// Returns the first index of `n` contiguous free slots, or -1 when the pool is exhausted.
+__device__ __forceinline__ int chunk_alloc(int32_t& next, int32_t& end, int n, int chunk, int32_t* global_count, int max_total) {
+    if (next + n > end) {
+        const int take = n > chunk ? n : chunk;
+        const int base = atomicAdd(global_count, take);
+        if (base + take > max_total) return -1;
+        next = base;
+        end = base + take;
+    }
+    const int r = next;
+    next += n;
+    return r;
+}
+
 constexpr int MCTS_WARPS = 4;
 
 __global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_step_kernel(SearchParams sp) {
     __shared__ float s_p[MCTS_WARPS][MAX_MOVES];
     __shared__ uint16_t s_m[MCTS_WARPS][MAX_MOVES];
+    __shared__ int32_t s_path[MCTS_WARPS][MCTS_MAX_PATH];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tree = blockIdx.x * MCTS_WARPS + warp;
     if (tree >= sp.n_trees) return;
@@ -103,11 +133,11 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_step_kernel(SearchParams
         const float sum = numpy_sum_f32_warp(pv, n, lane);
         int base = 0;
         if (lane == 0) {
-            base = atomicAdd(sp.node_count, n);
-            if (base + n > sp.max_nodes) { ts.error = 1; atomicAdd(&sp.counters[2], 1); }
+            base = chunk_alloc(ts.node_next, ts.node_end, n, NODE_CHUNK, sp.node_count, sp.max_nodes);
+            if (base < 0) { ts.error = 1; atomicAdd(&sp.counters[2], 1); }
         }
         base = __shfl_sync(0xffffffffu, base, 0);
-        if (base + n > sp.max_nodes) return;
+        if (base < 0) return;
         const bool is_root = status == TREE_WAIT_ROOT;
         for (int i = lane; i < n; i += 32) {
             Node c;
@@ -124,6 +154,7 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_step_kernel(SearchParams
             }
         }
         __syncwarp();
+        const int plen = ts.path_len;
         if (lane == 0) {
             Node& lf = sp.nodes[leaf];
             lf.first_child = base;
@@ -132,15 +163,16 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_step_kernel(SearchParams
             ts.n_evals += 1;
             atomicAdd(&sp.counters[0], 1);
             if (!is_root) {
-                backup(sp.nodes, leaf, -sp.value[tree]);
+                if (plen == 0) backup(sp.nodes, leaf, -sp.value[tree]);
                 ts.sims_done += 1;
                 atomicAdd(&sp.counters[1], 1);
             }
             __threadfence_block();
         }
         __syncwarp();
+        if (!is_root && plen > 0) backup_path(sp.nodes, sp.path + (size_t)tree * MCTS_MAX_PATH, plen, -sp.value[tree], lane);
+        __syncwarp();
     }
-
     // ------------------------------------------------------------------ B. simulate to the next leaf
     int sims_done = __shfl_sync(0xffffffffu, ts.sims_done, 0);
     const int sims_target = ts.sims_target;
@@ -153,9 +185,15 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_step_kernel(SearchParams
         }
         int node = ts.root_node;
         int parent_pos = ts.root_pos;
-        // ---- select (mcts.py:62-64,119-140)
+        int32_t* path = s_path[warp];
+        int depth = 0;  // nodes recorded in path[] (root first); -1: too deep, not recorded
+        // ---- select (mcts.py:62-64,119-140).  The header of the node being expanded (N, first_child, n_children, ...)
+        // travels in registers: it is the child entry the previous level has just read, so a level costs ONE
+        // dependent memory access (its children), not two.
+        Node nd = sp.nodes[node];
         while (true) {
-            const Node nd = sp.nodes[node];
+            if (lane == 0 && depth >= 0) path[depth] = node;
+            depth = (depth >= 0 && depth + 1 < MCTS_MAX_PATH) ? depth + 1 : -1;
             if (nd.n_children == 0) break;
             if (nd.pos_id >= 0) parent_pos = nd.pos_id;
             const int np = nd.N < sp.tab_len ? nd.N : sp.tab_len - 1;
@@ -168,6 +206,7 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_step_kernel(SearchParams
             // which case nothing ever replaces it.
             double best_u = 0, u0 = 0;
             int best_key = -1, best_i = -1;
+            Node best_ch = nd, ch0 = nd;
             for (int i = lane; i < nd.n_children; i += 32) {
                 const Node ch = sp.nodes[nd.first_child + i];
                 double u;
@@ -182,10 +221,10 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_step_kernel(SearchParams
                     t = __fdiv_rn(t, (float)(ch.N + 1));
                     u = (double)__fadd_rn(ch.Q, t);  // f32 value, exactly representable in f64
                 }
-                if (i == 0) u0 = u;
+                if (i == 0) { u0 = u; ch0 = ch; }
                 if (u != u) continue;
                 const int key = uci_sort_key(ch.move);
-                if (best_i < 0 || u > best_u || (u == best_u && key > best_key)) { best_u = u; best_key = key; best_i = i; }
+                if (best_i < 0 || u > best_u || (u == best_u && key > best_key)) { best_u = u; best_key = key; best_i = i; best_ch = ch; }
             }
             for (int o = 16; o > 0; o >>= 1) {
                 const double ou = __shfl_xor_sync(0xffffffffu, best_u, o);
@@ -195,9 +234,23 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_step_kernel(SearchParams
             }
             u0 = __shfl_sync(0xffffffffu, u0, 0);
             best_i = __shfl_sync(0xffffffffu, best_i, 0);   // one decision for the whole warp
-            if (u0 != u0 || best_i < 0) best_i = 0;
+            if (u0 != u0 || best_i < 0) { best_i = 0; best_ch = ch0; }
             node = nd.first_child + best_i;
+            // the winning child was read by lane best_i % 32 (child 0 by lane 0): broadcast its entry as the next header
+            const int owner = best_i & 31;
+            Node nx;
+            nx.N = __shfl_sync(0xffffffffu, best_ch.N, owner);
+            nx.W = 0.f; nx.Q = 0.f; nx.P = 0.f;
+            nx.first_child = __shfl_sync(0xffffffffu, best_ch.first_child, owner);
+            nx.parent = 0;
+            nx.pos_id = __shfl_sync(0xffffffffu, best_ch.pos_id, owner);
+            const int packed = __shfl_sync(0xffffffffu, (int)best_ch.move | ((int)best_ch.n_children << 16) | ((int)(uint8_t)best_ch.term << 24), owner);
+            nx.move = (uint16_t)(packed & 0xFFFF);
+            nx.n_children = (uint8_t)((packed >> 16) & 0xFF);
+            nx.term = (int8_t)(packed >> 24);
+            nd = nx;
         }
+        __syncwarp();
         // ---- leaf: position, outcome (mcts.py:67, game.py:49-59)
         // lane 0 makes the move and generates the legal moves; the threefold claim-ahead scan (one make-move +
         // history walk per legal move, the expensive part of outcome(claim_draw=True)) runs one move per lane
@@ -205,15 +258,16 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_step_kernel(SearchParams
         uint16_t* sm = s_m[warp];
         if (lane == 0) {
             Node& lf = sp.nodes[node];
-            term = lf.term;
-            leaf_pos = lf.pos_id;
+            term = nd.term;
+            leaf_pos = nd.pos_id;
             if (leaf_pos < 0) {
-                const Pos& pp = sp.pos[parent_pos];
-                Pos np_ = push_move(pp, lf.move);
+                const Pos* ppg = sp.pos + parent_pos;
+                const Pos pp = *ppg;  // private copy: the rules code reads its fields many times
+                Pos np_ = push_move(pp, nd.move);
                 np_.pad_[0] = (uint32_t)parent_pos;
-                np_.occur = (uint8_t)count_occurrences(np_, &pp, PoolPrev{sp.pos});
-                leaf_pos = atomicAdd(sp.pos_count, 1);
-                if (leaf_pos >= sp.max_pos) {
+                np_.occur = (uint8_t)count_occurrences(np_, ppg, PoolPrev{sp.pos});
+                leaf_pos = chunk_alloc(ts.pos_next, ts.pos_end, 1, POS_CHUNK, sp.pos_count, sp.max_pos);
+                if (leaf_pos < 0) {
                     err = 1;
                 } else {
                     sp.pos[leaf_pos] = np_;
@@ -221,7 +275,7 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_step_kernel(SearchParams
                     MoveList ml;
                     generate_legal(np_, ml);
                     bool need_scan = false;
-                    const int out = outcome_before_scan(np_, ml, &pp, PoolPrev{sp.pos}, ts.max_len, &need_scan);
+                    const int out = outcome_before_scan(np_, ml, ppg, PoolPrev{sp.pos}, ts.max_len, &need_scan);
                     if (out != OUT_NONE) term = terminal_value_to_play(out) < 0 ? 2 : 1;
                     n_moves = ml.n;
                     scan = need_scan;
@@ -235,19 +289,30 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_step_kernel(SearchParams
         if (scan) {
             n_moves = __shfl_sync(0xffffffffu, n_moves, 0);
             leaf_pos = __shfl_sync(0xffffffffu, leaf_pos, 0);
-            const Pos& cur = sp.pos[leaf_pos];
+            const Pos cur = sp.pos[leaf_pos];  // private copy per lane
             bool found = false;
             for (int i = lane; i < n_moves && !found; i += 32) found = move_claims_threefold(cur, sm[i], &sp.pos[parent_pos], PoolPrev{sp.pos});
             if (__any_sync(0xffffffffu, found)) term = 1;  // draw by threefold claim
         }
+        err = __shfl_sync(0xffffffffu, err, 0);
+        term = __shfl_sync(0xffffffffu, term, 0);
+        if (!err && term && depth > 0) {
+            // evaluate() returned (value, True): update(node, -value) with value = -1 or 0
+            backup_path(sp.nodes, path, depth, term == 2 ? 1.0f : -0.0f, lane);
+        } else if (!err && !term) {
+            // keep the path for the backup that follows the network evaluation (phase A of the next step)
+            int32_t* gp = sp.path + (size_t)tree * MCTS_MAX_PATH;
+            for (int d = lane; d < depth; d += 32) gp[d] = path[d];
+        }
+        __syncwarp();
         if (lane == 0) {
             if (!err && term) {
                 sp.nodes[node].term = (int8_t)term;
-                // evaluate() returned (value, True): update(node, -value) with value = -1 or 0
-                backup(sp.nodes, node, term == 2 ? 1.0f : -0.0f);
+                if (depth <= 0) backup(sp.nodes, node, term == 2 ? 1.0f : -0.0f);
                 ts.sims_done += 1;
                 atomicAdd(&sp.counters[1], 1);
             } else if (!err) {
+                ts.path_len = depth > 0 ? depth : 0;
                 uint16_t* pm = sp.pend_moves + (size_t)tree * MAX_MOVES;
                 for (int i = 0; i < n_moves; ++i) pm[i] = sm[i];
                 ts.leaf_node = node;
@@ -275,8 +340,8 @@ __global__ void __launch_bounds__(128) mcts_begin_kernel(SearchParams sp) {
     if (tree >= sp.n_trees) return;
     TreeState& ts = sp.trees[tree];
     if (ts.status != TREE_WAIT_ROOT) return;
-    const int node = atomicAdd(sp.node_count, 1);
-    if (node >= sp.max_nodes) { ts.error = 1; atomicAdd(&sp.counters[2], 1); return; }
+    const int node = chunk_alloc(ts.node_next, ts.node_end, 1, NODE_CHUNK, sp.node_count, sp.max_nodes);
+    if (node < 0) { ts.error = 1; atomicAdd(&sp.counters[2], 1); return; }
     Node r;
     r.N = 1; r.W = 0.f; r.Q = 0.f; r.P = 0.f;
     r.first_child = -1; r.parent = -1; r.pos_id = ts.root_pos; r.move = 0; r.n_children = 0; r.term = 0;

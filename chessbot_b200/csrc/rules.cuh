@@ -18,9 +18,13 @@
 #if defined(__CUDACC__)
 #define CB_HD __host__ __device__ __forceinline__
 #define CB_HDN __host__ __device__ inline
+// Large rule functions stay real calls on the device: fully inlined, move generation alone was ~20,000 SASS
+// instructions per call site (0.3 MB), far beyond the instruction cache of an SM running one warp per tree.
+#define CB_HDC __host__ __device__ __noinline__ inline
 #else
 #define CB_HD inline
 #define CB_HDN inline
+#define CB_HDC inline
 #endif
 
 namespace cb {
@@ -175,7 +179,7 @@ CB_HD int piece_type_at(const Pos& p, int sq) {  // -1 if empty
         if (p.bb[t] & b) return t;
     return KING;
 }
-CB_HD u64 attackers_mask(const Pos& p, int color, int sq, u64 occ) {
+CB_HDC u64 attackers_mask(const Pos& p, int color, int sq, u64 occ) {
     u64 qr = p.bb[QUEEN] | p.bb[ROOK], qb = p.bb[QUEEN] | p.bb[BISHOP];
     u64 a = (king_attacks(sq) & p.bb[KING]) | (knight_attacks(sq) & p.bb[KNIGHT]) |
             (rook_attacks(sq, occ) & qr) | (bishop_attacks(sq, occ) & qb) |
@@ -241,7 +245,7 @@ struct MoveList {
 };
 
 // blockers: own pieces that alone stand between the king and an enemy slider
-CB_HD u64 slider_blockers(const Pos& p, int king) {
+CB_HDC u64 slider_blockers(const Pos& p, int king) {
     u64 snipers = ((rook_attacks(king, 0) & (p.bb[ROOK] | p.bb[QUEEN])) |
                    (bishop_attacks(king, 0) & (p.bb[BISHOP] | p.bb[QUEEN]))) & p.occ[p.turn ^ 1];
     u64 occ = occupied(p), blockers = 0;
@@ -262,7 +266,7 @@ CB_HD bool ep_skewered(const Pos& p, int king, int capturer) {
     return false;
 }
 // line on which the piece on sq is pinned to its king, or all ones
-CB_HD u64 pin_mask(const Pos& p, int color, int sq) {
+CB_HDC u64 pin_mask(const Pos& p, int color, int sq) {
     int king = king_square(p, color);
     if (king < 0) return ~0ULL;
     u64 line = line_through(king, sq);
@@ -278,7 +282,7 @@ CB_HD u64 pin_mask(const Pos& p, int color, int sq) {
     }
     return ~0ULL;
 }
-CB_HD bool is_safe(const Pos& p, int king, u64 blockers, Move m) {
+CB_HDC bool is_safe(const Pos& p, int king, u64 blockers, Move m) {
     int f = move_from(m), t = move_to(m);
     if (f == king) {
         if (is_castling_move(p, m)) return true;
@@ -422,7 +426,7 @@ struct Gen {
     }
 };
 
-CB_HDN void generate_legal(const Pos& p, MoveList& out, u64 from_mask = ~0ULL, u64 to_mask = ~0ULL) {
+CB_HDC void generate_legal(const Pos& p, MoveList& out, u64 from_mask = ~0ULL, u64 to_mask = ~0ULL) {
     out.n = 0;
     int king = king_square(p, p.turn);
     if (king < 0) {
@@ -435,12 +439,12 @@ CB_HDN void generate_legal(const Pos& p, MoveList& out, u64 from_mask = ~0ULL, u
     if (checkers) g.evasions(checkers, from_mask, to_mask);
     else g.pseudo_legal(from_mask, to_mask);
 }
-CB_HDN bool has_legal_moves(const Pos& p) {
+CB_HDC bool has_legal_moves(const Pos& p) {
     MoveList ml;
     generate_legal(p, ml);
     return ml.n > 0;
 }
-CB_HDN bool has_legal_en_passant(const Pos& p) {
+CB_HDC bool has_legal_en_passant(const Pos& p) {
     if (p.ep < 0) return false;
     // cheap reject: no own pawn attacks the ep square
     if (!(p.bb[PAWN] & p.occ[p.turn] & pawn_attacks(p.turn ^ 1, p.ep))) return false;
@@ -486,7 +490,7 @@ CB_HD void set_piece(Pos& p, int sq, int type, int color) {
 }
 // Board after `m` (python-chess Board.push).  Fills everything except `occur`, which needs the record
 // before it (see count_occurrences).  `m` must be legal.
-CB_HDN Pos push_move(const Pos& prev, Move m) {
+CB_HDC Pos push_move(const Pos& prev, Move m) {
     Pos p = prev;
     int f = move_from(m), t = move_to(m), promo = move_promo(m);
     int us = prev.turn;
