@@ -274,3 +274,30 @@ def test_puzzle_bot_matches_oracle_search():
         omove, _ = ref_mcts.run_mcts(OGame(OracleConfig(), board=ochess.Board(f)), synthetic_net.as_network(2), 40, 0, False, None,
                                      rng=_Rng())
         assert mv == omove
+
+
+def test_config4_top_move_agreement_with_fp32_reference_path():
+    """BASELINE config 4 at test scale (puzzle-style sweep: top-move agreement vs the reference).  Here the two
+    sides use their OWN networks — device: tcgen05 bf16 tower, reference path: torch-fp32 — so logits differ by
+    up to 2e-2 and visit counts may drift; the arg-max-visit move must still agree on the large majority of
+    positions, and where it differs the reference's move must be among the device's most visited."""
+    from gpu_util import oracle_board, random_games
+    from chessbot_b200.model import DeviceNetwork
+    from oracle import ref_gameimage, ref_mcts, ref_model
+    from oracle.ref_game import Game as OGame
+    from oracle.ref_game import OracleConfig
+    games = random_games(40, seed=404, max_plies=80)
+    images = np.stack([ref_gameimage.board_to_image(oracle_board(f, m), 8) for f, m in games])
+    w = ref_model.calibrate_bn(ref_model.init_weights(48, 4, seed=4), images, device="cuda")
+    w["policy.fc"] = w["policy.fc"] * 8.0            # sharpen the random-init policy so that searches have a clear favourite
+    import chessbot_b200.mcts as mcts
+    res = mcts.run_mcts_batch([_game(None, m.split()) for _, m in games], DeviceNetwork(w, 48, 4, max_batch=64), 100, 0, False, None, rng=_Rng())
+    net = ref_model.as_network(w, "cuda")
+    agree, in_top3 = 0, 0
+    for (move, root), (f, m) in zip(res, games):
+        omove, _ = ref_mcts.run_mcts(OGame(OracleConfig(), board=oracle_board(f, m)), net, 100, 0, False, None, rng=_Rng())
+        agree += move == omove
+        top3 = sorted(root.children, key=lambda u: -root.children[u].N)[:3]
+        in_top3 += omove in top3
+    print(f"\nconfig 4 (40 positions x 100 sims, 4x48): top-move agreement {agree}/40, reference move in device top-3 {in_top3}/40")
+    assert agree >= 30 and in_top3 >= 36
