@@ -13,6 +13,7 @@
 //      restarts; a non-terminal leaf records its ordered legal moves + the 8 frames to encode.
 #include "kernels.cuh"
 #include "policy.cuh"
+#include "rules_warp.cuh"
 
 namespace cb {
 
@@ -254,10 +255,9 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_step_kernel(SearchParams
         // ---- leaf: position, outcome (mcts.py:67, game.py:49-59)
         // lane 0 makes the move and generates the legal moves; the threefold claim-ahead scan (one make-move +
         // history walk per legal move, the expensive part of outcome(claim_draw=True)) runs one move per lane
-        int term = 0, n_moves = 0, leaf_pos = -1, err = 0, scan = 0;
+        int term = 0, n_moves = 0, leaf_pos = -1, err = 0, scan = 0, fresh = 0;
         uint16_t* sm = s_m[warp];
         if (lane == 0) {
-            Node& lf = sp.nodes[node];
             term = nd.term;
             leaf_pos = nd.pos_id;
             if (leaf_pos < 0) {
@@ -271,28 +271,32 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_step_kernel(SearchParams
                     err = 1;
                 } else {
                     sp.pos[leaf_pos] = np_;
-                    lf.pos_id = leaf_pos;
-                    MoveList ml;
-                    generate_legal(np_, ml);
-                    bool need_scan = false;
-                    const int out = outcome_before_scan(np_, ml, ppg, PoolPrev{sp.pos}, ts.max_len, &need_scan);
-                    if (out != OUT_NONE) term = terminal_value_to_play(out) < 0 ? 2 : 1;
-                    n_moves = ml.n;
-                    scan = need_scan;
-                    for (int i = 0; i < ml.n; ++i) sm[i] = ml.m[i];
+                    sp.nodes[node].pos_id = leaf_pos;
+                    fresh = 1;
                     __threadfence_block();
                 }
             }
         }
         __syncwarp();
-        scan = __shfl_sync(0xffffffffu, scan, 0);
-        if (scan) {
-            n_moves = __shfl_sync(0xffffffffu, n_moves, 0);
+        fresh = __shfl_sync(0xffffffffu, fresh, 0);
+        if (fresh) {
+            // first visit of this node: legal moves by the whole warp, then the outcome
             leaf_pos = __shfl_sync(0xffffffffu, leaf_pos, 0);
             const Pos cur = sp.pos[leaf_pos];  // private copy per lane
-            bool found = false;
-            for (int i = lane; i < n_moves && !found; i += 32) found = move_claims_threefold(cur, sm[i], &sp.pos[parent_pos], PoolPrev{sp.pos});
-            if (__any_sync(0xffffffffu, found)) term = 1;  // draw by threefold claim
+            n_moves = generate_legal_warp(cur, sm, lane);
+            __syncwarp();
+            if (lane == 0) {
+                bool need_scan = false;
+                const int out = outcome_before_scan(cur, sm, n_moves, sp.pos + parent_pos, PoolPrev{sp.pos}, ts.max_len, &need_scan);
+                if (out != OUT_NONE) term = terminal_value_to_play(out) < 0 ? 2 : 1;
+                scan = need_scan;
+            }
+            scan = __shfl_sync(0xffffffffu, scan, 0);
+            if (scan) {
+                bool found = false;
+                for (int i = lane; i < n_moves && !found; i += 32) found = move_claims_threefold(cur, sm[i], sp.pos + parent_pos, PoolPrev{sp.pos});
+                if (__any_sync(0xffffffffu, found)) term = 1;  // draw by threefold claim
+            }
         }
         err = __shfl_sync(0xffffffffu, err, 0);
         term = __shfl_sync(0xffffffffu, term, 0);
@@ -381,19 +385,12 @@ __global__ void __launch_bounds__(128) policy_softmax_kernel(const Pos* __restri
                                                              int32_t* __restrict__ out_n) {
     __shared__ float s_p[4][MAX_MOVES];
     __shared__ uint16_t s_m[4][MAX_MOVES];
-    __shared__ int s_n[4];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i = blockIdx.x * 4 + warp;
     if (i >= n) return;
-    const Pos& p = pos[cur_idx[i]];
-    if (lane == 0) {
-        MoveList ml;
-        generate_legal(p, ml);
-        s_n[warp] = ml.n;
-        for (int k = 0; k < ml.n; ++k) s_m[warp][k] = ml.m[k];
-    }
+    const Pos p = pos[cur_idx[i]];
+    const int nm = generate_legal_warp(p, s_m[warp], lane);
     __syncwarp();
-    const int nm = s_n[warp];
     for (int k = lane; k < nm; k += 32) {
         const int a = move_to_action(s_m[warp][k], p.turn);
         out_moves[(size_t)i * MAX_MOVES + k] = s_m[warp][k];

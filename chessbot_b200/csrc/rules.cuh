@@ -600,22 +600,22 @@ CB_HDN bool move_claims_threefold(const Pos& cur, Move m, const Pos* before, Pre
 // outcome(claim_draw=True) (game.py:57-58) for a position whose `occur` is filled in, EXCEPT the threefold
 // claim-ahead scan over the legal moves: *scan is set when that scan (move_claims_threefold for every legal
 // move, any order) still has to decide between OUT_THREEFOLD_REPETITION and the returned OUT_NONE.
-// `legal` must hold generate_legal(cur).  max_len: config.max_game_length (game.py:55), 0 to disable.
+// `legal` / `n_legal` must hold generate_legal(cur).  max_len: config.max_game_length (game.py:55), 0 to disable.
 template <class PrevFn>
-CB_HDN int outcome_before_scan(const Pos& cur, const MoveList& legal, const Pos* before, PrevFn prev, int max_len, bool* scan) {
+CB_HDN int outcome_before_scan(const Pos& cur, const Move* legal, int n_legal, const Pos* before, PrevFn prev, int max_len, bool* scan) {
     *scan = false;
     if (max_len > 0 && cur.ply == max_len) return OUT_MAX_LENGTH;
-    if (legal.n == 0 && checkers_mask(cur)) return OUT_CHECKMATE;
+    if (n_legal == 0 && checkers_mask(cur)) return OUT_CHECKMATE;
     if (is_insufficient_material(cur)) return OUT_INSUFFICIENT_MATERIAL;
-    if (legal.n == 0) return OUT_STALEMATE;
+    if (n_legal == 0) return OUT_STALEMATE;
     if (cur.halfmove >= 150) return OUT_SEVENTYFIVE_MOVES;
     if (cur.occur >= 5) return OUT_FIVEFOLD_REPETITION;
     // can_claim_fifty_moves
     if (cur.halfmove >= 100) return OUT_FIFTY_MOVES;
     if (cur.halfmove >= 99) {
-        for (int i = 0; i < legal.n; ++i) {
-            if (is_zeroing(cur, legal.m[i])) continue;
-            Pos nxt = push_move(cur, legal.m[i]);
+        for (int i = 0; i < n_legal; ++i) {
+            if (is_zeroing(cur, legal[i])) continue;
+            Pos nxt = push_move(cur, legal[i]);
             if (has_legal_moves(nxt)) return OUT_FIFTY_MOVES;
         }
     }
@@ -632,7 +632,7 @@ CB_HDN int outcome_before_scan(const Pos& cur, const MoveList& legal, const Pos*
 template <class PrevFn>
 CB_HDN int outcome_claim_draw(const Pos& cur, const MoveList& legal, const Pos* before, PrevFn prev, int max_len) {
     bool scan;
-    const int out = outcome_before_scan(cur, legal, before, prev, max_len, &scan);
+    const int out = outcome_before_scan(cur, legal.m, legal.n, before, prev, max_len, &scan);
     if (!scan) return out;
     for (int i = 0; i < legal.n; ++i)
         if (move_claims_threefold(cur, legal.m[i], before, prev)) return OUT_THREEFOLD_REPETITION;
