@@ -96,8 +96,10 @@ __device__ __forceinline__ uint32_t mapa(uint32_t saddr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
     return r;
 }
+// arrive on a barrier of another CTA of the cluster.  Default semantics (release at CTA scope), as CUTLASS does for the
+// accumulator hand-back: a cluster-scope release would first drain this thread's outstanding global stores.
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // wait on a local barrier whose arrivals come from the peer CTA
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {

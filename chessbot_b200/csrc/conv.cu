@@ -21,7 +21,8 @@
 //   cluster walks its range layer by layer over its units, and a unit shared between two neighbouring
 //   clusters is handed over through a per-board-pair progress flag in global memory.  The same flag
 //   orders "epilogue wrote layer l" before "TMA reads layer l as the input of layer l+1".
-// * Warp roles per CTA: warp 0 = TMA producer, warp 1 = MMA issuer (leader CTA), warps 2..9 = epilogue
+// * Warp roles per CTA: warp 0 = TMA producer of the activations, warp 10 = TMA producer of the weights (independent of the
+//   progress flags), warp 11 = publisher of the progress flags, warp 1 = MMA issuer (leader CTA), warps 2..9 = epilogue
 //   (tcgen05.ld -> BN scale/shift -> +skip -> LeakyReLU -> bf16 -> HBM in the same tile-native layout; on
 //   the last layer also the three 1x1 head convolutions of model.py:43,52 as dot products over the fp32
 //   row).  Two epilogue warps share a TMEM lane quarter and split the channel batches.
@@ -31,22 +32,23 @@
 
 namespace cb {
 
-constexpr int CONV_THREADS = 320;
-constexpr int A_SLOTS = 3, B_SLOTS = 8;
+constexpr int CONV_THREADS = 384;  // activation producer, MMA issuer, 8 epilogue warps, weight producer, flag publisher
+constexpr int PUB_SLOTS = 8;
+constexpr int A_SLOTS = 3, B_SLOTS = 16;  // weight ring: up to 16 stages inside B_RING_BYTES
 constexpr int A_SLOT_BYTES = ACT_K64_BYTES;  // one board pair x 64 channels
-constexpr int B_SLOT_BYTES = 128 * 128;      // N/2 <= 128 rows x 64 k x bf16
+constexpr int B_RING_BYTES = 8 * 128 * 128;  // N = 256: 8 stages of one tap (16 KB per CTA); N <= 128: stages of three taps
 constexpr int EPI_WARPS = 8;
 
 struct ConvSmem {
     uint64_t a_full[A_SLOTS], a_empty[A_SLOTS];
     uint64_t b_full[B_SLOTS], b_empty[B_SLOTS];
     uint64_t acc_full[2], acc_empty[2];
+    uint64_t pub_full[PUB_SLOTS], pub_empty[PUB_SLOTS];  // epilogue warps -> flag publisher
     uint32_t tmem_base;
-    int item_cnt[4];  // epilogue warps that finished item j (slot j & 3)
 };
 static_assert(sizeof(ConvSmem) <= 1024, "barrier block");
 constexpr int CONV_SMEM_PARAM_FLOATS = 256 * 3 + 2 * 128 * 3;
-constexpr size_t CONV_SMEM_BYTES = 1024 + A_SLOTS * A_SLOT_BYTES + B_SLOTS * B_SLOT_BYTES + CONV_SMEM_PARAM_FLOATS * 4;
+constexpr size_t CONV_SMEM_BYTES = 1024 + A_SLOTS * A_SLOT_BYTES + B_RING_BYTES + CONV_SMEM_PARAM_FLOATS * 4;
 
 // This cluster's share of the flattened (unit, layer) items i = unit * nl + layer: the range [lo, hi).
 struct WorkRange {
@@ -77,7 +79,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
     ConvSmem* s = reinterpret_cast<ConvSmem*>(smem);
     uint8_t* a_buf = smem + 1024;
     uint8_t* b_buf = a_buf + A_SLOTS * A_SLOT_BYTES;
-    float* s_head = reinterpret_cast<float*>(b_buf + B_SLOTS * B_SLOT_BYTES);
+    float* s_head = reinterpret_cast<float*>(b_buf + B_RING_BYTES);
     float* s_hpart = s_head + 768;  // [2 stages][128 rows][3]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -85,6 +87,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
     const int cid = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
     const int units = (p.pairs + 1) / 2;  // one unit = two board pairs = one M=256 accumulator stage
     const int n = p.n, nh = n >> 1, nl = p.nl;
+    // a weight stage = `tps` taps of one k-chunk (one TMA box of tps * N/2 rows per CTA): three taps for narrow layers, whose
+    // single-tap stages (4-8 KB, 32-64 tensor cycles per MMA) would be bound by barrier round trips, not by the tensor pipe
+    const int tps = conv_taps_per_stage(n), stages = 9 / tps;
+    const uint32_t slot_bytes = (uint32_t)tps * nh * 128;
+    const int nbs = min(B_SLOTS, B_RING_BYTES / (int)slot_bytes);
     const WorkRange w(cid, nclusters, units, nl);
     const int flag_base = p.epoch << 8;
 
@@ -101,7 +108,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
             ptx::mbar_init(&s->acc_full[i], 1);
             ptx::mbar_init(&s->acc_empty[i], 2 * EPI_WARPS);  // every epilogue warp of both CTAs
         }
-        for (int i = 0; i < 4; ++i) s->item_cnt[i] = 0;
+        for (int i = 0; i < PUB_SLOTS; ++i) { ptx::mbar_init(&s->pub_full[i], EPI_WARPS); ptx::mbar_init(&s->pub_empty[i], 1); }
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
@@ -115,45 +122,69 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
     const uint32_t tmem = s->tmem_base;
 
     if (warp == 0) {
-        // ------------------------------------------------------------------ producer (both CTAs; whole warp, one elected lane issues)
-        uint32_t a_it = 0, b_it = 0;
-        const uint32_t b_bytes = (uint32_t)nh * 128;
+        // ------------------------------------------------------------------ activation producer (both CTAs; whole warp, one elected lane issues)
+        uint32_t a_it = 0;
         // operands of BOTH CTAs complete on the leader's "full" barriers (the MMA issuer lives there)
-        const uint32_t a_full0 = ptx::mapa(ptx::smem_u32(&s->a_full[0]), 0), b_full0 = ptx::mapa(ptx::smem_u32(&s->b_full[0]), 0);
-        for (int l = 0; l < nl; ++l) {
-            const LayerDesc L = p.layers[l];
+        const uint32_t a_full0 = ptx::mapa(ptx::smem_u32(&s->a_full[0]), 0);
+        // flat walk over this cluster's items with one item of look-ahead: the progress flag of the NEXT item is read
+        // (ld.acquire.gpu, an L2 round trip) while this item's loads are being issued
+        int l = 0, k = -1;
+        auto advance = [&](int& ll, int& kk) {  // next (layer, unit slot) of this cluster, ll == nl at the end
+            do {
+                if (++kk == w.nu) { kk = 0; ++ll; }
+            } while (ll < nl && !w.mine(w.unit(kk), ll));
+        };
+        advance(l, k);
+        int seen = l < nl && l > 0 ? ld_acquire_gpu(p.flags + 2 * w.unit(k) + rank) : 0;
+        int l_loaded = -1;
+        LayerDesc L{};
+        while (l < nl) {
+            if (l != l_loaded) { L = p.layers[l]; l_loaded = l; }
             const CUtensorMap* tm_in = &p.tm_act[L.in_buf];
-            const CUtensorMap* tm_w = &p.maps[L.w_map];
+            const int u = w.unit(k);
+            const int pair = min(2 * u + (int)rank, p.pairs - 1);  // odd tail: the peer re-reads the last pair, its result is dropped
+            if (l > 0) {
+                // the input of this item is the output of (unit, layer - 1): written by this CTA's epilogue warps, or by
+                // the same-rank CTA of the previous cluster; either way its progress flag says when it is in L2
+                const int* flag = p.flags + 2 * u + rank;
+                while (seen < flag_base + l) seen = ld_acquire_gpu(flag);
+                fence_proxy_async();
+            }
+            int nl_ = l, nk_ = k;
+            advance(nl_, nk_);
+            if (nl_ < nl && nl_ > 0) seen = ld_acquire_gpu(p.flags + 2 * w.unit(nk_) + rank);  // consumed at the top of the next item
+            for (int kc = 0; kc < L.kc; ++kc) {
+                const int as = a_it % A_SLOTS;
+                ptx::mbar_wait(&s->a_empty[as], ((a_it / A_SLOTS) & 1) ^ 1);
+                if (ptx::elect_one()) {
+                    if (rank == 0) ptx::mbar_expect_tx(&s->a_full[as], 2 * ACT_K64_BYTES);
+                    ptx::tma_load_2d_pair(a_buf + as * A_SLOT_BYTES, tm_in, 0, (pair * L.cj_in + 8 * (kc % L.kc_in)) * (ACT_CHUNK_BYTES / 128),
+                                          a_full0 + as * 8);
+                }
+                ++a_it;
+            }
+            l = nl_;
+            k = nk_;
+        }
+    } else if (warp == 10) {
+        // ------------------------------------------------------------------ weight producer (both CTAs): the weight stream does not depend on
+        // any activation, so it runs ahead of the progress flags the activation producer has to wait for
+        uint32_t b_it = 0;
+        const uint32_t b_full0 = ptx::mapa(ptx::smem_u32(&s->b_full[0]), 0);
+        for (int l = 0; l < nl; ++l) {
+            const int kcs = p.layers[l].kc;
+            const CUtensorMap* tm_w = &p.maps[p.layers[l].w_map];
             if (ptx::elect_one()) ptx::tma_prefetch_desc(tm_w);
             for (int k = 0; k < w.nu; ++k) {
-                const int u = w.unit(k);
-                if (!w.mine(u, l)) continue;
-                const int pair = min(2 * u + (int)rank, p.pairs - 1);  // odd tail: the peer re-reads the last pair, its result is dropped
-                if (l > 0) {
-                    // the input of this item is the output of (unit, layer - 1): written by this CTA's epilogue warps, or by
-                    // the same-rank CTA of the previous cluster; either way its progress flag says when it is in L2
-                    const int* flag = p.flags + 2 * u + rank;
-                    while (ld_acquire_gpu(flag) < flag_base + l) {
-                    }
-                    fence_proxy_async();
-                }
-                for (int kc = 0; kc < L.kc; ++kc) {
-                    const int as = a_it % A_SLOTS;
-                    ptx::mbar_wait(&s->a_empty[as], ((a_it / A_SLOTS) & 1) ^ 1);
-                    if (ptx::elect_one()) {
-                        if (rank == 0) ptx::mbar_expect_tx(&s->a_full[as], 2 * ACT_K64_BYTES);
-                        ptx::tma_load_2d_pair(a_buf + as * A_SLOT_BYTES, tm_in, 0, (pair * L.cj_in + 8 * (kc % L.kc_in)) * (ACT_CHUNK_BYTES / 128),
-                                              a_full0 + as * 8);
-                    }
-                    ++a_it;
-                    const int wrow = (kc * 9 * 2 + (int)rank) * nh;
-#pragma unroll
-                    for (int tap = 0; tap < 9; ++tap) {
-                        const int bs = b_it % B_SLOTS;
-                        ptx::mbar_wait(&s->b_empty[bs], ((b_it / B_SLOTS) & 1) ^ 1);
+                if (!w.mine(w.unit(k), l)) continue;
+                for (int kc = 0; kc < kcs; ++kc) {
+                    const int wrow = (kc * 2 + (int)rank) * 9 * nh;  // [kc][half][tap][8][N/2][8]
+                    for (int sg = 0; sg < stages; ++sg) {
+                        const int bs = b_it % nbs;
+                        ptx::mbar_wait(&s->b_empty[bs], ((b_it / nbs) & 1) ^ 1);
                         if (ptx::elect_one()) {
-                            if (rank == 0) ptx::mbar_expect_tx(&s->b_full[bs], 2 * b_bytes);
-                            ptx::tma_load_2d_pair(b_buf + bs * B_SLOT_BYTES, tm_w, 0, wrow + tap * 2 * nh, b_full0 + bs * 8);
+                            if (rank == 0) ptx::mbar_expect_tx(&s->b_full[bs], 2 * slot_bytes);
+                            ptx::tma_load_2d_pair(b_buf + bs * slot_bytes, tm_w, 0, wrow + sg * tps * nh, b_full0 + bs * 8);
                         }
                         ++b_it;
                     }
@@ -181,17 +212,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
                         const int as = a_it % A_SLOTS;
                         ptx::mbar_wait(&s->a_full[as], (a_it / A_SLOTS) & 1);
                         const uint64_t a_desc = a_desc0 + (uint64_t)(as * (A_SLOT_BYTES / 16));
-#pragma unroll
-                        for (int tap = 0; tap < 9; ++tap) {
-                            const int bs = b_it % B_SLOTS;
-                            ptx::mbar_wait(&s->b_full[bs], (b_it / B_SLOTS) & 1);
+                        for (int sg = 0; sg < stages; ++sg) {
+                            const int bs = b_it % nbs;
+                            ptx::mbar_wait(&s->b_full[bs], (b_it / nbs) & 1);
                             ptx::tc_fence_after();
-                            const uint64_t bd0 = b_desc0 + (uint64_t)(bs * (B_SLOT_BYTES / 16));
-                            const uint64_t ad0 = a_desc + (uint64_t)((tap / 3) * 20 + (tap % 3));  // tap (dy, dx): start cell (1+dy)*20 + 1+dx
+                            const uint64_t bd_slot = b_desc0 + (uint64_t)(bs * (slot_bytes / 16));
                             if (ptx::elect_one()) {
+                                for (int t = 0; t < tps; ++t) {
+                                    const int tap = sg * tps + t;
+                                    const uint64_t ad0 = a_desc + (uint64_t)((tap / 3) * 20 + (tap % 3));  // tap (dy, dx): start cell (1+dy)*20 + 1+dx
+                                    const uint64_t bd0 = bd_slot + (uint64_t)(t * nh * 8);                   // one tap = N/2 rows x 128 B
 #pragma unroll
-                                for (int ks = 0; ks < 4; ++ks)
-                                    ptx::umma2_bf16(d, ad0 + ks * a_ks, bd0 + ks * b_ks, idesc, (kc | tap | ks) != 0);
+                                    for (int ks = 0; ks < 4; ++ks)
+                                        ptx::umma2_bf16(d, ad0 + ks * a_ks, bd0 + ks * b_ks, idesc, (kc | tap | ks) != 0);
+                                }
                                 ptx::umma2_commit_mc(&s->b_empty[bs]);  // weight stage of BOTH CTAs is free when these MMAs retire
                             }
                             __syncwarp();
@@ -207,7 +241,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
                 }
             }
         }
-    } else {
+    } else if (warp < 10) {
         // ------------------------------------------------------------------ epilogue (warps 2..9, both CTAs)
         // Two warps per TMEM lane quarter (a warp may only read lanes 32*(warp%4)..+31) split the 32-channel
         // batches of the row: warp half h takes batches h, h+2, ...  The skip tile is read through a 4-deep
@@ -318,21 +352,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
                         ho[0] = h0 + hp[0]; ho[1] = h1 + hp[1]; ho[2] = h2 + hp[2];
                     }
                 }
-                // publish "layer l of this board pair is in memory": the last of the eight warps sets the progress flag
-                // that the TMA producer of (unit, l + 1) — here or in the next cluster — waits for
-                __threadfence();
-                fence_proxy_async();
+                // "layer l of this board pair is in memory": the warp reports to the flag publisher (warp 11), which issues
+                // the generic->async proxy fence and the device-scope release.  Both cost microseconds; on an epilogue warp
+                // they would bound the item rate of narrow layers (measured: 2,000 cycles of accumulator hand-back wait
+                // per item at N = 64).
                 __syncwarp();
                 if (lane == 0) {
-                    const int old = atomicAdd(&s->item_cnt[j & 3], 1);
-                    if (old == EPI_WARPS - 1) {
-                        s->item_cnt[j & 3] = 0;
-                        __threadfence();
-                        st_release_gpu(p.flags + 2 * u + rank, flag_base + l + 1);
-                    }
+                    ptx::mbar_wait(&s->pub_empty[j % PUB_SLOTS], ((j / PUB_SLOTS) & 1) ^ 1);
+                    ptx::mbar_arrive(&s->pub_full[j % PUB_SLOTS]);
                 }
+                __syncwarp();
                 ++j;
             }
+        }
+    } else if (warp == 11) {
+        // ------------------------------------------------------------------ flag publisher (both CTAs): when all eight epilogue warps have
+        // stored item j, release-store the progress flag of its board pair (the release is cumulative over the mbarrier)
+        // for the activation producer of (unit, l + 1), here or in the next cluster
+        if (lane == 0) {
+            uint32_t j = 0;
+            for (int l = 0; l < nl; ++l)
+                for (int k = 0; k < w.nu; ++k) {
+                    const int u = w.unit(k);
+                    if (!w.mine(u, l)) continue;
+                    ptx::mbar_wait(&s->pub_full[j % PUB_SLOTS], (j / PUB_SLOTS) & 1);
+                    ptx::mbar_arrive(&s->pub_empty[j % PUB_SLOTS]);
+                    fence_proxy_async();  // the epilogue's generic stores (observed through the mbarrier) before the TMA reads that follow the flag
+                    st_release_gpu(p.flags + 2 * u + rank, flag_base + l + 1);
+                    ++j;
+                }
         }
     }
     ptx::tc_fence_before();

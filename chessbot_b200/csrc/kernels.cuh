@@ -12,7 +12,7 @@ struct ConvParams {
     const __nv_bfloat16* in;    // tile-native, cj_in chunks
     __nv_bfloat16* out;         // tile-native, n/8 chunks
     const __nv_bfloat16* skip;  // tile-native like out, or nullptr
-    const __nv_bfloat16* wgt;   // [kc][tap][half][8][n/2][8], see conv_weight_index
+    const __nv_bfloat16* wgt;   // [kc][half][tap][8][n/2][8], see conv_weight_index
     const float* scale;         // [n] gamma / sqrt(var + eps)
     const float* shift;         // [n] beta - mean * scale
     const float* head_w;        // [3][n] 1x1 head conv weights (value, policy0, policy1) or nullptr
@@ -37,7 +37,7 @@ struct LayerDesc {
 
 struct TowerParams {
     CUtensorMap tm_act[4];      // the activation buffers as rows of 128 B, box = one 64-channel chunk of a board pair (200 rows)
-    const CUtensorMap* maps;    // device array: packed weights of each layer as rows of 128 B, box = one half weight block (n/2 rows)
+    const CUtensorMap* maps;    // device array: packed weights of each layer as rows of 128 B, box = conv_taps_per_stage(n) tap blocks of n/2 rows
     const LayerDesc* layers;    // device array [nl]
     uint8_t* bufs[4];           // raw pointers of the same four buffers (epilogue stores, skip reads)
     const float* head_w;        // [3][n] 1x1 head conv weights fused into the LAST layer, or nullptr
@@ -50,12 +50,14 @@ struct TowerParams {
     float slope;
 };
 
-// Packed weight layout: per (k-chunk of 64 input channels, tap) two halves of N/2 output channels, each a
-// K-major / no-swizzle block [k/8][N/2][k%8] = the B operand one CTA of the pair stages with one bulk copy.
+// Packed weight layout [kc][half][tap][k/8][N/2][k%8]: per k-chunk of 64 input channels and half of the output
+// channels nine K-major / no-swizzle tap blocks of N/2 rows x 128 B, contiguous, so that one TMA box can fetch one
+// tap (wide layers) or three (narrow layers) as the B operand a CTA of the pair stages.
 __host__ __device__ inline size_t conv_weight_index(int kc, int tap, int k /*0..63*/, int co, int n) {
     const int nh = n >> 1, half = co >= nh, c = co - half * nh;
-    return ((size_t)((kc * 9 + tap) * 2 + half) * 8 + (k >> 3)) * nh * 8 + (size_t)c * 8 + (k & 7);
+    return ((size_t)(((kc * 2 + half) * 9 + tap) * 8 + (k >> 3)) * nh + c) * 8 + (k & 7);
 }
+__host__ __device__ inline int conv_taps_per_stage(int n) { return n <= 128 ? 3 : 1; }
 
 struct HeadParams {
     const float* head_raw;   // [boards][64][3]
