@@ -93,6 +93,28 @@ class DeviceNetwork:
         return {"value_head": value.cpu().numpy().reshape(-1, 1), "policy_head": logits.cpu().numpy()}
 
 
+def save_weights(path, weights):
+    """Checkpoint interchange (train.py:88-101,124-136 write Keras / SavedModel files, unreadable without TensorFlow):
+    the float32 master tensors under the names of include/chessbot_b200.h (cb_net_set_tensor) in one .npz.  A Keras
+    model exports with  {"stem.w": conv2d.kernel, "stem.bn": [gamma, beta, moving_mean, moving_variance], "res{i}.w1": ...}
+    — kernels HWIO and Dense [in, out] exactly as Keras stores them."""
+    np.savez(path, **{k: np.asarray(v, dtype=np.float32) for k, v in weights.items()})
+
+
+def load_weights(path):
+    """(weights dict, filters, blocks) from a save_weights() file."""
+    with np.load(path) as z:
+        w = {k: np.asarray(z[k], dtype=np.float32) for k in z.files}
+    filters = int(w["stem.w"].shape[-1])
+    blocks = sum(1 for k in w if k.endswith(".w1"))
+    return w, filters, blocks
+
+
+def load_network(path, max_batch=1024, device=None):
+    w, filters, blocks = load_weights(path)
+    return DeviceNetwork(w, filters, blocks, max_batch, device)
+
+
 class SyntheticNetwork:
     """The reference tests' mock network (tests/mcts_v2.py:51-67) as a device kernel: outputs are an
     integer hash of the planes (csrc/heads.cu; NumPy statement in oracle/synthetic_net.py)."""

@@ -171,3 +171,15 @@ def test_export_record_covers_frames_and_repetition_window(cb):
     assert list(ply) == list(range(2, 12)) and rec[0, 80] == 1 and rec[-1, 81] == 3   # irrev_in barrier, occur = 3
     b2 = board.Board("r2qk2r/pppb1ppp/2np1n2/2b1p3/2B1P3/2NP1N2/PPPB1PPP/R2QK2R w KQkq - 4 7")
     assert b2.export_record().shape == (1, 96)
+
+
+def test_weight_checkpoint_roundtrip(tmp_path):
+    # model.save_weights / load_weights: the tensor names and Keras layouts of include/chessbot_b200.h (no GPU needed)
+    from chessbot_b200.model import keras_init_weights, load_weights, save_weights
+    w = keras_init_weights(48, 4, seed=3)
+    path = str(tmp_path / "net.npz")
+    save_weights(path, w)
+    w2, filters, blocks = load_weights(path)
+    assert (filters, blocks) == (48, 4) and sorted(w2) == sorted(w)
+    assert all(np.array_equal(w[k], w2[k]) and w2[k].dtype == np.float32 for k in w)
+    assert w["stem.w"].shape == (3, 3, 119, 48) and w["policy.fc"].shape == (128, 4672) and w["res0.bn1"].shape == (4, 48)
