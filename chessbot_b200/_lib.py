@@ -50,6 +50,7 @@ _SIGS = {
     "cb_synth_forward": (i32, [vp, vp, i32, u32, vp, vp, vp]),
     "cb_policy_softmax": (i32, [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]),
     "cb_search_create": (i32, [vp, i32, i32, i32, i32]),
+    "cb_search_set_leaves": (i32, [vp, i32]),
     "cb_search_begin": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, i32, i32, u32, vp]),
     "cb_search_step": (i32, [vp, vp]),
     "cb_search_run": (i32, [vp, i32, vp]),

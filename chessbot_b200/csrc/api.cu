@@ -81,7 +81,8 @@ struct Net {
 };
 
 struct Search {
-    int max_trees = 0, n_trees = 0, max_sims = 0, eval_mode = 0;
+    int max_trees = 0, n_trees = 0, max_sims = 0, eval_mode = 0, leaves = 1;
+    DevBuf<SlotState> slots;
     uint32_t seed = 0;
     DevBuf<Node> nodes;
     DevBuf<Pos> pos;
@@ -373,9 +374,10 @@ int cb_net_forward(cb_ctx* ctx, const void* planes_act_dev, int n, float* value_
 }
 
 int cb_synth_forward(cb_ctx* ctx, const int16_t* planes_i16_dev, int n, uint32_t seed, float* value_dev, void* logits_bf16_dev, void* stream) {
-    Search& s = ctx->search;
-    if (s.synth_hash.n < (size_t)n && s.synth_hash.alloc(n)) return -1;
-    return launch_synth(planes_i16_dev, n, seed, s.synth_hash.p, value_dev, (__nv_bfloat16*)logits_bf16_dev, (cudaStream_t)stream);
+    (void)ctx;
+    static thread_local DevBuf<uint32_t> hash;  // scratch of the stand-alone call (the search owns its own per-slot hashes)
+    if (hash.n < (size_t)n && hash.alloc(n)) return -1;
+    return launch_synth(planes_i16_dev, n, seed, hash.p, value_dev, (__nv_bfloat16*)logits_bf16_dev, (cudaStream_t)stream);
 }
 
 int cb_policy_softmax(cb_ctx* ctx, const void* pos_dev, const int32_t* cur_idx_dev, int n, const void* logits_bf16_dev,
@@ -454,9 +456,8 @@ int cb_search_create(cb_ctx* ctx, int max_trees, int max_nodes, int max_position
     max_positions += max_trees * POS_CHUNK;
     const size_t mt = max_trees, mm = (size_t)max_trees * MAX_MOVES;
     if (s.nodes.alloc(max_nodes, false) || s.pos.alloc(max_positions, false) || s.trees.alloc(mt) || s.node_count.alloc(1) ||
-        s.pos_count.alloc(1) || s.frame_idx.alloc(mt * 8) || s.path.alloc(mt * MCTS_MAX_PATH) || s.counters.alloc(4) || s.scratch_i32.alloc(4) || s.pend_moves.alloc(mm) ||
-        s.root_p64.alloc(mm) || s.noise.alloc(mm) || s.value.alloc(mt) || s.synth_hash.alloc(mt) ||
-        s.planes_act.alloc(act_bytes(max_trees, 128) / 2) || s.planes_i16.alloc(mt * 7616) || s.flags.alloc(mt) ||
+        s.pos_count.alloc(1) || s.counters.alloc(4) || s.scratch_i32.alloc(4) ||
+        s.root_p64.alloc(mm) || s.noise.alloc(mm) || s.flags.alloc(mt) ||
         s.r_moves.alloc(mm) || s.r_n.alloc(mm) || s.r_w.alloc(mm) || s.r_q.alloc(mm) || s.r_p.alloc(mm) || s.r_nc.alloc(mt) ||
         s.r_rootn.alloc(mt) || s.r_nodes.alloc(mt))
         return -1;
@@ -473,9 +474,28 @@ int cb_search_create(cb_ctx* ctx, int max_trees, int max_nodes, int max_position
     SearchParams& sp = s.sp;
     sp.nodes = s.nodes.p; sp.node_count = s.node_count.p; sp.max_nodes = max_nodes;
     sp.pos = s.pos.p; sp.pos_count = s.pos_count.p; sp.max_pos = max_positions;
-    sp.trees = s.trees.p; sp.path = s.path.p; sp.pend_moves = s.pend_moves.p; sp.frame_idx = s.frame_idx.p; sp.root_p64 = s.root_p64.p;
+    sp.trees = s.trees.p; sp.root_p64 = s.root_p64.p;
     sp.noise = s.noise.p; sp.cpuct_tab = s.cpuct_tab.p; sp.sqrt_tab = s.sqrt_tab.p; sp.tab_len = tl;
-    sp.value = s.value.p; sp.synth_hash = s.synth_hash.p; sp.exp_table = ctx->exp_table.p; sp.counters = s.counters.p;
+    sp.exp_table = ctx->exp_table.p; sp.counters = s.counters.p;
+    s.leaves = 0;
+    return cb_search_set_leaves(ctx, 1);
+}
+
+// Buffers indexed by evaluation slot (tree * leaves + i): the batch of a step is max_trees * leaves positions.
+int cb_search_set_leaves(cb_ctx* ctx, int leaves) {
+    Search& s = ctx->search;
+    if (leaves < 1 || leaves > 32) { cb_set_error("leaves per tree must be 1..32"); return -1; }
+    if (s.max_trees <= 0) { cb_set_error("cb_search_create first"); return -1; }
+    if (leaves == s.leaves) return 0;
+    const size_t ns = (size_t)s.max_trees * leaves;
+    if (s.frame_idx.alloc(ns * 8) || s.path.alloc(ns * MCTS_MAX_PATH) || s.pend_moves.alloc(ns * MAX_MOVES) || s.value.alloc(ns) ||
+        s.synth_hash.alloc(ns) || s.slots.alloc(ns) || s.planes_act.alloc(act_bytes((int)ns, 128) / 2) || s.planes_i16.alloc(ns * 7616))
+        return -1;
+    s.expvals.free_();
+    s.leaves = leaves;
+    SearchParams& sp = s.sp;
+    sp.leaves = leaves; sp.slots = s.slots.p; sp.path = s.path.p; sp.pend_moves = s.pend_moves.p; sp.frame_idx = s.frame_idx.p;
+    sp.value = s.value.p; sp.synth_hash = s.synth_hash.p; sp.expvals = nullptr;
     return 0;
 }
 
@@ -486,7 +506,8 @@ int cb_search_begin(cb_ctx* ctx, int n_trees, const void* records_host, const in
     cudaStream_t st = (cudaStream_t)stream;
     if (n_trees > s.max_trees) { cb_set_error("n_trees > max_trees"); return -1; }
     if (eval_mode == CB_EVAL_NET && !ctx->net.ready) { cb_set_error("CB_EVAL_NET without a finalized network"); return -1; }
-    if (eval_mode == CB_EVAL_NET && n_trees > ctx->net.max_batch) { cb_set_error("n_trees > network max_batch"); return -1; }
+    if (eval_mode == CB_EVAL_NET && n_trees * s.leaves > ctx->net.max_batch) { cb_set_error("n_trees * leaves > network max_batch"); return -1; }
+    if (eval_mode == CB_EVAL_EXTERNAL && s.leaves != 1) { cb_set_error("a host network evaluates one leaf per tree (leaves = 1)"); return -1; }
     s.n_trees = n_trees;
     s.eval_mode = eval_mode;
     s.seed = synth_seed;
@@ -541,13 +562,13 @@ int cb_search_step(cb_ctx* ctx, void* stream) {
     Search& s = ctx->search;
     cudaStream_t st = (cudaStream_t)stream;
     if (s.eval_mode == CB_EVAL_NET) {
-        if (prof_begin(ctx, CB_PROF_ENCODE, st) || launch_encode(s.pos.p, s.frame_idx.p, s.n_trees, s.planes_act.p, nullptr, st) ||
+        if (prof_begin(ctx, CB_PROF_ENCODE, st) || launch_encode(s.pos.p, s.frame_idx.p, s.n_trees * s.leaves, s.planes_act.p, nullptr, st) ||
             prof_end(ctx, st) || debug_sync(st, "encode"))
             return -1;
-        if (net_tower(ctx, s.planes_act.p, s.n_trees, s.value.p, st) || debug_sync(st, "tower")) return -1;
+        if (net_tower(ctx, s.planes_act.p, s.n_trees * s.leaves, s.value.p, st) || debug_sync(st, "tower")) return -1;
     } else if (s.eval_mode == CB_EVAL_SYNTH) {
-        if (launch_encode(s.pos.p, s.frame_idx.p, s.n_trees, nullptr, s.planes_i16.p, st)) return -1;
-        if (launch_synth(s.planes_i16.p, s.n_trees, s.seed, s.synth_hash.p, s.value.p, nullptr, st)) return -1;
+        if (launch_encode(s.pos.p, s.frame_idx.p, s.n_trees * s.leaves, nullptr, s.planes_i16.p, st)) return -1;
+        if (launch_synth(s.planes_i16.p, s.n_trees * s.leaves, s.seed, s.synth_hash.p, s.value.p, nullptr, st)) return -1;
     } else {
         cb_set_error("cb_search_step: external evaluation uses cb_search_step_external");
         return -1;

@@ -78,7 +78,8 @@ struct Node {  // 32 bytes; children of a node are contiguous, in legal-move ord
     int32_t pos_id;      // position of this node in the pos pool, -1 until first visited
     uint16_t move;       // move that leads here
     uint8_t n_children;
-    int8_t term;         // 0 unknown / not terminal, 1 terminal value 0, 2 terminal value -1 (side to move is mated)
+    int8_t term;         // 0 unknown / not terminal, 1 terminal value 0, 2 terminal value -1 (side to move is mated),
+                         // 3 selected and waiting for its evaluation (only marked when leaves > 1)
 };
 static_assert(sizeof(Node) == 32, "Node must be 32 bytes");
 
@@ -91,39 +92,49 @@ constexpr int POS_CHUNK = 128;    // positions likewise
 struct TreeState {  // 80 bytes
     int32_t root_node, root_pos;
     int32_t sims_done, sims_target;
-    int32_t leaf_node, leaf_pos;
-    int32_t n_moves, status;
+    int32_t n_pending;   // leaves of this tree waiting for their evaluation (slots tree * leaves + 0 .. n_pending - 1)
+    int32_t pad0_, pad1_;
+    int32_t status;
     int32_t n_nodes, n_evals;
     int32_t noisy;       // add_exploration_noise applied at the root (P held in f64)
     int32_t max_len;     // config.max_game_length
     double cpuct;        // < 0: AlphaZero schedule log((N+19653)/19652)+1.25, else fixed (mcts.py:135-139)
     int32_t error;
-    int32_t path_len;    // nodes on the root..leaf path of the pending leaf (SearchParams::path), 0 = not recorded (too deep)
+    int32_t pad2_;
     int32_t node_next, node_end;  // this tree's current chunk of the node pool: [node_next, node_end) is free
     int32_t pos_next, pos_end;    // and of the position pool
 };
 static_assert(sizeof(TreeState) == 80, "TreeState must be 80 bytes");
 
+// One in-flight leaf (evaluation slot).  Slot s = tree * leaves + i; the batch of a step is n_trees * leaves slots.
+struct SlotState {
+    int32_t leaf_node, leaf_pos, n_moves;
+    int32_t path_len;    // nodes on the root..leaf path recorded in SearchParams::path (0 = not recorded: too deep)
+};
+
 struct SearchParams {
     Node* nodes; int32_t* node_count; int32_t max_nodes;
     Pos* pos; int32_t* pos_count; int32_t max_pos;
     TreeState* trees; int n_trees;
-    uint16_t* pend_moves;      // [n_trees][MAX_MOVES]
-    int32_t* frame_idx;        // [n_trees][8] newest first
+    SlotState* slots;          // [n_trees * leaves]
+    int leaves;                // leaves per tree in flight: 1 = the reference's strictly sequential simulations (parity mode);
+                               // > 1 = throughput mode with virtual loss (north_star), results differ from the sequential order
+    uint16_t* pend_moves;      // [slots][MAX_MOVES]
+    int32_t* frame_idx;        // [slots][8] newest first
     double* root_p64;          // [n_trees][MAX_MOVES]
     const double* noise;       // [n_trees][MAX_MOVES] Gamma(0.3,1) samples drawn by the host (mcts.py:158)
     const double* cpuct_tab;   // [tab_len] log((N+19653)/19652)+1.25 from the host libm
     const double* sqrt_tab;    // [tab_len] pow(N, 0.5) from the host libm
     int tab_len;
     int eval_mode;
-    const float* value;        // [n_trees]
-    const float* pfeat;        // EVAL_NET: [n_trees][128]
+    const float* value;        // [slots]
+    const float* pfeat;        // EVAL_NET: [slots][128]
     const float* wpt;          // EVAL_NET: policy Dense transposed [4672][128]
-    const uint32_t* synth_hash;  // EVAL_SYNTH: [n_trees]
-    const float* expvals;      // EVAL_EXTERNAL: [n_trees][4672] exp(logit) from the host
+    const uint32_t* synth_hash;  // EVAL_SYNTH: [slots]
+    const float* expvals;      // EVAL_EXTERNAL: [slots][4672] exp(logit) from the host (leaves == 1)
     const float* exp_table;    // [65536] f32 exp indexed by bf16 bits
     int32_t* counters;         // [0] evals, [1] sims, [2] errors
-    int32_t* path;             // [n_trees][MCTS_MAX_PATH] node ids root..leaf of every pending leaf
+    int32_t* path;             // [slots][MCTS_MAX_PATH] node ids root..leaf of every pending leaf
 };
 
 int launch_tower(const TowerParams& p, int num_sms, cudaStream_t stream);

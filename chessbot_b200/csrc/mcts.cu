@@ -1,7 +1,8 @@
 // K6/K7/K8 — PUCT select, device chess rules at the leaf, expand and backup (mcts.py:38-161) for
-// many concurrent trees over a GPU-resident node pool.  One warp per tree, one in-flight leaf per
-// tree: every tree runs the reference's strictly sequential simulation order, the batching is
-// ACROSS trees (batch = number of games), so visit counts are those of the reference.
+// many concurrent trees over a GPU-resident node pool.  One warp per tree.  With one in-flight leaf per
+// tree (leaves = 1, the default) every tree runs the reference's strictly sequential simulation order, the
+// batching is ACROSS trees (batch = number of games), so visit counts are those of the reference.  With
+// leaves > 1 (throughput mode for few games) a tree selects several leaves per step under virtual loss.
 //
 // One launch of mcts_step_kernel per batch step does, per tree:
 //   A. if a leaf evaluation is pending: priors for its legal moves (K5: gather, exp table, NumPy
@@ -36,8 +37,8 @@ __device__ __forceinline__ uint32_t fmix32_d(uint32_t x) {
 }
 
 // frames for the encoder: walk the record newest first, stop after a position with an empty move stack
-__device__ void fill_frames(const SearchParams& sp, int tree, int pos_id) {
-    int32_t* fi = sp.frame_idx + (size_t)tree * 8;
+__device__ void fill_frames(const SearchParams& sp, int slot, int pos_id) {
+    int32_t* fi = sp.frame_idx + (size_t)slot * 8;
     int cur = pos_id;
     for (int t = 0; t < 8; ++t) {
         fi[t] = cur;
@@ -89,6 +90,28 @@ __device__ __forceinline__ int chunk_alloc(int32_t& next, int32_t& end, int n, i
     return r;
 }
 
+// Throughput mode (leaves > 1): a selected leaf lowers every node of its path by one lost game (N += 1, W -= 1) until its
+// evaluation arrives, so that the next selections of the same step go elsewhere ...
+__device__ __forceinline__ void virtual_loss_path(Node* nodes, const int32_t* path, int len, int lane) {
+    for (int d = lane; d < len; d += 32) {
+        Node& nd = nodes[path[d]];
+        const int n = nd.N + 1;
+        const float w = __fadd_rn(nd.W, -1.0f);
+        nd.N = n;
+        nd.W = w;
+        nd.Q = __fdiv_rn(w, (float)n);
+    }
+}
+// ... and the evaluation replaces the lost game by the real value (the visit is already counted)
+__device__ __forceinline__ void settle_path(Node* nodes, const int32_t* path, int len, float v, int lane) {
+    for (int d = lane; d < len; d += 32) {
+        Node& nd = nodes[path[d]];
+        const float w = __fadd_rn(nd.W, __fadd_rn(1.0f, ((len - 1 - d) & 1) ? -v : v));
+        nd.W = w;
+        nd.Q = __fdiv_rn(w, (float)nd.N);
+    }
+}
+
 constexpr int MCTS_WARPS = 4;
 
 __global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_step_kernel(SearchParams sp) {
@@ -99,21 +122,26 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_step_kernel(SearchParams
     const int tree = blockIdx.x * MCTS_WARPS + warp;
     if (tree >= sp.n_trees) return;
     TreeState& ts = sp.trees[tree];
-    int status = ts.status;
+    const int status = ts.status;
     if (status == TREE_IDLE || status == TREE_DONE || ts.error) return;
     float* pv = s_p[warp];
+    const int L = sp.leaves;
+    const bool vl = L > 1;  // throughput mode: virtual loss, several leaves of this tree per step
 
-    // ------------------------------------------------------------------ A. expand + backup
-    {
-        const int n = ts.n_moves, leaf = ts.leaf_node;
-        const uint16_t* moves = sp.pend_moves + (size_t)tree * MAX_MOVES;
-        const int turn = sp.pos[ts.leaf_pos].turn;
+    // ------------------------------------------------------------------ A. expand + backup every evaluated leaf
+    const int n_pending = ts.n_pending;
+    for (int li = 0; li < n_pending; ++li) {
+        const int slot = tree * L + li;
+        const SlotState sl = sp.slots[slot];
+        const int n = sl.n_moves, leaf = sl.leaf_node;
+        const uint16_t* moves = sp.pend_moves + (size_t)slot * MAX_MOVES;
+        const int turn = sp.pos[sl.leaf_pos].turn;
         for (int i = lane; i < n; i += 32) {
             const int a = move_to_action(moves[i], turn);
             float e;
             if (sp.eval_mode == EVAL_NET) {
                 const float4* wr = reinterpret_cast<const float4*>(sp.wpt + (size_t)a * 128);
-                const float4* pf = reinterpret_cast<const float4*>(sp.pfeat + (size_t)tree * 128);
+                const float4* pf = reinterpret_cast<const float4*>(sp.pfeat + (size_t)slot * 128);
                 float acc = 0.f;
 #pragma unroll 8
                 for (int k = 0; k < 32; ++k) {
@@ -122,11 +150,11 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_step_kernel(SearchParams
                 }
                 e = sp.exp_table[__bfloat16_as_ushort(__float2bfloat16_rn(acc))];
             } else if (sp.eval_mode == EVAL_SYNTH) {
-                const uint32_t u = fmix32_d(sp.synth_hash[tree] ^ (((uint32_t)a + 1u) * 0x9E3779B1u));
+                const uint32_t u = fmix32_d(sp.synth_hash[slot] ^ (((uint32_t)a + 1u) * 0x9E3779B1u));
                 const float logit = (float)((int)((u >> 16) & 0xFF) - 128) / 32.0f;
                 e = sp.exp_table[__bfloat16_as_ushort(__float2bfloat16_rn(logit))];
             } else {
-                e = sp.expvals[(size_t)tree * 4672 + a];
+                e = sp.expvals[(size_t)slot * 4672 + a];
             }
             pv[i] = e;
         }
@@ -155,35 +183,39 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_step_kernel(SearchParams
             }
         }
         __syncwarp();
-        const int plen = ts.path_len;
+        const int plen = sl.path_len;
+        const float v = -sp.value[slot];  // update(node, -value), mcts.py:74
         if (lane == 0) {
             Node& lf = sp.nodes[leaf];
             lf.first_child = base;
             lf.n_children = (uint8_t)n;
+            lf.term = 0;
             ts.n_nodes += n;
             ts.n_evals += 1;
             atomicAdd(&sp.counters[0], 1);
             if (!is_root) {
-                if (plen == 0) backup(sp.nodes, leaf, -sp.value[tree]);
+                if (plen == 0) backup(sp.nodes, leaf, v);  // path too deep to record: walk the parent links (never with virtual loss)
                 ts.sims_done += 1;
                 atomicAdd(&sp.counters[1], 1);
             }
             __threadfence_block();
         }
         __syncwarp();
-        if (!is_root && plen > 0) backup_path(sp.nodes, sp.path + (size_t)tree * MCTS_MAX_PATH, plen, -sp.value[tree], lane);
+        if (!is_root && plen > 0) {
+            const int32_t* path = sp.path + (size_t)slot * MCTS_MAX_PATH;
+            if (vl) settle_path(sp.nodes, path, plen, v, lane);
+            else backup_path(sp.nodes, path, plen, v, lane);
+        }
         __syncwarp();
     }
-    // ------------------------------------------------------------------ B. simulate to the next leaf
+
+    // ------------------------------------------------------------------ B. simulate until `leaves` leaves wait for the network
     int sims_done = __shfl_sync(0xffffffffu, ts.sims_done, 0);
     const int sims_target = ts.sims_target;
     const bool noisy = ts.noisy != 0;
     const double cpuct_fixed = ts.cpuct;
-    while (true) {
-        if (sims_done >= sims_target) {
-            if (lane == 0) ts.status = TREE_DONE;
-            return;
-        }
+    int n_new = 0;
+    while (sims_done + n_new < sims_target && n_new < L) {
         int node = ts.root_node;
         int parent_pos = ts.root_pos;
         int32_t* path = s_path[warp];
@@ -252,9 +284,10 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_step_kernel(SearchParams
             nd = nx;
         }
         __syncwarp();
+        if (nd.term == 3) break;  // ran into a leaf that already waits for its evaluation: nothing new to select this step
         // ---- leaf: position, outcome (mcts.py:67, game.py:49-59)
-        // lane 0 makes the move and generates the legal moves; the threefold claim-ahead scan (one make-move +
-        // history walk per legal move, the expensive part of outcome(claim_draw=True)) runs one move per lane
+        // lane 0 makes the move; the legal moves come from the whole warp (rules_warp.cuh); the threefold claim-ahead
+        // scan (one make-move + history walk per legal move) runs one move per lane
         int term = 0, n_moves = 0, leaf_pos = -1, err = 0, scan = 0, fresh = 0;
         uint16_t* sm = s_m[warp];
         if (lane == 0) {
@@ -300,41 +333,53 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_step_kernel(SearchParams
         }
         err = __shfl_sync(0xffffffffu, err, 0);
         term = __shfl_sync(0xffffffffu, term, 0);
-        if (!err && term && depth > 0) {
-            // evaluate() returned (value, True): update(node, -value) with value = -1 or 0
-            backup_path(sp.nodes, path, depth, term == 2 ? 1.0f : -0.0f, lane);
-        } else if (!err && !term) {
-            // keep the path for the backup that follows the network evaluation (phase A of the next step)
-            int32_t* gp = sp.path + (size_t)tree * MCTS_MAX_PATH;
-            for (int d = lane; d < depth; d += 32) gp[d] = path[d];
+        leaf_pos = __shfl_sync(0xffffffffu, leaf_pos, 0);
+        if (err) {
+            if (lane == 0) { ts.error = 2; atomicAdd(&sp.counters[2], 1); }
+            return;
         }
-        __syncwarp();
-        if (lane == 0) {
-            if (!err && term) {
+        if (term) {
+            // evaluate() returned (value, True): update(node, -value) with value = -1 or 0; terminal leaves are
+            // re-evaluated on every visit and never expanded (mcts.py:67-74)
+            if (depth > 0) backup_path(sp.nodes, path, depth, term == 2 ? 1.0f : -0.0f, lane);
+            __syncwarp();
+            if (lane == 0) {
                 sp.nodes[node].term = (int8_t)term;
                 if (depth <= 0) backup(sp.nodes, node, term == 2 ? 1.0f : -0.0f);
                 ts.sims_done += 1;
                 atomicAdd(&sp.counters[1], 1);
-            } else if (!err) {
-                ts.path_len = depth > 0 ? depth : 0;
-                uint16_t* pm = sp.pend_moves + (size_t)tree * MAX_MOVES;
-                for (int i = 0; i < n_moves; ++i) pm[i] = sm[i];
-                ts.leaf_node = node;
-                ts.leaf_pos = leaf_pos;
-                ts.n_moves = n_moves;
-                ts.status = TREE_WAIT_LEAF;
-                fill_frames(sp, tree, leaf_pos);
-            } else {
-                ts.error = 2;
-                atomicAdd(&sp.counters[2], 1);
+                __threadfence_block();
             }
+            __syncwarp();
+            ++sims_done;
+            continue;
+        }
+        // ---- a leaf for the network: evaluation slot n_new of this tree
+        const int slot = tree * L + n_new;
+        {
+            // keep the path for the backup that follows the evaluation (phase A of the next step)
+            int32_t* gp = sp.path + (size_t)slot * MCTS_MAX_PATH;
+            for (int d = lane; d < depth; d += 32) gp[d] = path[d];
+            uint16_t* pm = sp.pend_moves + (size_t)slot * MAX_MOVES;
+            for (int i = lane; i < n_moves; i += 32) pm[i] = sm[i];
+        }
+        if (vl && depth > 0) virtual_loss_path(sp.nodes, path, depth, lane);
+        __syncwarp();
+        if (lane == 0) {
+            SlotState sl;
+            sl.leaf_node = node; sl.leaf_pos = leaf_pos; sl.n_moves = n_moves; sl.path_len = depth > 0 ? depth : 0;
+            sp.slots[slot] = sl;
+            if (vl) sp.nodes[node].term = 3;
+            fill_frames(sp, slot, leaf_pos);
             __threadfence_block();
         }
         __syncwarp();
-        term = __shfl_sync(0xffffffffu, term, 0);
-        err = __shfl_sync(0xffffffffu, err, 0);
-        if (err || !term) return;
-        ++sims_done;
+        ++n_new;
+        if (vl && depth <= 0) break;  // no recorded path, no virtual loss: do not select a second leaf on top of it
+    }
+    if (lane == 0) {
+        ts.n_pending = n_new;
+        ts.status = n_new > 0 ? TREE_WAIT_LEAF : TREE_DONE;
     }
 }
 
@@ -351,17 +396,19 @@ __global__ void __launch_bounds__(128) mcts_begin_kernel(SearchParams sp) {
     r.first_child = -1; r.parent = -1; r.pos_id = ts.root_pos; r.move = 0; r.n_children = 0; r.term = 0;
     sp.nodes[node] = r;
     ts.root_node = node;
-    ts.leaf_node = node;
-    ts.leaf_pos = ts.root_pos;
     ts.n_nodes = 1;
     ts.n_evals = 0;
     ts.sims_done = 0;
+    ts.n_pending = 1;
+    const int slot0 = tree * sp.leaves;
     MoveList ml;
     generate_legal(sp.pos[ts.root_pos], ml);
-    ts.n_moves = ml.n;
-    uint16_t* pm = sp.pend_moves + (size_t)tree * MAX_MOVES;
+    SlotState sl;
+    sl.leaf_node = node; sl.leaf_pos = ts.root_pos; sl.n_moves = ml.n; sl.path_len = 0;
+    sp.slots[slot0] = sl;
+    uint16_t* pm = sp.pend_moves + (size_t)slot0 * MAX_MOVES;
     for (int i = 0; i < ml.n; ++i) pm[i] = ml.m[i];
-    fill_frames(sp, tree, ts.root_pos);
+    for (int i = 0; i < sp.leaves; ++i) fill_frames(sp, slot0 + i, ts.root_pos);  // every slot of the batch encodes a valid position
 }
 
 int launch_mcts_begin(const SearchParams& sp, cudaStream_t stream) {

@@ -173,11 +173,17 @@ class Engine:
             return
         check(lib.cb_search_create(self._h, max_trees, max_nodes, max_positions, max_sims), "search_create")
         self.search_shape = (max_trees, max_nodes, max_positions, max_sims)
+        self.search_leaves = 1
 
-    def search_begin(self, records, sims, cpuct=None, noise=None, max_game_length=512, eval_mode=EVAL_NET, seed=0):
+    def search_begin(self, records, sims, cpuct=None, noise=None, max_game_length=512, eval_mode=EVAL_NET, seed=0, leaves=1):
         """records: list of uint8 [k_i,96]; sims: int or list; cpuct: None / float / list (None = AlphaZero
-        schedule); noise: None or list (per tree) of None / float64 arrays of Gamma(0.3,1) samples."""
+        schedule); noise: None or list (per tree) of None / float64 arrays of Gamma(0.3,1) samples.
+        leaves: leaves of a tree evaluated per step — 1 = the reference's sequential simulations (exact visit
+        counts), > 1 = throughput mode with virtual loss (evaluation batch = trees * leaves)."""
         n = len(records)
+        if leaves != getattr(self, "search_leaves", 1):
+            check(lib.cb_search_set_leaves(self._h, int(leaves)), "search_set_leaves")
+            self.search_leaves = int(leaves)
         lens = np.array([len(r) for r in records], dtype=np.int32)
         flat = np.ascontiguousarray(np.concatenate(records, axis=0))
         sims_a = np.full(n, sims, dtype=np.int32) if np.isscalar(sims) else np.asarray(sims, dtype=np.int32)
@@ -238,8 +244,14 @@ class Engine:
         """Complete batched search on the device network / synthetic network: returns read_roots() + counters."""
         self.search_begin(records, sims, **kw)
         max_sims = int(np.max(sims))
-        self.search_run(max_sims + 1)
+        leaves = self.search_leaves
+        self.search_run((max_sims + leaves - 1) // leaves + 1)
         st = self.search_status()
+        extra = 0
+        while st["unfinished"] and not st["errors"] and leaves > 1 and extra < max_sims:
+            self.search_run(4)                       # steps that selected fewer than `leaves` leaves (collisions) leave a remainder
+            extra += 4
+            st = self.search_status()
         if st["errors"]:
             raise RuntimeError("search: node or position pool exhausted (raise max_nodes / max_positions)")
         if st["unfinished"]:

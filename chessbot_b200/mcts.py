@@ -92,10 +92,12 @@ def _external_search(engine, network, records, sims, cpuct, noise, max_len):
     return out
 
 
-def search_batch(games, network, num_simulations=100, add_noise=True, CPUCT=None, rng=None, noise=None):
+def search_batch(games, network, num_simulations=100, add_noise=True, CPUCT=None, rng=None, noise=None, leaves_per_tree=1):
     """The search of run_mcts (mcts.py:50-74) for a list of games in one device batch, without the final move
     choice.  num_simulations / add_noise / CPUCT may be scalars or per-game lists.  `noise`: optional per-game
-    pre-drawn Gamma(0.3, 1) samples (else drawn from `rng` like mcts.py:158).  Returns the root Nodes."""
+    pre-drawn Gamma(0.3, 1) samples (else drawn from `rng` like mcts.py:158).  leaves_per_tree > 1 selects that many
+    leaves of every tree per step under virtual loss: more throughput for few games, visit counts no longer those of
+    the reference's sequential order (device networks only).  Returns the root Nodes."""
     from .engine import EVAL_NET, EVAL_SYNTH, Engine
     from .gameimage import as_device_board
     n = len(games)
@@ -120,24 +122,27 @@ def search_batch(games, network, num_simulations=100, add_noise=True, CPUCT=None
     has_noise = any(z is not None for z in noise)
     if isinstance(network, DeviceNetwork):
         network.ensure_loaded()
-        if network.max_batch < n:
-            network.max_batch = n
+        if network.max_batch < n * leaves_per_tree:
+            network.max_batch = n * leaves_per_tree
             network.load()
-        out = engine.search(records, sims, cpuct=cpuct, noise=noise if has_noise else None, max_game_length=max_len, eval_mode=EVAL_NET)
+        out = engine.search(records, sims, cpuct=cpuct, noise=noise if has_noise else None, max_game_length=max_len, eval_mode=EVAL_NET,
+                            leaves=leaves_per_tree)
     elif isinstance(network, SyntheticNetwork):
         out = engine.search(records, sims, cpuct=cpuct, noise=noise if has_noise else None, max_game_length=max_len,
-                            eval_mode=EVAL_SYNTH, seed=network.seed)
+                            eval_mode=EVAL_SYNTH, seed=network.seed, leaves=leaves_per_tree)
     else:
+        if leaves_per_tree != 1:
+            raise ValueError("a host network evaluates one leaf per tree: leaves_per_tree must be 1")
         out = _external_search(engine, network, records, sims, cpuct, noise if has_noise else None, max_len)
     out["noisy"] = [z is not None for z in noise]
     return [_root_from_device(out, i) for i in range(n)]
 
 
 def run_mcts_batch(games, network, num_simulations=100, num_sampling_moves=30, add_noise=True, CPUCT=None,
-                   rng=None, noise=None):
+                   rng=None, noise=None, leaves_per_tree=1):
     """run_mcts for a list of games in one device batch (one tree per game).  Returns [(move_uci, root Node), ...]."""
     rng = np.random.default_rng() if rng is None else rng
-    roots = search_batch(games, network, num_simulations, add_noise, CPUCT, rng=rng, noise=noise)
+    roots = search_batch(games, network, num_simulations, add_noise, CPUCT, rng=rng, noise=noise, leaves_per_tree=leaves_per_tree)
     results = []
     for g, root in zip(games, roots):
         temp = TEMP if g.history_len < num_sampling_moves else 0
@@ -145,9 +150,10 @@ def run_mcts_batch(games, network, num_simulations=100, num_sampling_moves=30, a
     return results
 
 
-def run_mcts(game: Game, network, num_simulations: int = 100, num_sampling_moves=30, add_noise=True, CPUCT=None):
-    """mcts.py:38-77: returns (move, root) with root.children[uci].N/W/Q/P filled in."""
-    return run_mcts_batch([game], network, num_simulations, num_sampling_moves, add_noise, CPUCT)[0]
+def run_mcts(game: Game, network, num_simulations: int = 100, num_sampling_moves=30, add_noise=True, CPUCT=None, leaves_per_tree=1):
+    """mcts.py:38-77: returns (move, root) with root.children[uci].N/W/Q/P filled in.  leaves_per_tree (extension, default 1 =
+    the reference's behaviour): leaves evaluated per network call under virtual loss."""
+    return run_mcts_batch([game], network, num_simulations, num_sampling_moves, add_noise, CPUCT, leaves_per_tree=leaves_per_tree)[0]
 
 
 # ------------------------------------------------------------------------------ node-level API

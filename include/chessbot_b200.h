@@ -102,6 +102,11 @@ int cb_policy_softmax(cb_ctx* ctx, const void* pos_dev, const int32_t* cur_idx_d
 #define CB_EVAL_SYNTH 1      /* synthetic hash network */
 #define CB_EVAL_EXTERNAL 2   /* host callable: cb_search_pending_planes / cb_search_step_external */
 int cb_search_create(cb_ctx* ctx, int max_trees, int max_nodes, int max_positions, int max_sims);
+/* leaves of one tree evaluated per step.  1 (default) = the reference's strictly sequential simulations: visit counts are
+ * the reference's.  > 1 = throughput mode for few games (north_star: "virtual-loss ... over many concurrent trees"): a tree
+ * selects up to `leaves` leaves per step, each lowering its path by one lost game until its evaluation arrives; the
+ * evaluation batch is n_trees * leaves.  Call between cb_search_create and cb_search_begin. */
+int cb_search_set_leaves(cb_ctx* ctx, int leaves);
 /* roots: concatenated game records (cb_board_export_record), rec_len[n_trees] positions each (host memory).
  * sims[n], cpuct[n] (<0 = AlphaZero schedule, mcts.py:135-139), noise: NULL or [n][CB_MAX_MOVES] Gamma(0.3,1)
  * samples per tree (mcts.py:158), has_noise[n] flags; max_game_length: config.py:33. */

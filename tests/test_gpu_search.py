@@ -292,3 +292,66 @@ def test_warp_move_generation_matches_host_rules_on_many_positions(engine):
         for i, b in enumerate(chunk):
             k = counts[i]
             assert [code_to_uci(c) for c in moves[i, :k]] == expected[lo + i], (b.fen(), k)
+
+
+def test_virtual_loss_mode_invariants_and_agreement(engine):
+    """Throughput mode (north_star: "virtual-loss ... over many concurrent trees"): several leaves of one tree per
+    network call.  Not the reference's sequential order, so no bit parity; what must hold: the requested number of
+    simulations exactly, every virtual loss settled (Q == W / N, |W| <= N, visits sum to the simulations), the search
+    is deterministic, and its preferred move mostly agrees with the exact sequential search."""
+    from gpu_util import device_board, random_games
+    from chessbot_b200.engine import EVAL_SYNTH
+    games = random_games(40, seed=88, max_plies=100)
+    recs = [device_board(f, m).export_record() for f, m in games]
+    noise = [np.random.default_rng(i).gamma(0.3, 1, 256) if i % 2 else None for i in range(40)]
+    exact = engine.search(recs, 200, noise=noise, eval_mode=EVAL_SYNTH, seed=4)
+    outs = {}
+    for leaves in (4, 16):
+        out = engine.search(recs, 200, noise=noise, eval_mode=EVAL_SYNTH, seed=4, leaves=leaves)
+        again = engine.search(recs, 200, noise=noise, eval_mode=EVAL_SYNTH, seed=4, leaves=leaves)
+        assert out["unfinished"] == 0 and out["errors"] == 0 and out["sims"] == 40 * 200 and out["evals"] <= 40 * 201
+        agree = 0
+        for i in range(40):
+            k = out["n_children"][i]
+            n, w, q = out["N"][i, :k], out["W"][i, :k], out["Q"][i, :k]
+            assert k == exact["n_children"][i] and np.array_equal(out["moves"][i, :k], exact["moves"][i, :k])
+            assert np.array_equal(out["P"][i, :k], exact["P"][i, :k])          # the root expansion is the same
+            assert out["root_N"][i] == 201 and n.sum() == 200 and (n >= 0).all()
+            vis = n > 0
+            assert np.array_equal(q[vis], (w[vis] / n[vis].astype(np.float32)).astype(np.float32)) and not w[~vis].any()
+            assert (np.abs(w) <= n + 1e-3).all()
+            for key in ("N", "W", "Q"):
+                assert np.array_equal(out[key][i, :k], again[key][i, :k])
+            agree += int(np.argmax(n) == np.argmax(exact["N"][i, :k]))
+        outs[leaves] = agree
+        print(f"\nvirtual loss, {leaves} leaves per tree: most-visited move agrees with the sequential search on {agree}/40 positions")
+        assert agree >= 26
+    back = engine.search(recs, 200, noise=noise, eval_mode=EVAL_SYNTH, seed=4)   # back to one leaf per tree: exact again
+    for key in ("N", "W", "Q", "P"):
+        assert np.array_equal(back[key], exact[key])
+
+
+def test_virtual_loss_single_game_with_device_network():
+    """mcts.run_mcts(game, network, leaves_per_tree=8): one game, eight leaves per network call."""
+    import time
+    import chessbot_b200.mcts as mcts
+    from chessbot_b200.board import Board
+    from chessbot_b200.config import Config
+    from chessbot_b200.game import Game
+    from chessbot_b200.model import DeviceNetwork, keras_init_weights
+    import bench
+    net = DeviceNetwork(bench.trained_like_bn(keras_init_weights(128, 6, seed=2), 128, 6), 128, 6, max_batch=64)
+    game = Game(Config(), board=Board())
+    res = {}
+    for leaves in (1, 8):
+        mcts.run_mcts(game, net, 64, 0, False, None, leaves_per_tree=leaves)      # warm
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        move, root = mcts.run_mcts(game, net, 400, 0, False, None, leaves_per_tree=leaves)
+        res[leaves] = (move, root, time.perf_counter() - t0)
+        assert root.N == 401 and sum(c.N for c in root.children.values()) == 400
+    print(f"\nsingle game, 400 sims, 6x128: {res[1][2] * 1e3:.0f} ms sequential, {res[8][2] * 1e3:.0f} ms with 8 leaves per call")
+    # a random-init network has no clear favourite at the start position: only require a plausible choice
+    top = sorted(res[1][1].children, key=lambda u: -res[1][1].children[u].N)[:10]
+    assert res[8][0] in top
+    assert res[8][2] < res[1][2]
