@@ -51,21 +51,49 @@ def _uci(code):
     return u
 
 
-def _root_from_device(out, i):
-    """Root Node with its children dict (legal-move order) from the read-back root statistics of tree i."""
-    root = Node()
-    root.N = int(out["root_N"][i])
-    k = int(out["n_children"][i])
-    moves = out["moves"][i, :k].tolist()
-    ns = out["N"][i, :k].tolist()
-    ws, qs = list(out["W"][i, :k]), list(out["Q"][i, :k])                 # np.float32 scalars, like the reference's nodes
-    ps = list(out["P"][i, :k]) if out["noisy"][i] else list(out["P"][i, :k].astype(np.float32))
-    children = root.children
-    for j in range(k):
-        c = Node.__new__(Node)
-        c.parent, c.children, c.N, c.W, c.P, c.Q = root, {}, ns[j], ws[j], ps[j], qs[j]
-        children[_uci(moves[j])] = c
-    return root
+def _roots_from_device(out, n):
+    """Root Nodes with their children dicts (legal-move order) from the read-back root statistics of n trees.
+    The per-child values keep the reference's scalar types (np.float32 W / Q / P, np.float64 P at a noisy root).
+    All trees are unpacked with one masked gather per array, and the cyclic collector is paused while the ~30 nodes per
+    tree are created (it would rescan every live node of earlier searches otherwise)."""
+    import gc
+    k = np.asarray(out["n_children"][:n])
+    mask = np.arange(out["moves"].shape[1])[None, :] < k[:, None]
+    codes = out["moves"][:n][mask].tolist()
+    ns = out["N"][:n][mask].tolist()
+    ws, qs = list(out["W"][:n][mask]), list(out["Q"][:n][mask])
+    noisy = np.asarray(out["noisy"][:n], dtype=bool)
+    p_flat = out["P"][:n][mask]
+    if noisy.all():
+        ps = list(p_flat)
+    elif not noisy.any():
+        ps = list(p_flat.astype(np.float32))
+    else:
+        per_child = np.repeat(noisy, k)
+        ps = np.empty(len(codes), dtype=object)
+        ps[per_child] = list(p_flat[per_child])
+        ps[~per_child] = list(p_flat[~per_child].astype(np.float32))
+        ps = ps.tolist()
+    ucis = [_uci(c) for c in codes]
+    root_n = out["root_N"][:n].tolist()
+    roots, new, off = [], Node.__new__, 0
+    was_enabled = gc.isenabled()
+    gc.disable()
+    try:
+        for i, ki in enumerate(k.tolist()):
+            root = Node()
+            root.N = root_n[i]
+            children = root.children
+            for j in range(off, off + ki):
+                c = new(Node)
+                c.parent, c.children, c.N, c.W, c.P, c.Q = root, {}, ns[j], ws[j], ps[j], qs[j]
+                children[ucis[j]] = c
+            off += ki
+            roots.append(root)
+    finally:
+        if was_enabled:
+            gc.enable()
+    return roots
 
 
 def _external_search(engine, network, records, sims, cpuct, noise, max_len):
@@ -135,7 +163,7 @@ def search_batch(games, network, num_simulations=100, add_noise=True, CPUCT=None
             raise ValueError("a host network evaluates one leaf per tree: leaves_per_tree must be 1")
         out = _external_search(engine, network, records, sims, cpuct, noise if has_noise else None, max_len)
     out["noisy"] = [z is not None for z in noise]
-    return [_root_from_device(out, i) for i in range(n)]
+    return _roots_from_device(out, n)
 
 
 def run_mcts_batch(games, network, num_simulations=100, num_sampling_moves=30, add_noise=True, CPUCT=None,
