@@ -61,6 +61,7 @@ _SIGS = {
     "cb_profile": (i32, [vp, i32]),
     "cb_profile_read_sync": (i32, [vp, vp, vp]),
     "cb_debug_conv_layer": (i32, [vp, i32, vp, vp, vp, i32, i32, vp]),
+    "cb_debug_wgrad": (i32, [vp, vp, vp, i32, i32, i32, vp, i32, vp]),
 }
 for _name, (_res, _args) in _SIGS.items():
     _f = getattr(lib, _name)

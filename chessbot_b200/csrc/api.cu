@@ -446,6 +446,27 @@ int cb_debug_conv_layer(cb_ctx* ctx, int layer, const void* in_act_dev, const vo
     return launch_tower(tp, ctx->sms, st);
 }
 
+// weight gradient of one 3x3 convolution on tile-native buffers: out_dev f32 [9][cin_pad][n] (padded channels included)
+int cb_debug_wgrad(cb_ctx* ctx, const void* in_act_dev, const void* dy_act_dev, int n_boards, int cin_pad, int n, float* out_dev,
+                   int use_reference, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int pairs = (n_boards + 1) / 2, cj_in = cin_pad / 8;
+    if (use_reference)
+        return launch_wgrad_reference((const __nv_bfloat16*)in_act_dev, (const __nv_bfloat16*)dy_act_dev, pairs, cj_in, n, out_dev, st);
+    WgradParams wp{};
+    wp.pairs = pairs; wp.cj_in = cj_in; wp.n = n; wp.splits = wgrad_splits(ctx->sms, cj_in);
+    const int dy_chunks = n / 16;
+    if (conv_make_row_map(&wp.tm_a, in_act_dev, (uint64_t)pairs * cj_in * 25, 200) ||
+        conv_make_row_map(&wp.tm_dy, dy_act_dev, (uint64_t)pairs * (n / 8) * 25, 25 * (dy_chunks < 8 ? dy_chunks : 8)))
+        return -1;
+    DevBuf<float> partial;
+    if (partial.alloc((size_t)wp.splits * 9 * cin_pad * n, false)) return -1;
+    wp.partial = partial.p;
+    if (launch_wgrad(wp, st) || launch_wgrad_reduce(partial.p, wp.splits, cin_pad, n, cin_pad, n, 0, out_dev, st)) return -1;
+    CB_CUDA_OK(cudaStreamSynchronize(st));  // the scratch buffer is freed on return
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------ search
 int cb_search_create(cb_ctx* ctx, int max_trees, int max_nodes, int max_positions, int max_sims) {
     Search& s = ctx->search;

@@ -139,6 +139,21 @@ __device__ __forceinline__ void tma_load_2d_pair(void* dst_smem, const void* ten
         "l"(tensor_map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
         : "memory");
 }
+// TMA tile load (2-D tensor map) into this CTA's shared memory, completing on this CTA's barrier
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const void* tensor_map, int c0, int c1, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(tensor_map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+// the same tile delivered to the same shared-memory offset (and barrier offset) of every CTA of the cluster in cta_mask
+__device__ __forceinline__ void tma_load_2d_multicast(void* dst_smem, const void* tensor_map, int c0, int c1, uint64_t* bar, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(tensor_map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+        : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const void* tensor_map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tensor_map) : "memory");
 }
@@ -216,6 +231,10 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
 __device__ __forceinline__ uint32_t idesc_bf16_f32(int m, int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
+// the same with both operands MN-major (bits 15 / 16): shared memory holds 8 consecutive M (or N) indices in 16 bytes and
+// steps along K from one 16-byte cell to the next.  In the no-swizzle descriptor LBO is then the stride between the
+// 8-cell groups along K and SBO the stride between 8-index groups along M / N.
+__device__ __forceinline__ uint32_t idesc_bf16_f32_mn(int m, int n) { return idesc_bf16_f32(m, n) | (1u << 15) | (1u << 16); }
 }  // namespace ptx
 #endif
 

@@ -137,7 +137,22 @@ struct SearchParams {
     int32_t* path;             // [slots][MCTS_MAX_PATH] node ids root..leaf of every pending leaf
 };
 
+// Weight gradient of one 3x3 convolution (wgrad.cu)
+struct WgradParams {
+    CUtensorMap tm_a;    // layer input (tile-native, cj_in chunks per board pair) as rows of 128 B, box = 200 rows (64 channels of a pair)
+    CUtensorMap tm_dy;   // gradient of the layer's raw output (n/8 chunks per pair), box = 25 * min(8, n/16) rows
+    float* partial;      // [splits][9][cj_in*8][n] f32 partial sums
+    int pairs;           // board pairs in the batch
+    int cj_in;           // input channels / 8: 8, 16 or 32
+    int n;               // output channels (padded): 64, 128 or 256
+    int splits;          // split-K factor over the board pairs (wgrad_splits)
+};
+
 int launch_tower(const TowerParams& p, int num_sms, cudaStream_t stream);
+int wgrad_splits(int num_sms, int cj_in);
+int launch_wgrad(const WgradParams& p, cudaStream_t stream);
+int launch_wgrad_reduce(const float* partial, int splits, int ci_pad, int n, int cin, int c, int stem, float* out, cudaStream_t stream);
+int launch_wgrad_reference(const __nv_bfloat16* in, const __nv_bfloat16* dy, int pairs, int cj_in, int n, float* out, cudaStream_t stream);
 int conv_make_row_map(CUtensorMap* tm, const void* base, uint64_t rows, uint32_t box_rows);
 int launch_conv3x3_reference(const ConvParams& p, cudaStream_t stream);
 int launch_encode(const Pos* pos_base, const int32_t* frame_idx, int n, __nv_bfloat16* planes_act, int16_t* planes_i16, cudaStream_t stream);

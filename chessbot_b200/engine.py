@@ -165,6 +165,12 @@ class Engine:
                                       _stream()), "debug_conv_layer")
         return out
 
+    def debug_wgrad(self, in_act, dy_act, n_boards, cin_pad, n, use_reference=False):
+        out = torch.zeros(9, cin_pad, n, dtype=torch.float32, device=self.device)
+        check(lib.cb_debug_wgrad(self._h, _ptr(in_act), _ptr(dy_act), n_boards, cin_pad, n, _ptr(out), int(use_reference), _stream()),
+              "debug_wgrad")
+        return out
+
     # ------------------------------------------------------------------ mcts
     def search_create(self, max_trees, max_nodes=None, max_positions=None, max_sims=800):
         max_nodes = max_nodes or max_trees * (max_sims + 2) * 40

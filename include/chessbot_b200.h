@@ -142,6 +142,11 @@ int cb_profile_read_sync(cb_ctx* ctx, double* total_ms /*[CB_PROF_STAGES]*/, int
 int cb_debug_conv_layer(cb_ctx* ctx, int layer, const void* in_act_dev, const void* skip_act_dev, void* out_act_dev,
                         int n_boards, int use_reference, void* stream);
 
+/* weight gradient of one 3x3 convolution (csrc/wgrad.cu) on tile-native buffers: dW[tap][ci][co] = sum over boards and
+ * squares of in[.., ci] shifted by the tap times dy[.., co]; out_dev f32 [9][cin_pad][n], padded channels included. */
+int cb_debug_wgrad(cb_ctx* ctx, const void* in_act_dev, const void* dy_act_dev, int n_boards, int cin_pad, int n,
+                   float* out_dev, int use_reference, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
