@@ -468,6 +468,124 @@ def run_leaf_eval_arm(args):
         dist.destroy_process_group()
 
 
+def run_train_arm(args):
+    """BASELINE config 5: train.py step — 20x256 net, batch 4096 per GPU, data parallel with one NCCL
+    all-reduce of the gradient buffer per step.  A step = forward + backward + all-reduce + SGD update on one synthetic batch."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from chessbot_b200.model import keras_init_weights
+    from chessbot_b200.train import Trainer, train_flops_per_sample
+    filters, blocks = parse_net(args.net)
+    B, W, K = args.batch, args.warmup, args.steps
+    tr = Trainer(keras_init_weights(filters, blocks, seed=0), filters, blocks, B, device=local_rank)
+    rng = np.random.default_rng(100 + rank)
+    images = rng.integers(0, 2, (B, 8, 8, 119), dtype=np.int16)            # synthetic planes of the sample format (train.py:104-110)
+    images[..., 113] = rng.integers(0, 200, (B, 1, 1))
+    images[..., 118] = rng.integers(0, 100, (B, 1, 1))
+    z = rng.integers(-1, 2, B).astype(np.float32)
+    pi = np.zeros((B, 4672), dtype=np.float32)
+    cols = rng.integers(0, 4672, (B, 32))
+    np.put_along_axis(pi, cols, rng.random((B, 32)).astype(np.float32), axis=1)
+    pi /= pi.sum(1, keepdims=True)
+    h_img, h_z, h_pi = (torch.from_numpy(a).pin_memory() for a in (images, z, pi))
+    d_img, d_z, d_pi = (t.cuda() for t in (h_img, h_z, h_pi))
+    lr = 0.01
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for _ in range(W):
+        tr.forward_backward(d_img, d_z, d_pi)
+        tr.apply(lr)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(K):                                   # inputs resident in HBM
+        tr.forward_backward(d_img, d_z, d_pi)
+        tr.apply(lr)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    losses = tr.losses()
+    tr.profile(True)
+    for _ in range(max(2, K // 4)):
+        tr.forward_backward(d_img, d_z, d_pi)
+        tr.apply(lr)
+    prof = tr.profile_read()
+    tr.profile(False)
+    prof_steps = max(2, K // 4)
+    barrier()
+    t0 = time.perf_counter()
+    reps = max(2, K // 4)
+    for _ in range(reps):                                # end to end: pinned host batch -> H2D -> step -> losses D2H
+        out = tr.train_on_batch(h_img, h_z, h_pi, lr)
+    torch.cuda.synchronize()
+    e2e_dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([ms, e2e_dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_dt = t.tolist()
+    if rank == 0:
+        peak_tf, peak_gbs, peak_src = measured_peaks()
+        mma_ms = prof["conv_fwd"][0] + prof["wgrad"][0] + prof["dgrad"][0]
+        tf = train_flops_per_sample(filters, blocks) * B * prof_steps / (mma_ms * 1e-3) / 1e12
+        tot = sum(v[0] for v in prof.values())
+        npad = (filters + 63) // 64 * 64
+        act_mb = B / 2 * npad / 8 * 3200 / 1e6
+        kernels = {k: {"launches": v[1], "ms_per_step": v[0] / prof_steps, "share_of_step": v[0] / tot} for k, v in prof.items() if v[1]}
+        for k, passes in (("bn_fwd", 3.5), ("bn_bwd", 8.5)):   # tensors streamed per layer: fwd stats r + apply r,(skip) w; bwd reduce 3r + apply 3r, 1-2 w
+            gbs = passes * act_mb * 1e6 * (1 + 2 * blocks) / (prof[k][0] / prof_steps * 1e-3) / 1e9
+            kernels[k].update({"bound": "hbm", "achieved_gbs": gbs, "peak_gbs": peak_gbs, "frac": gbs / peak_gbs})
+        cpu = None if args.no_cpu_baseline else train_cpu_baseline_leg(filters, blocks)
+        print(json.dumps({
+            "metric": "training samples/s (train.py step: forward + backward + gradient all-reduce + SGD update)", "value": world * B * K / (ms * 1e-3),
+            "unit": "samples/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"train.py step (BASELINE config 5): {blocks}x{filters} net, batch {B} per GPU, BN batch statistics per GPU, "
+                                   f"SGD nesterov + l2, gradients all-reduced over NCCL ({world} GPU(s))", "net": args.net, "batch_per_gpu": B,
+                       "l2": "every layer's activation tensor (%.0f MB) exceeds the 126 MB L2; no flush" % act_mb},
+            "roofline": {"bound": "tensor", "kernel": "tower_tcgen05_kernel (forward, data gradient) + wgrad_tcgen05_kernel", "achieved": tf,
+                         "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf, "traffic": None, "peak_source": peak_src,
+                         "how": f"algorithmic FLOPs of the three 3x3-convolution passes / CUDA-event time of their launches over {prof_steps} steps",
+                         "mma_share_of_step": mma_ms / tot},
+            "kernels": kernels, "losses": losses,
+            "e2e": {"value": world * B * reps / e2e_dt, "unit": "samples/s", "h2d_bytes_per_step": int(h_img.numel() * 2 + h_z.numel() * 4 + h_pi.numel() * 4),
+                    "d2h_bytes_per_step": 24, "what": "Trainer.train_on_batch from pinned host arrays: H2D of images / z / pi, step, losses D2H"},
+            "gpu_launches": int(sum(v[1] for v in prof.values()) / prof_steps) * K, "clocks": clocks, "cpu_baseline": cpu}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def train_cpu_baseline_leg(filters, blocks, budget_s=15.0, batch=16):
+    """The reference's training step restated in torch fp32 on the host cores (oracle/ref_train.py), bounded sample."""
+    import torch
+    from oracle import ref_model, ref_train
+    w = ref_model.init_weights(filters, blocks, seed=0)
+    rng = np.random.default_rng(5)
+    images = rng.integers(0, 2, (batch, 8, 8, 119)).astype(np.int16)
+    z, pi = ref_train.synthetic_targets(batch, 5)
+    vel, steps = None, 0
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < budget_s or steps < 1:
+        _, w, vel, _ = ref_train.train_step(w, vel, images, z, pi, 0.01)
+        steps += 1
+    dt = time.perf_counter() - t0
+    return {"value": steps * batch / dt, "unit": "samples/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{steps} steps of batch {batch}, {blocks}x{filters} torch-fp32 autograd on the host cores, {dt:.1f} s (TensorFlow/Keras replaced by the oracle)"}
+
+
 def main():
     # NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION; the bench prints exactly one JSON line there
     if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
@@ -481,14 +599,18 @@ def main():
     ap.add_argument("--e2e-sims", type=int, default=100, help="simulations per search of the end-to-end leg (run_mcts default, mcts.py:38)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="search", choices=["search", "leaf_eval"],
-                    help="search = the headline (batched MCTS, BASELINE north_star); leaf_eval = BASELINE config 2 (use --net 6x128)")
+    ap.add_argument("--workload", default="search", choices=["search", "leaf_eval", "train"],
+                    help="search = the headline (batched MCTS, BASELINE north_star); leaf_eval = BASELINE config 2 (use --net 6x128); "
+                         "train = BASELINE config 5 (train.py step, --batch per GPU)")
+    ap.add_argument("--batch", type=int, default=4096, help="train workload: samples per GPU per step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference_arm(args)
     elif args.workload == "leaf_eval":
         run_leaf_eval_arm(args)
+    elif args.workload == "train":
+        run_train_arm(args)
     else:
         run_gpu_arm(args)
 

@@ -61,6 +61,17 @@ _SIGS = {
     "cb_profile": (i32, [vp, i32]),
     "cb_profile_read_sync": (i32, [vp, vp, vp]),
     "cb_debug_conv_layer": (i32, [vp, i32, vp, vp, vp, i32, i32, vp]),
+    "cb_train_param_count": (C.c_size_t, [i32, i32, C.POINTER(C.c_size_t)]),
+    "cb_train_create": (vp, [vp, i32, i32, i32, C.c_float, C.c_float, C.c_float, vp, vp, vp]),
+    "cb_train_destroy": (None, [vp]),
+    "cb_train_set_tensor": (i32, [vp, C.c_char_p, vp, C.c_size_t, vp]),
+    "cb_train_get_tensor": (i32, [vp, C.c_char_p, i32, vp, C.c_size_t, vp]),
+    "cb_train_forward_backward": (i32, [vp, vp, vp, vp, i32, vp]),
+    "cb_train_apply": (i32, [vp, C.c_float, C.c_float, i32, C.c_float, C.c_float, vp]),
+    "cb_train_losses_sync": (i32, [vp, vp, vp]),
+    "cb_train_outputs_sync": (i32, [vp, vp, vp]),
+    "cb_train_profile": (i32, [vp, i32]),
+    "cb_train_profile_read_sync": (i32, [vp, vp, vp]),
     "cb_debug_wgrad": (i32, [vp, vp, vp, i32, i32, i32, vp, i32, vp]),
 }
 for _name, (_res, _args) in _SIGS.items():

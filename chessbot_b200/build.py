@@ -12,7 +12,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libchessbot_b200.so")
-SOURCES = ["api.cu", "conv.cu", "wgrad.cu", "encode.cu", "heads.cu", "mcts.cu", "host_api.cpp"]
+SOURCES = ["api.cu", "conv.cu", "wgrad.cu", "train.cu", "train_api.cu", "encode.cu", "heads.cu", "mcts.cu", "host_api.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "--expt-relaxed-constexpr"]
 

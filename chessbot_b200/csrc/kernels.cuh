@@ -155,6 +155,34 @@ int launch_wgrad_reduce(const float* partial, int splits, int ci_pad, int n, int
 int launch_wgrad_reference(const __nv_bfloat16* in, const __nv_bfloat16* dy, int pairs, int cj_in, int n, float* out, cudaStream_t stream);
 int conv_make_row_map(CUtensorMap* tm, const void* base, uint64_t rows, uint32_t box_rows);
 int launch_conv3x3_reference(const ConvParams& p, cudaStream_t stream);
+// training step (train.cu)
+int launch_planes_from_images(const int16_t* img, int n, __nv_bfloat16* planes, cudaStream_t st);
+int launch_bn_stats(const __nv_bfloat16* y, int pairs, int cj, double* stats, cudaStream_t st);
+int launch_bn_apply(const __nv_bfloat16* y, const __nv_bfloat16* skip, __nv_bfloat16* out, int n, int cj, int c, const double* stats, const float* gamma,
+                    const float* beta, float* mean_rstd, float* moving, float eps, float slope, float momentum, cudaStream_t st);
+int launch_bn_bwd_reduce(const __nv_bfloat16* g, const __nv_bfloat16* a, const __nv_bfloat16* y, int n, int cj, const float* mean_rstd, float slope,
+                         double* sums, cudaStream_t st);
+int launch_bn_bwd_apply(const __nv_bfloat16* g, const __nv_bfloat16* a, const __nv_bfloat16* y, __nv_bfloat16* dy, __nv_bfloat16* dz, int n, int cj, int c,
+                        const float* mean_rstd, const float* gamma, const double* sums, float slope, float* dgamma, float* dbeta, cudaStream_t st);
+int launch_head_conv_fwd(const __nv_bfloat16* a, int n, int cj, const float* wv, const float* wp, int c, float* head_raw, cudaStream_t st);
+int launch_head_stats(const float* head_raw, int n, double* stats, cudaStream_t st);
+int launch_head_features_train(const float* head_raw, int n, const double* stats, const float* vbn, const float* pbn, float* vmoving, float* pmoving,
+                               const float* fc1, const float* fc2, int c, float eps, float slope, float momentum, float* hmr, float* vfeat,
+                               float* pfeat, float* h1pre, float* value, cudaStream_t st);
+int launch_sgemm(const float* A, const float* B, float* C, int M, int N, int K, int ta, int tb, cudaStream_t st);
+int launch_softmax_ce(float* logits, const float* pi, int n, double* losses, cudaStream_t st);
+int launch_value_loss_bwd(const float* value, const float* z, const float* h1pre, const float* fc2, int n, int c, float slope, float* dpre, float* dh1pre,
+                          float* dfc2, double* losses, cudaStream_t st);
+int launch_head_bn_bwd_reduce(const float* head_raw, const float* vfeat, const float* pfeat, const float* dvfeat, const float* dpfeat, int n,
+                              const float* hmr, float slope, double* hsums, cudaStream_t st);
+int launch_head_conv_bwd(const __nv_bfloat16* a, __nv_bfloat16* gout, int n, int cj, int c, const float* head_raw, const float* vfeat, const float* pfeat,
+                         const float* dvfeat, const float* dpfeat, const float* hmr, const double* hsums, const float* vbn, const float* pbn,
+                         const float* wv, const float* wp, float slope, float* dwv, float* dwp, float* dvbn, float* dpbn, cudaStream_t st);
+int launch_sgd(float* w, float* v, const float* g, size_t n, size_t n_reg, float lr, float mom, float l2, float gscale, int nesterov, double* losses,
+               cudaStream_t st);
+int launch_pack_conv(const float* w, int cin, int cin_pad, int c, int n, int stem, __nv_bfloat16* fwd, __nv_bfloat16* tr, cudaStream_t st);
+int launch_fill(float* p, size_t n, float v, cudaStream_t st);
+
 int launch_encode(const Pos* pos_base, const int32_t* frame_idx, int n, __nv_bfloat16* planes_act, int16_t* planes_i16, cudaStream_t stream);
 int launch_head_features(const HeadParams& p, int boards, cudaStream_t stream);
 int launch_policy_dense(const float* pfeat, const float* w, int boards, __nv_bfloat16* logits_bf16, float* logits_f32, cudaStream_t stream);

@@ -125,6 +125,31 @@ int cb_search_status_sync(cb_ctx* ctx, int64_t* counters, void* stream);
 int cb_search_read_roots_sync(cb_ctx* ctx, uint16_t* moves, int32_t* n, float* w, float* q, double* p, int32_t* n_children,
                               int32_t* root_n, int32_t* tree_nodes, void* stream);
 
+/* ---- train.py training step (train.py:150-164 -> model.fit; loss / optimizer of model.py:59-70) ------------------------ */
+/* One SGD step on a batch of replay samples (train.py:104-110: int16 images, terminal values z, visit distributions pi):
+ * loss = mean_squared_error(value, z) + CategoricalCrossentropy(from_logits)(logits, pi) + l2 * sum(kernel^2);
+ * BatchNormalization in training mode (batch statistics, moving averages with `bn_momentum`); SGD with (Nesterov) momentum.
+ * Parameters, gradients and momentum are three caller-owned flat f32 device buffers of cb_train_param_count() elements
+ * (the first *n_regularized are the conv / dense kernels the l2 term applies to, then the BN gamma / beta).  With several
+ * GPUs the caller all-reduces the gradient buffer (NCCL) between cb_train_forward_backward and cb_train_apply and
+ * passes grad_scale = 1 / world_size.  Tensor names and layouts are those of cb_net_set_tensor. */
+typedef struct cb_trainer cb_trainer;
+size_t cb_train_param_count(int filters, int blocks, size_t* n_regularized);
+cb_trainer* cb_train_create(cb_ctx* ctx, int filters, int blocks, int batch, float leaky_slope, float bn_eps, float bn_momentum,
+                            float* params_dev, float* grads_dev, float* momentum_dev);
+void cb_train_destroy(cb_trainer* t);
+int cb_train_set_tensor(cb_trainer* t, const char* name, const float* host, size_t count, void* stream);      /* synchronises */
+/* what: 0 = parameter (BN: gamma, beta, moving mean, moving variance), 1 = gradient, 2 = momentum; synchronises */
+int cb_train_get_tensor(cb_trainer* t, const char* name, int what, float* host, size_t count, void* stream);
+int cb_train_forward_backward(cb_trainer* t, const int16_t* images_dev /*[n][8][8][119]*/, const float* z_dev /*[n]*/,
+                              const float* pi_dev /*[n][4672]*/, int n, void* stream);
+int cb_train_apply(cb_trainer* t, float lr, float momentum, int nesterov, float l2, float grad_scale, void* stream);
+int cb_train_losses_sync(cb_trainer* t, double* out3 /* value mse, policy ce, l2 term */, void* stream);
+int cb_train_outputs_sync(cb_trainer* t, float* value_host /*[n]*/, void* stream);
+#define CB_TRAIN_PROF_STAGES 8   /* conv forward, BN forward, heads + losses, BN backward, wgrad, dgrad, optimizer + packing, input */
+int cb_train_profile(cb_trainer* t, int enable);
+int cb_train_profile_read_sync(cb_trainer* t, double* total_ms, int* launches);
+
 /* ---- measurement: CUDA events (on the launching stream) around every kernel launch of the entry points above ---- */
 #define CB_PROF_ENCODE 0
 #define CB_PROF_CONV 1

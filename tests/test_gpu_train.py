@@ -37,3 +37,101 @@ def test_wgrad_against_cuda_core_kernel_and_torch(engine, cin_pad, n, boards):
     y.backward(dy.float().permute(0, 3, 1, 2).contiguous())
     ref = w.grad.permute(2, 3, 1, 0).reshape(9, cin_pad, n)        # [kh*3+kw][ci][co]
     assert float((out_t - ref).abs().max()) <= 1e-3 * scale + 1e-3
+
+
+def _batch(n, seed):
+    from gpu_util import oracle_board, random_games
+    from oracle import ref_gameimage, ref_train
+    games = random_games(n, seed=seed, max_plies=100)
+    images = np.stack([ref_gameimage.board_to_image(oracle_board(f, m), 8) for f, m in games]).astype(np.int16)
+    z, pi = ref_train.synthetic_targets(n, seed)
+    return images, z, pi
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64).ravel(), np.asarray(b, np.float64).ravel()
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-12))
+
+
+def _cos(a, b):
+    a, b = np.asarray(a, np.float64).ravel(), np.asarray(b, np.float64).ravel()
+    return float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b) + 1e-30))
+
+
+def _proj(a, b):
+    a, b = np.asarray(a, np.float64).ravel(), np.asarray(b, np.float64).ravel()
+    return float(a @ b / (b @ b + 1e-30))
+
+
+# Two oracles (oracle/ref_train.py).  precision="fp32" is the reference's own arithmetic.  A weight gradient is a sum over
+# boards x squares of products that largely cancel, so the 2^-9 rounding of every activation / gradient element the device
+# stores in bf16 shows up amplified, as noise around the true gradient.  precision="bf16" is the SAME fp32 graph with those
+# tensors rounded at the same places: it measures what bf16 storage alone costs.  (Its roundings cannot be reproduced one
+# by one: a single differing rounding perturbs ~1000 sums of the next layer, so after two or three layers the rounding
+# decisions of any two implementations are independent.)  The bar: per tensor the device's distance to the fp32 gradient is
+# no larger than NOISE_X times the bf16 oracle's own distance to it (+ NOISE_ABS), it points the same way (FP32_COS), and the
+# two bf16 results are as close to each other as two independent roundings are (PAIR_X).  Losses: LOSS_TOL vs fp32.
+NOISE_X, NOISE_ABS, PAIR_X, FP32_COS, LOSS_TOL = 2.5, 0.02, 2.0, 0.95, 2e-2
+
+
+@pytest.mark.parametrize("filters,blocks,n", [(64, 1, 16), (48, 2, 33), (128, 2, 24), (256, 2, 16), (256, 3, 200)])
+def test_train_step_against_autograd_oracle(filters, blocks, n):
+    from chessbot_b200.train import Trainer
+    from oracle import ref_model, ref_train
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    w = ref_model.init_weights(filters, blocks, seed=filters + blocks, random_bn=True)
+    images, z, pi = _batch(n, seed=filters)
+    lr = 0.05
+    tr = Trainer(w, filters, blocks, n)
+    tr.forward_backward(images, z, pi)
+    g = tr.get_gradients()
+    tr.apply(lr)
+    losses = tr.losses()
+    new_w = tr.get_weights()
+    ref_losses, ref_new_w, _, ref_g = ref_train.train_step(w, None, images, z, pi, lr, device="cuda", precision="bf16")
+    fp32_losses, _, _, fp32_g = ref_train.train_step(w, None, images, z, pi, lr, device="cuda", precision="fp32")
+    for k in ("value", "policy", "l2"):
+        assert abs(losses[k] - ref_losses[k]) <= 5e-3 * max(1.0, abs(ref_losses[k])), (k, losses, ref_losses)
+        assert abs(losses[k] - fp32_losses[k]) <= LOSS_TOL * max(1.0, abs(fp32_losses[k])), (k, losses, fp32_losses)
+    rows = {}
+    for k in w:
+        a, b, c = g[k], ref_g[k], fp32_g[k]
+        if k.endswith(("bn", "bn1", "bn2")):
+            a, b, c = a[:2], b[:2], c[:2]
+        rows[k] = (round(_rel(a, c), 4), round(_rel(b, c), 4), round(_rel(a, b), 4), round(_cos(a, c), 5))
+    worst = max(rows.items(), key=lambda kv: kv[1][0])
+    print(f"\ntrain step {filters}x{blocks} batch {n}: losses {losses}; worst gradient (device vs fp32, bf16 oracle vs fp32, device vs "
+          f"bf16 oracle, cos device/fp32): {worst}")
+    big = {k: v for k, v in rows.items() if w[k].size > 8}        # value.bn / policy.bn: 2 / 4 numbers, covered by the update check
+    bad = {k: v for k, v in big.items() if v[0] > NOISE_X * v[1] + NOISE_ABS or v[3] < FP32_COS or v[2] > PAIR_X * max(v[0], v[1]) + NOISE_ABS}
+    assert not bad, bad
+    # the SGD(momentum, nesterov) + l2 update and the BN moving statistics (moving*0.99 + batch*0.01)
+    # (checked against the update the oracle's optimizer makes from the DEVICE's gradients: the optimizer itself is exact fp32)
+    own_w, _ = ref_train.sgd_step(w, g, None, {k: (new_w[k][2], new_w[k][3]) for k in w if k.endswith(("bn", "bn1", "bn2"))}, lr)
+    for k in w:
+        if k.endswith(("bn", "bn1", "bn2")):
+            assert np.allclose(new_w[k][:2], own_w[k][:2], rtol=1e-5, atol=1e-6), k
+            assert np.allclose(new_w[k][2:], ref_new_w[k][2:], rtol=2e-3, atol=2e-4), k      # moving statistics vs the oracle's batch statistics
+        else:
+            assert np.allclose(new_w[k], own_w[k], rtol=1e-5, atol=1e-6), k
+
+
+def test_training_reduces_the_loss_and_weights_serve_the_search():
+    """a few steps on one batch lower the loss; the trained weights load into the inference path (DeviceNetwork)."""
+    from chessbot_b200.model import DeviceNetwork
+    from chessbot_b200.train import Trainer
+    from oracle import ref_model
+    filters, blocks, n = 64, 2, 32
+    w = ref_model.init_weights(filters, blocks, seed=3)
+    images, z, pi = _batch(n, seed=9)
+    tr = Trainer(w, filters, blocks, n)
+    first = tr.train_on_batch(images, z, pi, 0.02)
+    for _ in range(15):
+        last = tr.train_on_batch(images, z, pi, 0.02)
+    assert np.isfinite(last["loss"]) and last["loss"] < first["loss"] - 0.5 and last["policy"] < first["policy"], (first, last)
+    trained = tr.get_weights()
+    net = DeviceNetwork(trained, filters, blocks)
+    v_ref, p_ref = ref_model.forward(trained, images[:4], device="cuda")
+    out = net(images[:1].astype(np.float32))
+    assert abs(float(np.asarray(out["value_head"]).ravel()[0]) - float(v_ref[0])) < 5e-2
