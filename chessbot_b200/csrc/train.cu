@@ -113,29 +113,36 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const uint8_t* __restrict
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float* __restrict__ mean_rstd, float* __restrict__ moving, float eps, float slope,
                                                         float momentum) {
+    __shared__ float s_scale[8], s_shift[8];
     const int j = blockIdx.x, t = threadIdx.x, cpad = cj * 8;
     const int lo = (int)((long long)pairs * blockIdx.y / gridDim.y), hi = (int)((long long)pairs * (blockIdx.y + 1) / gridDim.y);
-    const double count = (double)n * 64.0;
-    float scale[8], shift[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        const int ch = j * 8 + e;
-        scale[e] = shift[e] = 0.f;
+    if (t < 8) {  // the chunk's 8 channels: statistics -> scale / shift once per block (double: sum of squares minus squared sum)
+        const int ch = j * 8 + t;
+        float sc = 0.f, sh = 0.f;
         if (ch < c) {
+            const double count = (double)n * 64.0;
             const double mean = stats[ch] / count;
             double var = stats[cpad + ch] / count - mean * mean;
             var = var > 0.0 ? var : 0.0;
             const double rstd = 1.0 / sqrt(var + (double)eps);
-            scale[e] = (float)((double)gamma[ch] * rstd);
-            shift[e] = (float)((double)beta[ch] - mean * (double)gamma[ch] * rstd);
-            if (blockIdx.y == 0 && t == e) {
+            sc = (float)((double)gamma[ch] * rstd);
+            sh = (float)((double)beta[ch] - mean * (double)gamma[ch] * rstd);
+            if (blockIdx.y == 0) {
                 mean_rstd[ch] = (float)mean;
                 mean_rstd[cpad + ch] = (float)rstd;
+                mean_rstd[2 * cpad + ch] = sc;  // the backward pass recomputes the sign of a skip-less layer's pre-activation from y
+                mean_rstd[3 * cpad + ch] = sh;
                 moving[ch] = moving[ch] * momentum + (float)mean * (1.f - momentum);
                 moving[c + ch] = moving[c + ch] * momentum + (float)var * (1.f - momentum);
             }
         }
+        s_scale[t] = sc;
+        s_shift[t] = sh;
     }
+    __syncthreads();
+    float scale[8], shift[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { scale[e] = s_scale[e]; shift[e] = s_shift[e]; }
     if (t >= ACT_CELLS || !cell_is_square(t)) return;
     const int bip = cell_board(t);
 #pragma unroll 4
@@ -163,9 +170,13 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const uint8_t* __res
     __shared__ float red[8 * 16];
     const int j = blockIdx.x, t = threadIdx.x, cpad = cj * 8;
     const int lo = (int)((long long)pairs * blockIdx.y / gridDim.y), hi = (int)((long long)pairs * (blockIdx.y + 1) / gridDim.y);
-    float mean[8], rstd[8], acc[16];
+    float mean[8], rstd[8], sc[8], sh[8], acc[16];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { mean[e] = mean_rstd[j * 8 + e]; rstd[e] = mean_rstd[cpad + j * 8 + e]; acc[e] = acc[8 + e] = 0.f; }
+    for (int e = 0; e < 8; ++e) {
+        mean[e] = mean_rstd[j * 8 + e]; rstd[e] = mean_rstd[cpad + j * 8 + e];
+        sc[e] = mean_rstd[2 * cpad + j * 8 + e]; sh[e] = mean_rstd[3 * cpad + j * 8 + e];
+        acc[e] = acc[8 + e] = 0.f;
+    }
     if (t < ACT_CELLS && cell_is_square(t)) {
         const int bip = cell_board(t);
 #pragma unroll 2
@@ -174,8 +185,12 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const uint8_t* __res
             const size_t off = cell_off(p, cj, j, t);
             float gv[8], av[8], yv[8];
             unpack8(__ldg(reinterpret_cast<const uint4*>(g + off)), gv);
-            unpack8(__ldg(reinterpret_cast<const uint4*>(a + off)), av);
             unpack8(__ldg(reinterpret_cast<const uint4*>(y + off)), yv);
+            if (a) unpack8(__ldg(reinterpret_cast<const uint4*>(a + off)), av);
+            else {  // no residual add: the activation's sign is the sign of scale * y + shift, as the forward pass computed it
+#pragma unroll
+                for (int e = 0; e < 8; ++e) av[e] = fmaf(yv[e], sc[e], sh[e]);
+            }
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 const float dz = av[e] > 0.f ? gv[e] : gv[e] * slope;
@@ -198,12 +213,14 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint8_t* __rest
     const int j = blockIdx.x, t = threadIdx.x, cpad = cj * 8;
     const int lo = (int)((long long)pairs * blockIdx.y / gridDim.y), hi = (int)((long long)pairs * (blockIdx.y + 1) / gridDim.y);
     const double inv_count = 1.0 / ((double)n * 64.0);
-    float mean[8], rstd[8], k0[8], m1[8], m2[8];
+    float mean[8], rstd[8], sc[8], sh[8], k0[8], m1[8], m2[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         const int ch = j * 8 + e;
         mean[e] = mean_rstd[ch];
         rstd[e] = mean_rstd[cpad + ch];
+        sc[e] = mean_rstd[2 * cpad + ch];
+        sh[e] = mean_rstd[3 * cpad + ch];
         const bool real = ch < c;
         k0[e] = real ? gamma[ch] * rstd[e] : 0.f;
         m1[e] = (float)(sums[ch] * inv_count);
@@ -218,8 +235,12 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint8_t* __rest
         const size_t off = cell_off(p, cj, j, t);
         float gv[8], av[8], yv[8], o[8];
         unpack8(__ldg(reinterpret_cast<const uint4*>(g + off)), gv);
-        unpack8(__ldg(reinterpret_cast<const uint4*>(a + off)), av);
         unpack8(__ldg(reinterpret_cast<const uint4*>(y + off)), yv);
+        if (a) unpack8(__ldg(reinterpret_cast<const uint4*>(a + off)), av);
+        else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) av[e] = fmaf(yv[e], sc[e], sh[e]);
+        }
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const float dz = av[e] > 0.f ? gv[e] : gv[e] * slope;
@@ -341,47 +362,77 @@ __global__ void __launch_bounds__(256) head_features_train_kernel(const float* _
 }
 
 // C[m][n] = sum_k opA(A)[m][k] * opB(B)[k][n], row-major f32; ta: A is stored [k][m]; tb: B is stored [n][k].  The dense layers
-// of the heads (Dense 128 -> 4672, 64 -> C and their gradients): 0.1 % of the step's FLOPs, plain CUDA-core tiles of 64 x 64.
-__global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int M, int N, int K,
-                                                     int ta, int tb) {
-    __shared__ float As[16][65], Bs[16][65];
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
-    float acc[4][4];
+// of the heads (Dense 128 -> 4672, 64 -> C) and their gradients: plain GEMMs, 0.1 % of the step's FLOPs, on the legacy
+// mma.sync path with TF32 inputs (10-bit mantissa, f32 accumulate): 128 x 128 x 16 tiles, 8 warps of 64 x 32.
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+template <int BM, int BN>  // 128 x 128 for the big products, 64 x 64 where the output is small and the reduction long (more CTAs)
+__global__ void __launch_bounds__(256) gemm_tf32_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int M, int N, int K,
+                                                         int ta, int tb) {
+    constexpr int BK = 16, LD = BK + 4;  // row stride 20 words: the 8 x 4 fragment reads hit 32 different banks
+    constexpr int MI = BM / 32, NJ = BN / 32;  // 16 x 8 MMA tiles per warp (warps 2 x 4)
+    __shared__ uint32_t As[BM][LD], Bs[BN][LD];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wm = (warp >> 2) * (BM / 2), wn = (warp & 3) * (BN / 4);
+    const int g = lane >> 2, t4 = lane & 3;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    float acc[MI][NJ][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < MI; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int k0 = 0; k0 < K; k0 += 16) {
-        for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+        for (int j = 0; j < NJ; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
+    for (int k0 = 0; k0 < K; k0 += BK) {
+        for (int i = threadIdx.x; i < BM * BK; i += 256) {
             int mm, kk;
-            if (ta) { mm = i & 63; kk = i >> 6; } else { kk = i & 15; mm = i >> 4; }
+            if (ta) { mm = i % BM; kk = i / BM; } else { kk = i & (BK - 1); mm = i >> 4; }
             const int gm = m0 + mm, gk = k0 + kk;
-            As[kk][mm] = (gm < M && gk < K) ? (ta ? A[(size_t)gk * M + gm] : A[(size_t)gm * K + gk]) : 0.f;
+            As[mm][kk] = to_tf32((gm < M && gk < K) ? (ta ? A[(size_t)gk * M + gm] : A[(size_t)gm * K + gk]) : 0.f);
+        }
+        for (int i = threadIdx.x; i < BN * BK; i += 256) {
             int nn, kb;
-            if (tb) { kb = i & 15; nn = i >> 4; } else { nn = i & 63; kb = i >> 6; }
+            if (tb) { kb = i & (BK - 1); nn = i >> 4; } else { nn = i % BN; kb = i / BN; }
             const int gn = n0 + nn, gkb = k0 + kb;
-            Bs[kb][nn] = (gn < N && gkb < K) ? (tb ? B[(size_t)gn * K + gkb] : B[(size_t)gkb * N + gn]) : 0.f;
+            Bs[nn][kb] = to_tf32((gn < N && gkb < K) ? (tb ? B[(size_t)gn * K + gkb] : B[(size_t)gkb * N + gn]) : 0.f);
         }
         __syncthreads();
 #pragma unroll
-        for (int kk = 0; kk < 16; ++kk) {
-            float a[4], b[4];
+        for (int ks = 0; ks < BK; ks += 8) {
+            uint32_t af[MI][4], bf[NJ][2];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { a[i] = As[kk][ty * 4 + i]; b[i] = Bs[kk][tx * 4 + i]; }
+            for (int i = 0; i < MI; ++i) {
+                const int r = wm + i * 16 + g;
+                af[i][0] = As[r][ks + t4]; af[i][1] = As[r + 8][ks + t4]; af[i][2] = As[r][ks + t4 + 4]; af[i][3] = As[r + 8][ks + t4 + 4];
+            }
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < NJ; ++j) {
+                const int cc = wn + j * 8 + g;
+                bf[j][0] = Bs[cc][ks + t4]; bf[j][1] = Bs[cc][ks + t4 + 4];
+            }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NJ; ++j)
+                    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                                 : "+f"(acc[i][j][0]), "+f"(acc[i][j][1]), "+f"(acc[i][j][2]), "+f"(acc[i][j][3])
+                                 : "r"(af[i][0]), "r"(af[i][1]), "r"(af[i][2]), "r"(af[i][3]), "r"(bf[j][0]), "r"(bf[j][1]));
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < MI; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int gm = m0 + ty * 4 + i, gn = n0 + tx * 4 + j;
-            if (gm < M && gn < N) C[(size_t)gm * N + gn] = acc[i][j];
+        for (int j = 0; j < NJ; ++j) {
+            const int r = m0 + wm + i * 16 + g, cc = n0 + wn + j * 8 + 2 * t4;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int gm = r + (e >> 1) * 8, gn = cc + (e & 1);
+                if (gm < M && gn < N) C[(size_t)gm * N + gn] = acc[i][j][e];
+            }
         }
 }
 
@@ -648,7 +699,10 @@ int launch_head_features_train(const float* head_raw, int n, const double* stats
     CB_LAUNCH_OK();
 }
 int launch_sgemm(const float* A, const float* B, float* C, int M, int N, int K, int ta, int tb, cudaStream_t st) {
-    sgemm_kernel<<<dim3((N + 63) / 64, (M + 63) / 64), 256, 0, st>>>(A, B, C, M, N, K, ta, tb);
+    if ((size_t)((N + 127) / 128) * ((M + 127) / 128) >= 148)
+        gemm_tf32_kernel<128, 128><<<dim3((N + 127) / 128, (M + 127) / 128), 256, 0, st>>>(A, B, C, M, N, K, ta, tb);
+    else
+        gemm_tf32_kernel<64, 64><<<dim3((N + 63) / 64, (M + 63) / 64), 256, 0, st>>>(A, B, C, M, N, K, ta, tb);
     CB_LAUNCH_OK();
 }
 int launch_softmax_ce(float* logits, const float* pi, int n, double* losses, cudaStream_t st) {

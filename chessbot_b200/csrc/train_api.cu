@@ -220,7 +220,7 @@ cb_trainer* cb_train_create(cb_ctx* ctx, int filters, int blocks, int batch, flo
     const size_t part_stem = (size_t)t->wg_splits_stem * 9 * 128 * N, part_res = (size_t)t->wg_splits_res * 9 * N * N;
     const size_t mb = batch;
     if (t->wg_partial.alloc(part_stem > part_res ? part_stem : part_res) || t->stats.alloc((size_t)nl * 2 * N) ||
-        t->mean_rstd.alloc((size_t)nl * 2 * N) || t->bsums.alloc((size_t)nl * 2 * N) || t->hstats.alloc(6) || t->hsums.alloc(6) || t->losses.alloc(4) ||
+        t->mean_rstd.alloc((size_t)nl * 4 * N) || t->bsums.alloc((size_t)nl * 2 * N) || t->hstats.alloc(6) || t->hsums.alloc(6) || t->losses.alloc(4) ||
         t->flags.alloc(2 * ((size_t)batch / 4 + 2)) || t->head_raw.alloc(mb * 192) || t->hmr.alloc(6) || t->vfeat.alloc(mb * 64) ||
         t->pfeat.alloc(mb * 128) || t->h1pre.alloc(mb * filters) || t->value.alloc(mb) || t->logits.alloc(mb * 4672) || t->dpfeat.alloc(mb * 128) ||
         t->dvfeat.alloc(mb * 64) || t->dh1pre.alloc(mb * filters) || t->dpre.alloc(mb))
@@ -331,7 +331,7 @@ int cb_train_forward_backward(cb_trainer* t, const int16_t* images_dev, const fl
         const __nv_bfloat16* skip = (l > 0 && (l & 1) == 0) ? t->A[l - 2].p : nullptr;
         double* stats = t->stats.p + (size_t)l * 2 * N;
         if (tp_begin(t, TP_BN_FWD, st) || launch_bn_stats(t->Y[l].p, t->pairs, cj, stats, st) ||
-            launch_bn_apply(t->Y[l].p, skip, t->A[l].p, n, cj, C, stats, P + L.bn[l].off, P + L.bn[l].off + C, t->mean_rstd.p + (size_t)l * 2 * N,
+            launch_bn_apply(t->Y[l].p, skip, t->A[l].p, n, cj, C, stats, P + L.bn[l].off, P + L.bn[l].off + C, t->mean_rstd.p + (size_t)l * 4 * N,
                             t->moving.p + L.mov[l].off, t->eps, t->slope, t->bn_momentum, st) ||
             tp_end(t, st))
             return -1;
@@ -360,10 +360,11 @@ int cb_train_forward_backward(cb_trainer* t, const int16_t* images_dev, const fl
     for (int l = nl - 1; l >= 0; --l) {
         const __nv_bfloat16* g = t->g[cur].p;
         double* sums = t->bsums.p + (size_t)l * 2 * N;
-        const float* mr = t->mean_rstd.p + (size_t)l * 2 * N;
+        const float* mr = t->mean_rstd.p + (size_t)l * 4 * N;
         __nv_bfloat16* dz = (l > 0 && (l & 1) == 0) ? t->dz.p : nullptr;  // second convolution of a block: its dz also flows down the skip
-        if (tp_begin(t, TP_BN_BWD, st) || launch_bn_bwd_reduce(g, t->A[l].p, t->Y[l].p, n, cj, mr, t->slope, sums, st) ||
-            launch_bn_bwd_apply(g, t->A[l].p, t->Y[l].p, t->dy.p, dz, n, cj, C, mr, P + L.bn[l].off, sums, t->slope, G + L.bn[l].off,
+        const __nv_bfloat16* act = dz ? t->A[l].p : nullptr;              // without a residual add the sign of the pre-activation follows from y
+        if (tp_begin(t, TP_BN_BWD, st) || launch_bn_bwd_reduce(g, act, t->Y[l].p, n, cj, mr, t->slope, sums, st) ||
+            launch_bn_bwd_apply(g, act, t->Y[l].p, t->dy.p, dz, n, cj, C, mr, P + L.bn[l].off, sums, t->slope, G + L.bn[l].off,
                                 G + L.bn[l].off + C, st) ||
             tp_end(t, st))
             return -1;

@@ -35,6 +35,30 @@ def scheduler(epoch, lr, config=None):
     return config.learning_rate[epoch] if epoch in config.learning_rate else lr
 
 
+def data_parallel_world():
+    """(rank, world) of the data-parallel job: one process per GPU under torch.distributed, else (0, 1)."""
+    d = torch.distributed
+    return (d.get_rank(), d.get_world_size()) if d.is_available() and d.is_initialized() else (0, 1)
+
+
+def shard_batch(n, rank=None, world=None):
+    """the contiguous slice of a global batch of n samples that rank `rank` trains on (remainder to the first ranks)"""
+    r, w = data_parallel_world()
+    rank, world = (r if rank is None else rank), (w if world is None else world)
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return slice(lo, lo + base + (1 if rank < extra else 0))
+
+
+def allreduce_gradients(flat):
+    """Sums the flat gradient buffer over the ranks in place (NCCL over NVLink on the GPUs; gloo in the CPU tests) and returns
+    the factor that turns the sum of per-rank mean gradients into the gradient of the global mean loss (equal shards)."""
+    _, world = data_parallel_world()
+    if world > 1:
+        torch.distributed.all_reduce(flat)
+    return 1.0 / world
+
+
 def tensor_shapes(filters, blocks):
     """name -> Keras-layout shape of every tensor of the model (cb_net_set_tensor / cb_train_set_tensor)."""
     c = filters
@@ -73,7 +97,7 @@ class Trainer:
         self.shapes = tensor_shapes(self.filters, self.blocks)
         self.set_weights(weights)
         self.steps = 0
-        self.world = torch.distributed.get_world_size() if torch.distributed.is_available() and torch.distributed.is_initialized() else 1
+        self.rank, self.world = data_parallel_world()
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -122,9 +146,8 @@ class Trainer:
     def apply(self, lr, momentum=None, nesterov=True, l2=None):
         momentum = self.config.momentum if momentum is None else momentum
         l2 = self.config.l2_reg if l2 is None else l2
-        if self.world > 1:
-            torch.distributed.all_reduce(self.grads)       # NCCL over NVLink: the only collective of the training step
-        check(lib.cb_train_apply(self._h, float(lr), float(momentum), int(nesterov), float(l2), 1.0 / self.world, _stream()), "train_apply")
+        scale = allreduce_gradients(self.grads)            # NCCL over NVLink: the only collective of the training step
+        check(lib.cb_train_apply(self._h, float(lr), float(momentum), int(nesterov), float(l2), scale, _stream()), "train_apply")
         self.steps += 1
 
     def losses(self):
