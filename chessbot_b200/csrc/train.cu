@@ -29,17 +29,16 @@ __device__ __forceinline__ uint4 pack8(const float (&x)[8]) {
     }
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
-// cell 0..199 of a chunk = (row + 1, board in pair, col + 1): squares are the cells off the zero border
-__device__ __forceinline__ bool cell_is_square(int cell) {
-    const int c = cell % 10, r = cell / 20;
-    return c >= 1 && c <= 8 && r >= 1 && r <= 8;
-}
-__device__ __forceinline__ int cell_board(int cell) { return (cell / 10) & 1; }
 __device__ __forceinline__ size_t cell_off(int pair, int cj, int j, int cell) { return ((size_t)(pair * cj + j) * ACT_CELLS + cell) * 16; }
 
-// sum `v[0..NV)` over the block (256 threads), result in thread `i` for value i (i < NV) as double
+// one thread per SQUARE of a board pair (128 threads): thread t -> row t / 16, board (t / 8) % 2, column t % 8; 8 consecutive
+// threads touch 128 contiguous bytes.  The border cells (zero, never written) are skipped.
+constexpr int SQ_THREADS = 128;
+__device__ __forceinline__ int square_cell(int t) { return ((t >> 4) + 1) * 20 + ((t >> 3) & 1) * 10 + (t & 7) + 1; }
+
+// sum `v[0..NV)` over the block, result in thread `i` for value i (i < NV) as double
 template <int NV>
-__device__ __forceinline__ double block_sum(float (&v)[NV], float* red /*[8][NV]*/) {
+__device__ __forceinline__ double block_sum(float (&v)[NV], float* red /*[warps][NV]*/) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
@@ -51,7 +50,7 @@ __device__ __forceinline__ double block_sum(float (&v)[NV], float* red /*[8][NV]
     __syncthreads();
     double s = 0.0;
     if (threadIdx.x < NV)
-        for (int w = 0; w < 8; ++w) s += (double)red[w * NV + threadIdx.x];
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += (double)red[w * NV + threadIdx.x];
     return s;
 }
 }  // namespace
@@ -86,18 +85,18 @@ __global__ void planes_from_images_kernel(const int16_t* __restrict__ img, int n
 
 // ------------------------------------------------------------------------------------------------ BatchNormalization, forward
 // grid (cj, splits): per-channel sum and sum of squares of the raw convolution over the batch (border cells are zero)
-__global__ void __launch_bounds__(256) bn_stats_kernel(const uint8_t* __restrict__ y, int pairs, int cj, double* __restrict__ stats) {
-    __shared__ float red[8 * 16];
-    const int j = blockIdx.x, t = threadIdx.x;
+__global__ void __launch_bounds__(SQ_THREADS) bn_stats_kernel(const uint8_t* __restrict__ y, int pairs, int cj, double* __restrict__ stats) {
+    __shared__ float red[4 * 16];
+    const int j = blockIdx.x, t = threadIdx.x, cell = square_cell(t);
     const int lo = (int)((long long)pairs * blockIdx.y / gridDim.y), hi = (int)((long long)pairs * (blockIdx.y + 1) / gridDim.y);
     float acc[16];
 #pragma unroll
     for (int e = 0; e < 16; ++e) acc[e] = 0.f;
-    if (t < ACT_CELLS) {
+    {
 #pragma unroll 4
         for (int p = lo; p < hi; ++p) {
             float x[8];
-            unpack8(__ldg(reinterpret_cast<const uint4*>(y + cell_off(p, cj, j, t))), x);
+            unpack8(__ldg(reinterpret_cast<const uint4*>(y + cell_off(p, cj, j, cell))), x);
 #pragma unroll
             for (int e = 0; e < 8; ++e) { acc[e] += x[e]; acc[8 + e] = fmaf(x[e], x[e], acc[8 + e]); }
         }
@@ -108,7 +107,7 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const uint8_t* __restrict
 
 // out = LeakyReLU(gamma * (y - mean) * rstd + beta (+ skip)); saves mean / rstd for the backward pass and updates the moving
 // statistics (Keras: moving = moving * momentum + batch * (1 - momentum), biased batch variance)
-__global__ void __launch_bounds__(256) bn_apply_kernel(const uint8_t* __restrict__ y, const uint8_t* __restrict__ skip, uint8_t* __restrict__ out,
+__global__ void __launch_bounds__(SQ_THREADS) bn_apply_kernel(const uint8_t* __restrict__ y, const uint8_t* __restrict__ skip, uint8_t* __restrict__ out,
                                                         int n, int pairs, int cj, int c, const double* __restrict__ stats,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float* __restrict__ mean_rstd, float* __restrict__ moving, float eps, float slope,
@@ -143,12 +142,11 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const uint8_t* __restrict
     float scale[8], shift[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) { scale[e] = s_scale[e]; shift[e] = s_shift[e]; }
-    if (t >= ACT_CELLS || !cell_is_square(t)) return;
-    const int bip = cell_board(t);
+    const int cell = square_cell(t), bip = (t >> 3) & 1;
 #pragma unroll 4
     for (int p = lo; p < hi; ++p) {
         if (2 * p + bip >= n) continue;  // phantom board of an odd batch stays zero
-        const size_t off = cell_off(p, cj, j, t);
+        const size_t off = cell_off(p, cj, j, cell);
         float x[8], s[8];
         unpack8(__ldg(reinterpret_cast<const uint4*>(y + off)), x);
         if (skip) unpack8(__ldg(reinterpret_cast<const uint4*>(skip + off)), s);
@@ -164,10 +162,10 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const uint8_t* __restrict
 
 // ------------------------------------------------------------------------------------------------ BatchNormalization, backward
 // dz = g * LeakyReLU'(a);  sums[ch] = sum dz, sums[cpad + ch] = sum dz * xhat   (xhat = (y - mean) * rstd)
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const uint8_t* __restrict__ g, const uint8_t* __restrict__ a, const uint8_t* __restrict__ y,
+__global__ void __launch_bounds__(SQ_THREADS) bn_bwd_reduce_kernel(const uint8_t* __restrict__ g, const uint8_t* __restrict__ a, const uint8_t* __restrict__ y,
                                                              int n, int pairs, int cj, const float* __restrict__ mean_rstd, float slope,
                                                              double* __restrict__ sums) {
-    __shared__ float red[8 * 16];
+    __shared__ float red[4 * 16];
     const int j = blockIdx.x, t = threadIdx.x, cpad = cj * 8;
     const int lo = (int)((long long)pairs * blockIdx.y / gridDim.y), hi = (int)((long long)pairs * (blockIdx.y + 1) / gridDim.y);
     float mean[8], rstd[8], sc[8], sh[8], acc[16];
@@ -177,12 +175,12 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const uint8_t* __res
         sc[e] = mean_rstd[2 * cpad + j * 8 + e]; sh[e] = mean_rstd[3 * cpad + j * 8 + e];
         acc[e] = acc[8 + e] = 0.f;
     }
-    if (t < ACT_CELLS && cell_is_square(t)) {
-        const int bip = cell_board(t);
+    {
+        const int cell = square_cell(t), bip = (t >> 3) & 1;
 #pragma unroll 2
         for (int p = lo; p < hi; ++p) {
             if (2 * p + bip >= n) continue;
-            const size_t off = cell_off(p, cj, j, t);
+            const size_t off = cell_off(p, cj, j, cell);
             float gv[8], av[8], yv[8];
             unpack8(__ldg(reinterpret_cast<const uint4*>(g + off)), gv);
             unpack8(__ldg(reinterpret_cast<const uint4*>(y + off)), yv);
@@ -205,7 +203,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const uint8_t* __res
 
 // dy = gamma * rstd * (dz - mean(dz) - xhat * mean(dz * xhat)); optionally also stores dz (the residual branch's gradient);
 // dgamma = sum dz * xhat, dbeta = sum dz
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint8_t* __restrict__ g, const uint8_t* __restrict__ a, const uint8_t* __restrict__ y,
+__global__ void __launch_bounds__(SQ_THREADS) bn_bwd_apply_kernel(const uint8_t* __restrict__ g, const uint8_t* __restrict__ a, const uint8_t* __restrict__ y,
                                                             uint8_t* __restrict__ dy, uint8_t* __restrict__ dz_out, int n, int pairs, int cj, int c,
                                                             const float* __restrict__ mean_rstd, const float* __restrict__ gamma,
                                                             const double* __restrict__ sums, float slope, float* __restrict__ dgamma,
@@ -227,12 +225,11 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint8_t* __rest
         m2[e] = (float)(sums[cpad + ch] * inv_count);
         if (real && blockIdx.y == 0 && t == e) { dgamma[ch] = (float)sums[cpad + ch]; dbeta[ch] = (float)sums[ch]; }
     }
-    if (t >= ACT_CELLS || !cell_is_square(t)) return;
-    const int bip = cell_board(t);
+    const int cell = square_cell(t), bip = (t >> 3) & 1;
 #pragma unroll 2
     for (int p = lo; p < hi; ++p) {
         if (2 * p + bip >= n) continue;
-        const size_t off = cell_off(p, cj, j, t);
+        const size_t off = cell_off(p, cj, j, cell);
         float gv[8], av[8], yv[8], o[8];
         unpack8(__ldg(reinterpret_cast<const uint4*>(g + off)), gv);
         unpack8(__ldg(reinterpret_cast<const uint4*>(y + off)), yv);
@@ -372,7 +369,7 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {
 template <int BM, int BN>  // 128 x 128 for the big products, 64 x 64 where the output is small and the reduction long (more CTAs)
 __global__ void __launch_bounds__(256) gemm_tf32_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int M, int N, int K,
                                                          int ta, int tb) {
-    constexpr int BK = 16, LD = BK + 4;  // row stride 20 words: the 8 x 4 fragment reads hit 32 different banks
+    constexpr int BK = 32, LD = BK + 4;  // row stride 36 words: the 8 x 4 fragment reads hit 32 different banks
     constexpr int MI = BM / 32, NJ = BN / 32;  // 16 x 8 MMA tiles per warp (warps 2 x 4)
     __shared__ uint32_t As[BM][LD], Bs[BN][LD];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -387,17 +384,34 @@ __global__ void __launch_bounds__(256) gemm_tf32_kernel(const float* __restrict_
 #pragma unroll
             for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
     for (int k0 = 0; k0 < K; k0 += BK) {
-        for (int i = threadIdx.x; i < BM * BK; i += 256) {
-            int mm, kk;
-            if (ta) { mm = i % BM; kk = i / BM; } else { kk = i & (BK - 1); mm = i >> 4; }
-            const int gm = m0 + mm, gk = k0 + kk;
-            As[mm][kk] = to_tf32((gm < M && gk < K) ? (ta ? A[(size_t)gk * M + gm] : A[(size_t)gm * K + gk]) : 0.f);
+        // global -> shared in float4 along the operand's contiguous dimension (all of them are multiples of 4 here)
+        for (int i = threadIdx.x; i < BM * BK / 4; i += 256) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ta) {  // A stored [k][m]
+                const int mm = (i % (BM / 4)) * 4, kk = i / (BM / 4);
+                const int gm = m0 + mm, gk = k0 + kk;
+                if (gm < M && gk < K) v = *reinterpret_cast<const float4*>(A + (size_t)gk * M + gm);
+                As[mm][kk] = to_tf32(v.x); As[mm + 1][kk] = to_tf32(v.y); As[mm + 2][kk] = to_tf32(v.z); As[mm + 3][kk] = to_tf32(v.w);
+            } else {   // A stored [m][k]
+                const int kk = (i % (BK / 4)) * 4, mm = i / (BK / 4);
+                const int gm = m0 + mm, gk = k0 + kk;
+                if (gm < M && gk < K) v = *reinterpret_cast<const float4*>(A + (size_t)gm * K + gk);
+                *reinterpret_cast<uint4*>(&As[mm][kk]) = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+            }
         }
-        for (int i = threadIdx.x; i < BN * BK; i += 256) {
-            int nn, kb;
-            if (tb) { kb = i & (BK - 1); nn = i >> 4; } else { nn = i % BN; kb = i / BN; }
-            const int gn = n0 + nn, gkb = k0 + kb;
-            Bs[nn][kb] = to_tf32((gn < N && gkb < K) ? (tb ? B[(size_t)gn * K + gkb] : B[(size_t)gkb * N + gn]) : 0.f);
+        for (int i = threadIdx.x; i < BN * BK / 4; i += 256) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (tb) {  // B stored [n][k]
+                const int kb = (i % (BK / 4)) * 4, nn = i / (BK / 4);
+                const int gn = n0 + nn, gk = k0 + kb;
+                if (gn < N && gk < K) v = *reinterpret_cast<const float4*>(B + (size_t)gn * K + gk);
+                *reinterpret_cast<uint4*>(&Bs[nn][kb]) = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+            } else {   // B stored [k][n]
+                const int nn = (i % (BN / 4)) * 4, kb = i / (BN / 4);
+                const int gn = n0 + nn, gk = k0 + kb;
+                if (gn < N && gk < K) v = *reinterpret_cast<const float4*>(B + (size_t)gk * N + gn);
+                Bs[nn][kb] = to_tf32(v.x); Bs[nn + 1][kb] = to_tf32(v.y); Bs[nn + 2][kb] = to_tf32(v.z); Bs[nn + 3][kb] = to_tf32(v.w);
+            }
         }
         __syncthreads();
 #pragma unroll
@@ -644,7 +658,7 @@ __global__ void fill_kernel(float* p, size_t n, float v) {
 
 // ------------------------------------------------------------------------------------------------ launchers
 static dim3 chunk_grid(int pairs, int cj) {
-    int splits = 1184 / cj;  // ~8 blocks per SM
+    int splits = 2368 / cj;  // ~16 blocks of 128 threads per SM
     if (splits > pairs) splits = pairs;
     if (splits < 1) splits = 1;
     return dim3(cj, splits);
@@ -660,26 +674,26 @@ int launch_planes_from_images(const int16_t* img, int n, __nv_bfloat16* planes, 
     CB_LAUNCH_OK();
 }
 int launch_bn_stats(const __nv_bfloat16* y, int pairs, int cj, double* stats, cudaStream_t st) {
-    bn_stats_kernel<<<chunk_grid(pairs, cj), 256, 0, st>>>((const uint8_t*)y, pairs, cj, stats);
+    bn_stats_kernel<<<chunk_grid(pairs, cj), SQ_THREADS, 0, st>>>((const uint8_t*)y, pairs, cj, stats);
     CB_LAUNCH_OK();
 }
 int launch_bn_apply(const __nv_bfloat16* y, const __nv_bfloat16* skip, __nv_bfloat16* out, int n, int cj, int c, const double* stats, const float* gamma,
                     const float* beta, float* mean_rstd, float* moving, float eps, float slope, float momentum, cudaStream_t st) {
     const int pairs = (n + 1) / 2;
-    bn_apply_kernel<<<chunk_grid(pairs, cj), 256, 0, st>>>((const uint8_t*)y, (const uint8_t*)skip, (uint8_t*)out, n, pairs, cj, c, stats, gamma, beta,
+    bn_apply_kernel<<<chunk_grid(pairs, cj), SQ_THREADS, 0, st>>>((const uint8_t*)y, (const uint8_t*)skip, (uint8_t*)out, n, pairs, cj, c, stats, gamma, beta,
                                                           mean_rstd, moving, eps, slope, momentum);
     CB_LAUNCH_OK();
 }
 int launch_bn_bwd_reduce(const __nv_bfloat16* g, const __nv_bfloat16* a, const __nv_bfloat16* y, int n, int cj, const float* mean_rstd, float slope,
                          double* sums, cudaStream_t st) {
     const int pairs = (n + 1) / 2;
-    bn_bwd_reduce_kernel<<<chunk_grid(pairs, cj), 256, 0, st>>>((const uint8_t*)g, (const uint8_t*)a, (const uint8_t*)y, n, pairs, cj, mean_rstd, slope, sums);
+    bn_bwd_reduce_kernel<<<chunk_grid(pairs, cj), SQ_THREADS, 0, st>>>((const uint8_t*)g, (const uint8_t*)a, (const uint8_t*)y, n, pairs, cj, mean_rstd, slope, sums);
     CB_LAUNCH_OK();
 }
 int launch_bn_bwd_apply(const __nv_bfloat16* g, const __nv_bfloat16* a, const __nv_bfloat16* y, __nv_bfloat16* dy, __nv_bfloat16* dz, int n, int cj, int c,
                         const float* mean_rstd, const float* gamma, const double* sums, float slope, float* dgamma, float* dbeta, cudaStream_t st) {
     const int pairs = (n + 1) / 2;
-    bn_bwd_apply_kernel<<<chunk_grid(pairs, cj), 256, 0, st>>>((const uint8_t*)g, (const uint8_t*)a, (const uint8_t*)y, (uint8_t*)dy, (uint8_t*)dz, n, pairs,
+    bn_bwd_apply_kernel<<<chunk_grid(pairs, cj), SQ_THREADS, 0, st>>>((const uint8_t*)g, (const uint8_t*)a, (const uint8_t*)y, (uint8_t*)dy, (uint8_t*)dz, n, pairs,
                                                               cj, c, mean_rstd, gamma, sums, slope, dgamma, dbeta);
     CB_LAUNCH_OK();
 }
@@ -699,6 +713,7 @@ int launch_head_features_train(const float* head_raw, int n, const double* stats
     CB_LAUNCH_OK();
 }
 int launch_sgemm(const float* A, const float* B, float* C, int M, int N, int K, int ta, int tb, cudaStream_t st) {
+    if (((ta ? M : K) & 3) || ((tb ? K : N) & 3)) { cb_set_error("gemm: contiguous dimensions must be multiples of 4 (filters % 4 == 0)"); return -1; }
     if ((size_t)((N + 127) / 128) * ((M + 127) / 128) >= 148)
         gemm_tf32_kernel<128, 128><<<dim3((N + 127) / 128, (M + 127) / 128), 256, 0, st>>>(A, B, C, M, N, K, ta, tb);
     else

@@ -159,8 +159,8 @@ cb_trainer* cb_train_create(cb_ctx* ctx, int filters, int blocks, int batch, flo
                             float* grads_dev, float* momentum_dev) {
     if (!ctx) { cb_set_error("cb_train_create: no context"); return nullptr; }
     const int N = (filters + 63) / 64 * 64;
-    if (filters < 1 || (N != 64 && N != 128 && N != 256) || blocks < 0 || batch < 1) {
-        cb_set_error("cb_train_create: filters must pad to 64, 128 or 256 channels (1..64, 65..128, 193..256), batch >= 1");
+    if (filters < 4 || (filters & 3) || (N != 64 && N != 128 && N != 256) || blocks < 0 || batch < 1) {
+        cb_set_error("cb_train_create: filters must be a multiple of 4 that pads to 64, 128 or 256 channels (4..64, 68..128, 196..256), batch >= 1");
         return nullptr;
     }
     cb_trainer* t = new cb_trainer(filters, blocks);

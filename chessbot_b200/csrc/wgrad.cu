@@ -208,7 +208,8 @@ int launch_wgrad(const WgradParams& p, cudaStream_t stream) {
 }
 
 int launch_wgrad_reduce(const float* partial, int splits, int ci_pad, int n, int cin, int c, int stem, float* out, cudaStream_t stream) {
-    wgrad_reduce_kernel<<<296, 256, 0, stream>>>(partial, splits, ci_pad, n, cin, c, stem, out);
+    const size_t total = (size_t)9 * cin * c;
+    wgrad_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(partial, splits, ci_pad, n, cin, c, stem, out);
     CB_CUDA_OK(cudaGetLastError());
     return 0;
 }
