@@ -34,6 +34,7 @@ _SIGS = {
     "cb_board_mirror": (i32, [vp]),
     "cb_board_perft": (u64, [vp, i32]),
     "cb_board_export_record": (i32, [vp, vp, i32]),
+    "cb_boards_export_records": (i32, [vp, i32, vp, i32, vp, vp]),
     "cb_uci_to_action": (i32, [C.c_char_p, i32]),
     "cb_move_to_action": (i32, [C.c_uint16, i32]),
     "cb_move_to_uci": (i32, [C.c_uint16, C.c_char_p]),

@@ -268,6 +268,23 @@ class Board:
         return f"Board({self.fen()!r})"
 
 
+def export_records(boards):
+    """Game records of many boards in one C call: (list of uint8 [k_i, 96] views, int32 legal-move counts)."""
+    n = len(boards)
+    handles = (C.c_void_p * n)(*[b._h for b in boards])
+    lens = np.empty(n, dtype=np.int32)
+    n_legal = np.empty(n, dtype=np.int32)
+    cap = 16 * n
+    while True:
+        buf = np.empty((cap, CB_POS_BYTES), dtype=np.uint8)
+        total = lib.cb_boards_export_records(handles, n, buf.ctypes.data, cap, lens.ctypes.data, n_legal.ctypes.data)
+        if total <= cap:
+            break
+        cap = total
+    ends = np.cumsum(lens)
+    return [buf[e - k:e] for e, k in zip(ends.tolist(), lens.tolist())], n_legal
+
+
 def _piece_type_at(board, sq):
     for pt in range(1, 7):
         if (board.pieces_mask(pt, True) | board.pieces_mask(pt, False)) >> sq & 1:

@@ -255,6 +255,24 @@ int cb_board_export_record(const cb_board* b, void* pos_out, int cap) {
     return n;
 }
 
+// The same for `n` boards in one call (roots of a batched search): records concatenated in pos_out, rec_len[i] positions
+// each, n_legal[i] = number of legal moves of board i (size of its root noise vector, mcts.py:158).  Returns the total
+// number of positions, or the required total if cap is too small (nothing is written past cap).
+int cb_boards_export_records(const cb_board* const* boards, int n, void* pos_out, int cap, int32_t* rec_len, int32_t* n_legal) {
+    int total = 0;
+    for (int i = 0; i < n; ++i) {
+        const int k = cb_board_export_record(boards[i], total < cap ? (Pos*)pos_out + total : nullptr, cap > total ? cap - total : 0);
+        rec_len[i] = k;
+        total += k;
+        if (n_legal) {
+            MoveList ml;
+            generate_legal(boards[i]->rec.back(), ml);
+            n_legal[i] = ml.n;
+        }
+    }
+    return total;
+}
+
 int cb_move_to_action(uint16_t move, int player_white) { return move_to_action(move, player_white ? WHITE : BLACK); }
 int cb_uci_to_action(const char* uci, int player_white) {
     Move m;

@@ -132,13 +132,18 @@ def search_batch(games, network, num_simulations=100, add_noise=True, CPUCT=None
     sims = [num_simulations] * n if np.isscalar(num_simulations) else list(num_simulations)
     noisy = [bool(add_noise)] * n if isinstance(add_noise, (bool, np.bool_)) else [bool(a) for a in add_noise]
     cpuct = [CPUCT] * n if (CPUCT is None or np.isscalar(CPUCT)) else list(CPUCT)
+    from .board import export_records
     boards = [as_device_board(g.board) for g in games]
+    records, n_legal = export_records(boards)
     if noise is None:
+        # one draw for all noisy roots: Generator.gamma fills sequentially, so the slices are the per-game draws of mcts.py:158
         rng = np.random.default_rng() if rng is None else rng
-        noise = [rng.gamma(ROOT_DIRICHLET_ALPHA, 1, len(b.legal_moves)) if z else None for b, z in zip(boards, noisy)]
+        counts = [int(k) if z else 0 for k, z in zip(n_legal, noisy)]
+        flat = rng.gamma(ROOT_DIRICHLET_ALPHA, 1, sum(counts))
+        ends = np.cumsum(counts)
+        noise = [flat[e - k:e] if z else None for e, k, z in zip(ends.tolist(), counts, noisy)]
     else:
         noise = [z if f else None for z, f in zip(noise, noisy)]
-    records = [b.export_record() for b in boards]
     max_len = games[0].config.max_game_length
     engine = network.engine if isinstance(network, (DeviceNetwork, SyntheticNetwork)) else Engine.get()
     max_sims = max(max(sims), 1)

@@ -53,6 +53,11 @@ uint64_t cb_board_perft(const cb_board* b, int depth);
 /* Game record for the device: the last `n` positions (oldest first), enough for T=8 frames and for
  * repetition counting back to the last irreversible move.  Returns n, or the required n if cap is too small. */
 int cb_board_export_record(const cb_board* b, void* pos_out /*[cap][CB_POS_BYTES]*/, int cap);
+/* the same for n boards at once (roots of a batched search): records concatenated, rec_len[n] positions each, n_legal[n] =
+ * legal moves of each board (length of its root noise, mcts.py:158; may be NULL).  Returns the total number of positions,
+ * or the total required if cap is too small. */
+int cb_boards_export_records(const cb_board* const* boards, int n, void* pos_out /*[cap][CB_POS_BYTES]*/, int cap,
+                             int32_t* rec_len, int32_t* n_legal);
 /* actionspace.uci_to_action (actionspace.py:116-180): index 0..4671, -1 where the reference returns None */
 int cb_uci_to_action(const char* uci, int player_white);
 int cb_move_to_action(uint16_t move, int player_white);

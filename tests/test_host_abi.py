@@ -183,3 +183,22 @@ def test_weight_checkpoint_roundtrip(tmp_path):
     assert (filters, blocks) == (48, 4) and sorted(w2) == sorted(w)
     assert all(np.array_equal(w[k], w2[k]) and w2[k].dtype == np.float32 for k in w)
     assert w["stem.w"].shape == (3, 3, 119, 48) and w["policy.fc"].shape == (128, 4672) and w["res0.bn1"].shape == (4, 48)
+
+
+def test_batched_record_export_equals_per_board_export():
+    """cb_boards_export_records (roots of a batched search in one call) == cb_board_export_record per board + legal-move counts"""
+    import random
+    from chessbot_b200.board import Board, export_records
+    rnd = random.Random(4)
+    boards = []
+    for _ in range(40):
+        b = Board()
+        for _ in range(rnd.randint(0, 90)):
+            if b.is_game_over(claim_draw=True):
+                break
+            b.push(rnd.choice(list(b.legal_moves)))
+        boards.append(b)
+    boards.append(Board("8/8/8/4k3/8/8/4K3/7R w - - 12 40"))
+    recs, n_legal = export_records(boards)
+    for b, r, k in zip(boards, recs, n_legal):
+        assert np.array_equal(b.export_record(), r) and int(k) == len(b.legal_moves)
