@@ -139,7 +139,7 @@ def search_batch(games, network, num_simulations=100, add_noise=True, CPUCT=None
         # one draw for all noisy roots: Generator.gamma fills sequentially, so the slices are the per-game draws of mcts.py:158
         rng = np.random.default_rng() if rng is None else rng
         counts = [int(k) if z else 0 for k, z in zip(n_legal, noisy)]
-        flat = rng.gamma(ROOT_DIRICHLET_ALPHA, 1, sum(counts))
+        flat = rng.gamma(ROOT_DIRICHLET_ALPHA, 1, sum(counts)) if any(counts) else np.zeros(0)
         ends = np.cumsum(counts)
         noise = [flat[e - k:e] if z else None for e, k, z in zip(ends.tolist(), counts, noisy)]
     else:
