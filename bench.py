@@ -218,6 +218,8 @@ def run_reference_arm(args):
         return
     import multiprocessing as mp
     filters, blocks = parse_net(args.net)
+    if args.workload == "train":
+        return run_reference_train_arm(args, filters, blocks)
     P = min(os.cpu_count() or 1, 64)
     sims = 8
     pos = _oracle_positions(P, 321)
@@ -566,6 +568,36 @@ def run_train_arm(args):
             "gpu_launches": int(sum(v[1] for v in prof.values()) / prof_steps) * K, "clocks": clocks, "cpu_baseline": cpu}))
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_reference_train_arm(args, filters, blocks, batch=16):
+    """`--impl reference --workload train`: the reference's training step restated in torch fp32 (oracle/ref_train.py) on all host
+    cores (torch intra-op threads), each step one bounded batch of `batch` samples."""
+    import torch
+    from oracle import ref_model, ref_train
+    torch.set_num_threads(os.cpu_count() or 1)
+    w = ref_model.init_weights(filters, blocks, seed=0)
+    rng = np.random.default_rng(5)
+    images = rng.integers(0, 2, (batch, 8, 8, 119)).astype(np.int16)
+    z, pi = ref_train.synthetic_targets(batch, 5)
+    vel = None
+    for _ in range(max(args.warmup, 1)):
+        _, w, vel, _ = ref_train.train_step(w, vel, images, z, pi, 0.01)
+    steps = min(args.steps, 40)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        _, w, vel, _ = ref_train.train_step(w, vel, images, z, pi, 0.01)
+    dt = time.perf_counter() - t0
+    value = steps * batch / dt
+    unit = "samples/s"
+    sample = f"{steps} steps of batch {batch}, {blocks}x{filters} torch-fp32 autograd, {torch.get_num_threads()} threads (TensorFlow/Keras replaced by the oracle)"
+    emit(json.dumps({
+        "impl": "reference", "metric": "training samples/s (train.py step: forward + backward + gradient all-reduce + SGD update)", "value": value,
+        "unit": unit, "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"train.py step, {blocks}x{filters} net (reference CPU path, batch {batch})", "net": args.net},
+        "cpu_baseline": {"value": value, "unit": unit, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
 def train_cpu_baseline_leg(filters, blocks, budget_s=15.0, batch=16):
