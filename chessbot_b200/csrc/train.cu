@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(SQ_THREADS) bn_apply_kernel(const uint8_t* __r
 
 // ------------------------------------------------------------------------------------------------ BatchNormalization, backward
 // dz = g * LeakyReLU'(a);  sums[ch] = sum dz, sums[cpad + ch] = sum dz * xhat   (xhat = (y - mean) * rstd)
-__global__ void __launch_bounds__(SQ_THREADS) bn_bwd_reduce_kernel(const uint8_t* __restrict__ g, const uint8_t* __restrict__ a, const uint8_t* __restrict__ y,
+__global__ void __launch_bounds__(SQ_THREADS, 8) bn_bwd_reduce_kernel(const uint8_t* __restrict__ g, const uint8_t* __restrict__ a, const uint8_t* __restrict__ y,
                                                              int n, int pairs, int cj, const float* __restrict__ mean_rstd, float slope,
                                                              double* __restrict__ sums) {
     __shared__ float red[4 * 16];
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(SQ_THREADS) bn_bwd_reduce_kernel(const uint8_t
 
 // dy = gamma * rstd * (dz - mean(dz) - xhat * mean(dz * xhat)); optionally also stores dz (the residual branch's gradient);
 // dgamma = sum dz * xhat, dbeta = sum dz
-__global__ void __launch_bounds__(SQ_THREADS) bn_bwd_apply_kernel(const uint8_t* __restrict__ g, const uint8_t* __restrict__ a, const uint8_t* __restrict__ y,
+__global__ void __launch_bounds__(SQ_THREADS, 8) bn_bwd_apply_kernel(const uint8_t* __restrict__ g, const uint8_t* __restrict__ a, const uint8_t* __restrict__ y,
                                                             uint8_t* __restrict__ dy, uint8_t* __restrict__ dz_out, int n, int pairs, int cj, int c,
                                                             const float* __restrict__ mean_rstd, const float* __restrict__ gamma,
                                                             const double* __restrict__ sums, float slope, float* __restrict__ dgamma,
