@@ -107,3 +107,19 @@ class Bot:
 
     def get_move(self, board):
         return self.get_moves([board])[0]
+
+
+def solve_puzzles(puzzles, bot, max_rounds=64):
+    """puzzles.PuzzleSet.solve / eval_trt.solve_puzzles (puzzles.py:83-86,195-215; eval_trt.py:41-52) for many puzzles at once:
+    every round, the current positions of all puzzles still IN_PROGRESS are searched as ONE device batch (`bot.get_moves`) and
+    each answer is played with the puzzle's own `move_uci` (which also plays the opponent's scripted reply).  `puzzles` are
+    the reference's `Puzzle` objects, unmodified (anything with `.board`, `.status`, `.move_uci(uci)`); the result per puzzle is
+    what `puzzle.solve(bot)` leaves behind.  Returns the number of search rounds."""
+    rounds = 0
+    live = [p for p in puzzles if p.status == "IN_PROGRESS"]
+    while live and rounds < max_rounds:
+        for p, move in zip(live, bot.get_moves([p.board for p in live])):
+            p.move_uci(move)
+        live = [p for p in live if p.status == "IN_PROGRESS"]
+        rounds += 1
+    return rounds

@@ -276,6 +276,37 @@ def test_puzzle_bot_matches_oracle_search():
         assert mv == omove
 
 
+def test_batched_puzzle_solving_equals_puzzle_by_puzzle():
+    """selfplay.solve_puzzles (all live puzzles = one device batch per round) leaves every puzzle exactly where the reference's
+    own loop `puzzle.solve(bot)` (puzzles.py:83-86) leaves it."""
+    from test_puzzles_host import _Puzzle
+    from chessbot_b200 import selfplay
+    from chessbot_b200.model import SyntheticNetwork
+    from gpu_util import random_games
+    specs = []
+    for f, m in random_games(12, seed=77, min_plies=9, max_plies=40):
+        mv = m.split()
+        specs.append((f, " ".join(mv[-5:]), mv[:-5]))          # the last 5 plies are the "solution": opponent, bot, opponent, bot, opponent...
+
+    def make():
+        out = []
+        for f, sol, prefix in specs:
+            from chessbot_b200.board import Board
+            b = Board(str(f))
+            for u in prefix:
+                b.push_uci(u)
+            out.append(_Puzzle(b.fen(), sol))
+        return out
+    bot = selfplay.Bot(SyntheticNetwork(seed=5), num_simulations=24)
+    batched, single = make(), make()
+    selfplay.solve_puzzles(batched, bot)
+    for p in single:
+        while p.status == "IN_PROGRESS":
+            p.move_uci(bot.get_move(p.board))
+    assert [p.played for p in batched] == [p.played for p in single]
+    assert [p.status for p in batched] == [p.status for p in single]
+
+
 def test_config4_top_move_agreement_with_fp32_reference_path():
     """BASELINE config 4 at test scale (puzzle-style sweep: top-move agreement vs the reference).  Here the two
     sides use their OWN networks — device: tcgen05 bf16 tower, reference path: torch-fp32 — so logits differ by
