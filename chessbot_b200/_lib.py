@@ -65,7 +65,7 @@ _SIGS = {
     "cb_train_param_count": (C.c_size_t, [i32, i32, C.POINTER(C.c_size_t)]),
     "cb_train_create": (vp, [vp, i32, i32, i32, C.c_float, C.c_float, C.c_float, vp, vp, vp]),
     "cb_train_destroy": (None, [vp]),
-    "cb_train_set_tensor": (i32, [vp, C.c_char_p, vp, C.c_size_t, vp]),
+    "cb_train_set_tensor": (i32, [vp, C.c_char_p, i32, vp, C.c_size_t, vp]),
     "cb_train_get_tensor": (i32, [vp, C.c_char_p, i32, vp, C.c_size_t, vp]),
     "cb_train_forward_backward": (i32, [vp, vp, vp, vp, i32, vp]),
     "cb_train_apply": (i32, [vp, C.c_float, C.c_float, i32, C.c_float, C.c_float, vp]),

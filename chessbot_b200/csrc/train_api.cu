@@ -278,16 +278,18 @@ static int find_tensor(cb_trainer* t, const std::string& name, Span* par, Span* 
     return 0;
 }
 
-int cb_train_set_tensor(cb_trainer* t, const char* name, const float* host, size_t count, void* stream) {
+// what = 0: parameter (BN: gamma, beta, moving mean, moving variance), 2: momentum of the optimizer (BN: rows 2, 3 ignored)
+int cb_train_set_tensor(cb_trainer* t, const char* name, int what, const float* host, size_t count, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     Span par, mov;
     int bn_c;
+    if (what != 0 && what != 2) { cb_set_error("cb_train_set_tensor: what must be 0 (parameter) or 2 (momentum)"); return -1; }
     if (find_tensor(t, name, &par, &mov, &bn_c)) { cb_set_error(std::string("unknown tensor: ") + name); return -1; }
     if (count != (bn_c ? (size_t)4 * bn_c : par.count)) { cb_set_error(std::string("tensor has wrong size: ") + name); return -1; }
-    CB_CUDA_OK(cudaMemcpyAsync(t->params + par.off, host, par.count * 4, cudaMemcpyHostToDevice, st));
-    if (bn_c) CB_CUDA_OK(cudaMemcpyAsync(t->moving.p + mov.off, host + 2 * bn_c, mov.count * 4, cudaMemcpyHostToDevice, st));
+    CB_CUDA_OK(cudaMemcpyAsync((what == 0 ? t->params : t->mom) + par.off, host, par.count * 4, cudaMemcpyHostToDevice, st));
+    if (bn_c && what == 0) CB_CUDA_OK(cudaMemcpyAsync(t->moving.p + mov.off, host + 2 * bn_c, mov.count * 4, cudaMemcpyHostToDevice, st));
     CB_CUDA_OK(cudaStreamSynchronize(st));
-    t->weights_dirty = true;
+    if (what == 0) t->weights_dirty = true;
     return 0;
 }
 

@@ -105,12 +105,13 @@ class Trainer:
             lib.cb_train_destroy(h)
 
     # ------------------------------------------------------------------ weights
-    def set_weights(self, weights):
+    def set_weights(self, weights, what=0):
+        """what=0: the model's tensors; what=2: the optimizer's momentum (same names and layouts)"""
         for name, shape in self.shapes.items():
             a = np.ascontiguousarray(weights[name], dtype=np.float32)
             if a.size != int(np.prod(shape)):
                 raise ValueError(f"{name}: expected shape {shape}, got {a.shape}")
-            check(lib.cb_train_set_tensor(self._h, name.encode(), a.ctypes.data, a.size, _stream()), "train_set_tensor")
+            check(lib.cb_train_set_tensor(self._h, name.encode(), what, a.ctypes.data, a.size, _stream()), "train_set_tensor")
 
     def _get(self, what):
         out = {}
@@ -130,6 +131,20 @@ class Trainer:
 
     def get_velocity(self):
         return self._get(2)
+
+    def save(self, path):
+        """checkpoint for resuming (train.py:124-136 reloads the Keras model with its optimizer state): weights, momentum, step"""
+        w, v = self.get_weights(), self.get_velocity()
+        np.savez(path, __filters=self.filters, __blocks=self.blocks, __steps=self.steps,
+                 **{"w/" + k: a for k, a in w.items()}, **{"v/" + k: a for k, a in v.items()})
+
+    def load(self, path):
+        with np.load(path) as f:
+            if int(f["__filters"]) != self.filters or int(f["__blocks"]) != self.blocks:
+                raise ValueError("checkpoint is for another network shape")
+            self.set_weights({k[2:]: f[k] for k in f.files if k.startswith("w/")})
+            self.set_weights({k[2:]: f[k] for k in f.files if k.startswith("v/")}, what=2)
+            self.steps = int(f["__steps"])
 
     # ------------------------------------------------------------------ one step
     def forward_backward(self, images, z, pi):

@@ -143,8 +143,8 @@ size_t cb_train_param_count(int filters, int blocks, size_t* n_regularized);
 cb_trainer* cb_train_create(cb_ctx* ctx, int filters, int blocks, int batch, float leaky_slope, float bn_eps, float bn_momentum,
                             float* params_dev, float* grads_dev, float* momentum_dev);
 void cb_train_destroy(cb_trainer* t);
-int cb_train_set_tensor(cb_trainer* t, const char* name, const float* host, size_t count, void* stream);      /* synchronises */
-/* what: 0 = parameter (BN: gamma, beta, moving mean, moving variance), 1 = gradient, 2 = momentum; synchronises */
+/* what: 0 = parameter (BN: gamma, beta, moving mean, moving variance), 1 = gradient (get only), 2 = momentum; both synchronise */
+int cb_train_set_tensor(cb_trainer* t, const char* name, int what, const float* host, size_t count, void* stream);
 int cb_train_get_tensor(cb_trainer* t, const char* name, int what, float* host, size_t count, void* stream);
 int cb_train_forward_backward(cb_trainer* t, const int16_t* images_dev /*[n][8][8][119]*/, const float* z_dev /*[n]*/,
                               const float* pi_dev /*[n][4672]*/, int n, void* stream);

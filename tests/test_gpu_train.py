@@ -135,3 +135,33 @@ def test_training_reduces_the_loss_and_weights_serve_the_search():
     v_ref, p_ref = ref_model.forward(trained, images[:4], device="cuda")
     out = net(images[:1].astype(np.float32))
     assert abs(float(np.asarray(out["value_head"]).ravel()[0]) - float(v_ref[0])) < 5e-2
+
+
+def test_checkpoint_resume_and_error_paths(tmp_path):
+    """Trainer.save / load restore weights, optimizer momentum and step (train.py:124-136 resumes from its Keras checkpoint);
+    the C ABI rejects what it cannot train instead of falling back."""
+    from chessbot_b200._lib import lib
+    from chessbot_b200.train import Trainer
+    from oracle import ref_model
+    filters, blocks, n = 64, 1, 8
+    w = ref_model.init_weights(filters, blocks, seed=11)
+    images, z, pi = _batch(n, seed=11)
+    a = Trainer(w, filters, blocks, n)
+    a.train_on_batch(images, z, pi, 0.05)
+    a.train_on_batch(images, z, pi, 0.05)
+    path = str(tmp_path / "ckpt.npz")
+    a.save(path)
+    b = Trainer(ref_model.init_weights(filters, blocks, seed=12), filters, blocks, n)
+    b.load(path)
+    assert b.steps == 2
+    la, lb = a.train_on_batch(images, z, pi, 0.05), b.train_on_batch(images, z, pi, 0.05)
+    wa, wb = a.get_weights(), b.get_weights()
+    assert all(np.allclose(wa[k], wb[k], rtol=1e-4, atol=1e-6) for k in wa)
+    assert abs(la["loss"] - lb["loss"]) < 1e-5
+    with pytest.raises(RuntimeError):
+        a.forward_backward(images[:4], z[:4], pi[:4])                  # a trainer is built for one batch size
+    with pytest.raises(RuntimeError):
+        Trainer(ref_model.init_weights(50, 1, seed=1), 50, 1, 4)       # filters must be a multiple of 4
+    with pytest.raises(ValueError):
+        a.forward_backward(images[..., :100], z, pi)
+    assert lib.cb_train_set_tensor(a._h, b"nonsense.w", 0, None, 0, None) < 0
