@@ -74,6 +74,25 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 __device__ __forceinline__ void st_release_gpu(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
+// sum over the 32 lanes of a warp of 32 values per lane, transposed: afterwards lane c holds the total of value c in v[0].
+// Butterfly with halving payload: 16 + 8 + 4 + 2 + 1 = 31 shuffles instead of 32 x 5.
+__device__ __forceinline__ void warp_transpose_sum32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int k = 16; k >= 1; k >>= 1) {
+        const bool up = (lane & k) != 0;
+#pragma unroll
+        for (int i = 0; i < k; ++i) {
+            const float send = up ? v[i] : v[i + k];
+            const float recv = __shfl_xor_sync(0xffffffffu, send, k);
+            v[i] = (up ? v[i + k] : v[i]) + recv;
+        }
+    }
+}
+
+// STATS: the training forward pass (one layer per launch, identity epilogue, no residual add): the epilogue also accumulates the
+// per-channel sum and sum of squares of its bf16-rounded outputs (BatchNormalization's batch statistics), so the raw convolution
+// is not read again for them.
+template <bool STATS>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tower_tcgen05_kernel(const __grid_constant__ TowerParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     ConvSmem* s = reinterpret_cast<ConvSmem*>(smem);
@@ -95,7 +114,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
     const WorkRange w(cid, nclusters, units, nl);
     const int flag_base = p.epoch << 8;
 
-    if (p.head_w)
+    if (STATS)
+        for (int i = threadIdx.x; i < 512; i += CONV_THREADS) s_head[i] = 0.f;  // [2][256] running sums of this CTA (head weights are not used when training)
+    if (!STATS && p.head_w)
         for (int i = threadIdx.x; i < n; i += CONV_THREADS) {
             s_head[i] = p.head_w[i];
             s_head[256 + i] = p.head_w[n + i];
@@ -257,10 +278,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
         uint32_t j = 0;
         for (int l = 0; l < nl; ++l) {
             const LayerDesc L = p.layers[l];
-            const uint8_t* skip_buf = L.skip_buf >= 0 ? p.bufs[L.skip_buf] : nullptr;
+            const uint8_t* skip_buf = (!STATS && L.skip_buf >= 0) ? p.bufs[L.skip_buf] : nullptr;
             uint8_t* out_buf = p.bufs[L.out_buf];
-            const bool has_skip = skip_buf != nullptr;
-            const bool heads = p.head_w != nullptr && l == nl - 1;
+            const bool has_skip = !STATS && skip_buf != nullptr;
+            const bool heads = !STATS && p.head_w != nullptr && l == nl - 1;
             for (int k = 0; k < w.nu; ++k) {
                 const int u = w.unit(k);
                 if (!w.mine(u, l)) continue;
@@ -301,6 +322,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
                             const float4* sc4 = reinterpret_cast<const float4*>(L.scale + cb * 32);
                             const float4* sh4 = reinterpret_cast<const float4*>(L.shift + cb * 32);
                             ptx::tmem_wait_ld();
+                            float rsum[32], rsq[32];  // STATS only
 #pragma unroll
                             for (int jj = 0; jj < 4; ++jj) {
                                 float v[8];
@@ -333,6 +355,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
                                 o.z = *reinterpret_cast<uint32_t*>(&t2);
                                 o.w = *reinterpret_cast<uint32_t*>(&t3);
                                 *reinterpret_cast<uint4*>(out_buf + act_offset_bytes(pair, cjo, cb * 4 + jj, cell)) = o;
+                                if constexpr (STATS) {  // statistics of what was stored (bf16), as the BN pass will read it back
+                                    const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                                    for (int e = 0; e < 8; ++e) {
+                                        const float r = __uint_as_float((e & 1) ? (ow[e >> 1] & 0xFFFF0000u) : (ow[e >> 1] << 16));
+                                        rsum[jj * 8 + e] = r;
+                                        rsq[jj * 8 + e] = r * r;
+                                    }
+                                }
+                            }
+                            if constexpr (STATS) {
+                                warp_transpose_sum32(rsum, lane);
+                                warp_transpose_sum32(rsq, lane);
+                                atomicAdd(&s_head[cb * 32 + lane], rsum[0]);        // 4 lane quarters x item after item: little contention
+                                atomicAdd(&s_head[256 + cb * 32 + lane], rsq[0]);
                             }
                             if (has_skip && kk + 4 < nk) load_skip(sk[r], h + 2 * (kk + 4));
                         }
@@ -385,6 +422,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
     }
     ptx::tc_fence_before();
     __syncthreads();
+    if (STATS)  // this CTA's sums over all its items -> the layer's batch statistics
+        for (int i = threadIdx.x; i < 2 * n; i += CONV_THREADS) atomicAdd(p.stats + i, (double)s_head[(i >= n ? 256 - n : 0) + i]);
     ptx::cluster_sync();  // the peer may still be reading this CTA's shared memory / signalling its barriers
     if (warp == 1) ptx::tmem_dealloc2(tmem, 512);
 }
@@ -449,7 +488,8 @@ int conv_make_row_map(CUtensorMap* tm, const void* base, uint64_t rows, uint32_t
 int launch_tower(const TowerParams& p, int num_sms, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
-        CB_CUDA_OK(cudaFuncSetAttribute(tower_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV_SMEM_BYTES));
+        CB_CUDA_OK(cudaFuncSetAttribute(tower_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV_SMEM_BYTES));
+        CB_CUDA_OK(cudaFuncSetAttribute(tower_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV_SMEM_BYTES));
         attr_set = true;
     }
     if (p.n % 64 != 0 || p.n > 256 || p.n < 64 || p.nl < 1 || p.nl > 255 || p.pairs < 1) {
@@ -459,7 +499,12 @@ int launch_tower(const TowerParams& p, int num_sms, cudaStream_t stream) {
     const int units = (p.pairs + 1) / 2;
     const int max_clusters = num_sms / 2;
     const int clusters = units < max_clusters ? units : max_clusters;
-    tower_tcgen05_kernel<<<2 * clusters, CONV_THREADS, CONV_SMEM_BYTES, stream>>>(p);
+    if (p.stats) {
+        if (p.nl != 1 || p.head_w) { cb_set_error("tower: batch statistics are gathered one layer per launch, without heads"); return -1; }
+        tower_tcgen05_kernel<true><<<2 * clusters, CONV_THREADS, CONV_SMEM_BYTES, stream>>>(p);
+    } else {
+        tower_tcgen05_kernel<false><<<2 * clusters, CONV_THREADS, CONV_SMEM_BYTES, stream>>>(p);
+    }
     CB_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -42,6 +42,8 @@ struct TowerParams {
     uint8_t* bufs[4];           // raw pointers of the same four buffers (epilogue stores, skip reads)
     const float* head_w;        // [3][n] 1x1 head conv weights fused into the LAST layer, or nullptr
     float* head_out;            // [boards][64][3]
+    double* stats;              // training forward (one layer per launch, no skip): [2][n] per-channel sum / sum of squares of the
+                                // bf16-rounded outputs, accumulated on top of what is there; nullptr otherwise
     int* flags;                 // [2 * units] progress of every board pair: epoch * 256 + layers finished
     int epoch;                  // increases with every launch, so flags never need clearing
     int nl;                     // layers to run

@@ -8,6 +8,7 @@
 // residual branch's gradient as its "skip").  The raw convolution Y_l and the activation A_l of every layer stay in HBM for
 // the backward pass (2 x 41 x 210 MB at 20x256, batch 4096: 17 GB of the 180 GB).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -115,7 +116,8 @@ static int tp_end(cb_trainer* t, cudaStream_t st) {
 }
 
 // one layer of the tower kernel: raw convolution (identity epilogue), optionally + skip
-static int conv_layer(cb_trainer* t, int desc, const CUtensorMap& in_map, const void* in, void* out, const void* skip, cudaStream_t st) {
+static int conv_layer(cb_trainer* t, int desc, const CUtensorMap& in_map, const void* in, void* out, const void* skip, double* stats,
+                      cudaStream_t st) {
     if (++t->epoch >= (1 << 22)) {
         CB_CUDA_OK(cudaMemsetAsync(t->flags.p, 0, t->flags.n * sizeof(int), st));
         t->epoch = 1;
@@ -129,6 +131,7 @@ static int conv_layer(cb_trainer* t, int desc, const CUtensorMap& in_map, const 
     tp.layers = t->ldesc.p + desc;
     tp.head_w = nullptr;
     tp.head_out = nullptr;
+    tp.stats = stats;  // forward pass: the epilogue gathers the layer's batch statistics
     tp.flags = t->flags.p;
     tp.epoch = t->epoch;
     tp.nl = 1;
@@ -328,11 +331,14 @@ int cb_train_forward_backward(cb_trainer* t, const int16_t* images_dev, const fl
     // ---------------------------------------------------------------- forward tower
     for (int l = 0; l < nl; ++l) {
         const void* in = l == 0 ? (const void*)t->planes.p : (const void*)t->A[l - 1].p;
-        if (tp_begin(t, TP_CONV_FWD, st) || conv_layer(t, l, l == 0 ? t->map_planes : t->map_A[l - 1], in, t->Y[l].p, nullptr, st) || tp_end(t, st))
+        // CB_TRAIN_SEPARATE_STATS=1 (measurement only): batch statistics by a separate pass over Y instead of the conv epilogue
+        static const bool separate_stats = getenv("CB_TRAIN_SEPARATE_STATS") != nullptr;
+        double* stats = t->stats.p + (size_t)l * 2 * N;
+        if (tp_begin(t, TP_CONV_FWD, st) ||
+            conv_layer(t, l, l == 0 ? t->map_planes : t->map_A[l - 1], in, t->Y[l].p, nullptr, separate_stats ? nullptr : stats, st) || tp_end(t, st))
             return -1;
         const __nv_bfloat16* skip = (l > 0 && (l & 1) == 0) ? t->A[l - 2].p : nullptr;
-        double* stats = t->stats.p + (size_t)l * 2 * N;
-        if (tp_begin(t, TP_BN_FWD, st) || launch_bn_stats(t->Y[l].p, t->pairs, cj, stats, st) ||
+        if (tp_begin(t, TP_BN_FWD, st) || (separate_stats && launch_bn_stats(t->Y[l].p, t->pairs, cj, stats, st)) ||
             launch_bn_apply(t->Y[l].p, skip, t->A[l].p, n, cj, C, stats, P + L.bn[l].off, P + L.bn[l].off + C, t->mean_rstd.p + (size_t)l * 4 * N,
                             t->moving.p + L.mov[l].off, t->eps, t->slope, t->bn_momentum, st) ||
             tp_end(t, st))
@@ -382,7 +388,7 @@ int cb_train_forward_backward(cb_trainer* t, const int16_t* images_dev, const fl
             launch_wgrad_reduce(t->wg_partial.p, wp.splits, wp.cj_in * 8, N, l == 0 ? 119 : C, C, l == 0, G + L.w[l].off, st) || tp_end(t, st))
             return -1;
         if (l > 0) {
-            if (tp_begin(t, TP_DGRAD, st) || conv_layer(t, nl + l, t->map_dy_conv, t->dy.p, t->g[cur ^ 1].p, (l & 1) ? t->dz.p : nullptr, st) ||
+            if (tp_begin(t, TP_DGRAD, st) || conv_layer(t, nl + l, t->map_dy_conv, t->dy.p, t->g[cur ^ 1].p, (l & 1) ? t->dz.p : nullptr, nullptr, st) ||
                 tp_end(t, st))
                 return -1;
             cur ^= 1;

@@ -297,7 +297,7 @@ def test_batched_puzzle_solving_equals_puzzle_by_puzzle():
                 b.push_uci(u)
             out.append(_Puzzle(b.fen(), sol))
         return out
-    bot = selfplay.Bot(SyntheticNetwork(seed=5), num_simulations=24)
+    bot = selfplay.Bot(SyntheticNetwork(seed=5), num_simulations=24, rng=_Rng())      # ties among most-visited moves: first one
     batched, single = make(), make()
     selfplay.solve_puzzles(batched, bot)
     for p in single:
