@@ -154,10 +154,14 @@ def test_checkpoint_resume_and_error_paths(tmp_path):
     b = Trainer(ref_model.init_weights(filters, blocks, seed=12), filters, blocks, n)
     b.load(path)
     assert b.steps == 2
+    wa, wb, va, vb = a.get_weights(), b.get_weights(), a.get_velocity(), b.get_velocity()
+    assert all(np.array_equal(wa[k], wb[k]) for k in wa) and all(np.array_equal(va[k], vb[k]) for k in va)   # restored exactly
+    # the next step of both agrees to rounding (batch statistics are summed with atomics: order-dependent in the last bit, and
+    # one flipped bf16 rounding moves the whole gradient by its rounding noise, see the note above NOISE_X)
     la, lb = a.train_on_batch(images, z, pi, 0.05), b.train_on_batch(images, z, pi, 0.05)
+    assert abs(la["loss"] - lb["loss"]) < 5e-3
     wa, wb = a.get_weights(), b.get_weights()
-    assert all(np.allclose(wa[k], wb[k], rtol=1e-4, atol=1e-6) for k in wa)
-    assert abs(la["loss"] - lb["loss"]) < 1e-5
+    assert all(_rel(wa[k], wb[k]) < 2e-2 for k in wa)
     with pytest.raises(RuntimeError):
         a.forward_backward(images[:4], z[:4], pi[:4])                  # a trainer is built for one batch size
     with pytest.raises(RuntimeError):
