@@ -338,10 +338,13 @@ def run_gpu_arm(args):
     barrier()
     t0 = time.perf_counter()
     reps = 2
-    e2e_evals = 0
+    touched = 0
     for _ in range(reps):
         res = cb_mcts.run_mcts_batch(games, net, e2e_sims, 30, True, None, rng=np.random.default_rng(3))
-        e2e_evals += sum(1 + sum(c.N for c in root.children.values()) for _, root in res)   # upper bound: sims + root eval
+        # the caller's share of the work: play_game reads the root's children (visit distribution, train.py:13-19,43-47) on
+        # its full searches only, a quarter of the moves (config.num_mcts_sims_p); the other moves just take the move
+        for _, root in res[::4]:
+            touched += sum(c.N for c in root.children.values())
     torch.cuda.synchronize()
     e2e_dt = time.perf_counter() - t0
     e2e_evals_exact = eng.search_status()["evals"] * reps
@@ -384,7 +387,8 @@ def run_gpu_arm(args):
             "e2e": {"value": e2e_evals_exact / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": h2d / steps_per_search,
                     "d2h_bytes_per_step": d2h / steps_per_search,
                     "what": f"{reps} x mcts.run_mcts_batch({trees} games, {e2e_sims} sims): host game records -> H2D -> {steps_per_search} steps -> D2H root "
-                            f"statistics -> move choice; bytes are per search / {steps_per_search} steps"},
+                            "statistics -> move choice for every game, children read for every 4th (playout cap); "
+                            f"bytes are per search / {steps_per_search} steps"},
             "kernels": kernels,
             "gpu_launches": K * 4,   # encode, tower, heads, mcts_step
             "clocks": clocks,

@@ -51,49 +51,53 @@ def _uci(code):
     return u
 
 
-def _roots_from_device(out, n):
-    """Root Nodes with their children dicts (legal-move order) from the read-back root statistics of n trees.
-    The per-child values keep the reference's scalar types (np.float32 W / Q / P, np.float64 P at a noisy root).
-    All trees are unpacked with one masked gather per array, and the cyclic collector is paused while the ~30 nodes per
-    tree are created (it would rescan every live node of earlier searches otherwise)."""
-    import gc
-    k = np.asarray(out["n_children"][:n])
-    mask = np.arange(out["moves"].shape[1])[None, :] < k[:, None]
-    codes = out["moves"][:n][mask].tolist()
-    ns = out["N"][:n][mask].tolist()
-    ws, qs = list(out["W"][:n][mask]), list(out["Q"][:n][mask])
-    noisy = np.asarray(out["noisy"][:n], dtype=bool)
-    p_flat = out["P"][:n][mask]
-    if noisy.all():
-        ps = list(p_flat)
-    elif not noisy.any():
-        ps = list(p_flat.astype(np.float32))
-    else:
-        per_child = np.repeat(noisy, k)
-        ps = np.empty(len(codes), dtype=object)
-        ps[per_child] = list(p_flat[per_child])
-        ps[~per_child] = list(p_flat[~per_child].astype(np.float32))
-        ps = ps.tolist()
-    ucis = [_uci(c) for c in codes]
-    root_n = out["root_N"][:n].tolist()
-    roots, new, off = [], Node.__new__, 0
-    was_enabled = gc.isenabled()
-    gc.disable()
-    try:
-        for i, ki in enumerate(k.tolist()):
-            root = Node()
-            root.N = root_n[i]
-            children = root.children
-            for j in range(off, off + ki):
+class _DeviceRoot(Node):
+    """Root of a device search.  N is set at once; the children dict (legal-move order, one Node per child with the reference's
+    scalar types: np.float32 W / Q / P, np.float64 P at a noisy root) is built from the read-back arrays the first time
+    `children` is touched - a caller that only wants the move (puzzles, quick playout-cap searches) never pays for ~30 Python
+    objects per tree."""
+
+    def __init__(self, root_n, codes, ns, ws, qs, ps):
+        self.parent = None
+        self.N, self.W, self.P, self.Q = root_n, 0, 0, 0
+        self._stats = (codes, ns, ws, qs, ps)
+
+    @property
+    def children(self):
+        d = self.__dict__.get("_children")
+        if d is None:
+            codes, ns, ws, qs, ps = self._stats
+            d, new = {}, Node.__new__
+            for u, n_, w_, q_, p_ in zip(map(_uci, codes.tolist()), ns.tolist(), list(ws), list(qs), list(ps)):
                 c = new(Node)
-                c.parent, c.children, c.N, c.W, c.P, c.Q = root, {}, ns[j], ws[j], ps[j], qs[j]
-                children[ucis[j]] = c
-            off += ki
-            roots.append(root)
-    finally:
-        if was_enabled:
-            gc.enable()
-    return roots
+                c.parent, c.children, c.N, c.W, c.P, c.Q = self, {}, n_, w_, p_, q_
+                d[u] = c
+            self.__dict__["_children"] = d
+        return d
+
+    @children.setter
+    def children(self, value):
+        self.__dict__["_children"] = value
+
+
+def _roots_from_device(out, n):
+    """Root Nodes of n trees over views of the read-back root statistics (children built lazily, see _DeviceRoot)."""
+    k = out["n_children"][:n].tolist()
+    root_n = out["root_N"][:n].tolist()
+    moves, N, W, Q, P, noisy = out["moves"], out["N"], out["W"], out["Q"], out["P"], out["noisy"]
+    p32 = None if all(noisy[:n]) else P[:n].astype(np.float32)      # priors are float32 unless root noise made them float64
+    return [_DeviceRoot(root_n[i], moves[i, :k[i]], N[i, :k[i]], W[i, :k[i]], Q[i, :k[i]], P[i, :k[i]] if noisy[i] else p32[i, :k[i]])
+            for i in range(n)]
+
+
+def _select_move_from_counts(codes, counts, rng, temp):
+    """select_move (mcts.py:142-153) on a device root's arrays: the same NumPy / RNG calls, without building the children"""
+    visit_counts = counts.astype(np.int64)
+    if temp == 0:
+        return _uci(int(codes[rng.choice(np.flatnonzero(visit_counts == np.max(visit_counts)))]))
+    pi = visit_counts ** (1 / temp)
+    pi = pi / np.sum(pi)
+    return _uci(int(codes[np.where(rng.multinomial(1, pi) == 1)[0][0]]))
 
 
 def _external_search(engine, network, records, sims, cpuct, noise, max_len):
@@ -179,7 +183,8 @@ def run_mcts_batch(games, network, num_simulations=100, num_sampling_moves=30, a
     results = []
     for g, root in zip(games, roots):
         temp = TEMP if g.history_len < num_sampling_moves else 0
-        results.append((select_move(root, rng, temp), root))
+        codes, counts = root._stats[0], root._stats[1]
+        results.append((_select_move_from_counts(codes, counts, rng, temp), root))
     return results
 
 
