@@ -551,9 +551,14 @@ def run_train_arm(args):
         npad = (filters + 63) // 64 * 64
         act_mb = B / 2 * npad / 8 * 3200 / 1e6
         kernels = {k: {"launches": v[1], "ms_per_step": v[0] / prof_steps, "share_of_step": v[0] / tot} for k, v in prof.items() if v[1]}
-        for k, passes in (("bn_fwd", 3.5), ("bn_bwd", 8.5)):   # tensors streamed per layer: fwd stats r + apply r,(skip) w; bwd reduce 3r + apply 3r, 1-2 w
-            gbs = passes * act_mb * 1e6 * (1 + 2 * blocks) / (prof[k][0] / prof_steps * 1e-3) / 1e9
-            kernels[k].update({"bound": "hbm", "achieved_gbs": gbs, "peak_gbs": peak_gbs, "frac": gbs / peak_gbs})
+        # HBM-bound BN passes, ALGORITHMIC bytes: one tensor pass = batch x 64 squares x padded channels x 2 B (the zero border
+        # cells of the tile-native layout, +56 %, are not counted); passes per layer: forward = read Y, write A,
+        # + read skip on the `blocks` residual layers; backward = (G, Y) twice + write dY, + (A twice, write dz) on those layers
+        nl_ = 1 + 2 * blocks
+        pass_bytes = B * 64 * npad * 2
+        for k, passes in (("bn_fwd", 2 + blocks / nl_), ("bn_bwd", 5 + 3 * blocks / nl_)):
+            gbs = passes * pass_bytes * nl_ / (prof[k][0] / prof_steps * 1e-3) / 1e9
+            kernels[k].update({"bound": "hbm", "tensor_passes_per_layer": passes, "achieved_gbs": gbs, "peak_gbs": peak_gbs, "frac": gbs / peak_gbs})
         cpu = None if args.no_cpu_baseline else train_cpu_baseline_leg(filters, blocks)
         emit(json.dumps({
             "metric": "training samples/s (train.py step: forward + backward + gradient all-reduce + SGD update)", "value": world * B * K / (ms * 1e-3),
