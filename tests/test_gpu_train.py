@@ -169,3 +169,18 @@ def test_checkpoint_resume_and_error_paths(tmp_path):
     with pytest.raises(ValueError):
         a.forward_backward(images[..., :100], z, pi)
     assert lib.cb_train_set_tensor(a._h, b"nonsense.w", 0, None, 0, None) < 0
+
+
+def test_selfplay_to_training_cycle_runs_end_to_end():
+    """actors -> replay buffer -> trainer -> new network for the actors (train.py's cycle) on the device path, toy scale:
+    samples have the reference's format, losses are finite, and the trained weights differ from the initial ones."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("demo", os.path.join(os.path.dirname(__file__), "..", "scripts", "selfplay_train_demo.py"))
+    demo = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(demo)
+    lines = []
+    hist = demo.run(net="2x32", games=12, iters=2, batch=16, steps_per_iter=2, sims=(4, 8), max_game_length=20, log=lines.append)
+    assert len(hist) == 2 and hist[-1][0] >= 16, lines
+    logs = hist[-1][1]
+    assert logs is not None and all(np.isfinite(v) for v in logs.values()) and 5.0 < logs["policy"] < 9.5, logs
