@@ -73,6 +73,16 @@ class Engine:
             _engines[idx] = cls(idx)
         return _engines[idx]
 
+    @classmethod
+    def actor(cls, index, device=None):
+        """Device context number `index` of extra actors sharing this GPU (kept for the life of the process; index 0, 1, ...).
+        Every context owns its network copy, node pool and scratch, so actors on different CUDA streams do not interfere."""
+        idx = torch.cuda.current_device() if device is None else int(device)
+        key = (idx, "actor", int(index))
+        if key not in _engines:
+            _engines[key] = cls(idx)
+        return _engines[key]
+
     # ------------------------------------------------------------------ gameimage
     def upload_records(self, records):
         """records: list of uint8 [k_i, 96] game records (Board.export_record) -> (pos tensor, frame_idx [n,8])."""

@@ -51,11 +51,13 @@ def keras_init_weights(filters, blocks, in_channels=119, seed=None):
 class DeviceNetwork:
     """model.py:30-56 forward graph resident on one B200."""
 
-    def __init__(self, weights, filters, blocks, max_batch=1024, device=None):
+    def __init__(self, weights, filters, blocks, max_batch=1024, device=None, engine=None):
+        """engine: a device context of its own (engine.Engine(device)) instead of the per-GPU default one - one per actor
+        thread when several actors share a GPU (the reference runs num_actors processes per GPU, train.py:173,198-201)."""
         from .engine import Engine
         self.weights = {k: np.asarray(v, dtype=np.float32) for k, v in weights.items()}
         self.filters, self.blocks, self.max_batch = filters, blocks, max_batch
-        self.engine = Engine.get(device)
+        self.engine = Engine.get(device) if engine is None else engine
         self.load()
 
     def load(self):
