@@ -184,3 +184,42 @@ def test_selfplay_to_training_cycle_runs_end_to_end():
     assert len(hist) == 2 and hist[-1][0] >= 16, lines
     logs = hist[-1][1]
     assert logs is not None and all(np.isfinite(v) for v in logs.values()) and 5.0 < logs["policy"] < 9.5, logs
+
+
+def test_config5_full_size_step_against_fp32_oracle():
+    """BASELINE config 5 at full size: 20x256 net, batch 4096, one step against the torch-fp32 autograd oracle (on the GPU: it
+    needs seconds there).  41 layers of bf16 activations and gradients: the bar is the loss to LOSS_TOL and, per tensor, the
+    direction of the gradient (cosine) with no scale bias; plus exact size-independent properties of the device's own
+    gradients: the policy-logit gradient of every sample sums to zero, so every row of the policy Dense gradient sums to ~0."""
+    from chessbot_b200.train import Trainer
+    from oracle import ref_model, ref_train
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    filters, blocks, n = 256, 20, 4096
+    w = ref_model.init_weights(filters, blocks, seed=20)
+    images, z, pi = _batch(256, seed=5)
+    reps = n // 256
+    rng = np.random.default_rng(1)
+    images = np.concatenate([images[rng.permutation(256)] for _ in range(reps)])     # 4096 samples drawn from 256 real positions
+    z, pi = ref_train.synthetic_targets(n, 6)
+    tr = Trainer(w, filters, blocks, n)
+    tr.forward_backward(images, z, pi)
+    g = tr.get_gradients()
+    tr.apply(0.01)
+    losses = tr.losses()
+    ref_losses, ref_g, _, _, _ = ref_train.forward_backward(w, images, z, pi, device="cuda")
+    for k in ("value", "policy", "l2"):
+        assert abs(losses[k] - ref_losses[k]) <= LOSS_TOL * max(1.0, abs(ref_losses[k])), (k, losses, ref_losses)
+    rows = {}
+    for k in w:
+        a, b = (g[k][:2], ref_g[k][:2]) if k.endswith(("bn", "bn1", "bn2")) else (g[k], ref_g[k])
+        rows[k] = (round(_rel(a, b), 3), round(_cos(a, b), 4), round(_proj(a, b), 3))
+    worst = min(rows.items(), key=lambda kv: kv[1][1])
+    print(f"\nconfig 5 full size (20x256, batch 4096): losses {losses} (oracle {ref_losses}); worst gradient cosine {worst}; "
+          f"stem {rows['stem.w']}, res10.w1 {rows['res10.w1']}, res19.w2 {rows['res19.w2']}, policy.fc {rows['policy.fc']}")
+    big = {k: v for k, v in rows.items() if w[k].size > 8}
+    # measured: relative L2 error 2-5 %, cosine >= 0.9989, projection 0.998-1.003 (the large batch averages the rounding noise)
+    bad = {k: v for k, v in big.items() if v[0] > 0.10 or v[1] < 0.995 or abs(v[2] - 1) > 0.02}
+    assert not bad, bad
+    row_sums = np.abs(g["policy.fc"].sum(axis=1))
+    assert float(row_sums.max()) <= 1e-4 * float(np.abs(g["policy.fc"]).sum(axis=1).max()) + 1e-6
