@@ -87,7 +87,7 @@ struct Search {
     DevBuf<Node> nodes;
     DevBuf<Pos> pos;
     DevBuf<TreeState> trees;
-    DevBuf<int32_t> node_count, pos_count, frame_idx, counters, scratch_i32, path;
+    DevBuf<int32_t> node_count, pos_count, frame_idx, counters, scratch_i32, path, active_list, active_count;
     DevBuf<uint16_t> pend_moves;
     DevBuf<double> root_p64, noise, cpuct_tab, sqrt_tab;
     DevBuf<float> value, expvals;
@@ -331,7 +331,9 @@ static int next_epoch(Net& net, cudaStream_t st) {
 }
 
 // tower + head features; leaves pfeat/value for the callers below
-static int net_tower(cb_ctx* ctx, const void* planes_act_dev, int n, float* value_dev, cudaStream_t st) {
+// slot_list / n_dev (search loop): the batch holds *n_dev <= n boards, board b belongs to evaluation slot slot_list[b]
+static int net_tower(cb_ctx* ctx, const void* planes_act_dev, int n, float* value_dev, cudaStream_t st, const int32_t* slot_list = nullptr,
+                     const int* n_dev = nullptr) {
     Net& net = ctx->net;
     if (!net.ready) { cb_set_error("network not finalized"); return -1; }
     if (n > net.max_batch) { cb_set_error("batch larger than max_batch"); return -1; }
@@ -350,6 +352,7 @@ static int net_tower(cb_ctx* ctx, const void* planes_act_dev, int n, float* valu
     tp.layers = net.layer_desc.p;
     tp.head_w = net.head_w.p;
     tp.head_out = net.head_raw.p;
+    tp.n_boards_dev = n_dev;
     tp.flags = net.flags.p;
     tp.epoch = net.epoch;
     tp.nl = (int)net.layers.size();
@@ -357,7 +360,7 @@ static int net_tower(cb_ctx* ctx, const void* planes_act_dev, int n, float* valu
     tp.n = net.cpad;
     tp.slope = net.slope;
     if (prof_begin(ctx, CB_PROF_CONV, st) || launch_tower(tp, ctx->sms, st) || prof_end(ctx, st)) return -1;
-    HeadParams hp{net.head_raw.p, net.head_bn.p, net.fc1.p, net.fc2.p, net.filters, net.slope, value_dev, net.pfeat.p};
+    HeadParams hp{net.head_raw.p, net.head_bn.p, net.fc1.p, net.fc2.p, net.filters, net.slope, value_dev, net.pfeat.p, slot_list, n_dev};
     if (prof_begin(ctx, CB_PROF_HEADS, st) || launch_head_features(hp, n, st) || prof_end(ctx, st)) return -1;
     return 0;
 }
@@ -509,7 +512,7 @@ int cb_search_set_leaves(cb_ctx* ctx, int leaves) {
     if (s.max_trees <= 0) { cb_set_error("cb_search_create first"); return -1; }
     if (leaves == s.leaves) return 0;
     const size_t ns = (size_t)s.max_trees * leaves;
-    if (s.frame_idx.alloc(ns * 8) || s.path.alloc(ns * MCTS_MAX_PATH) || s.pend_moves.alloc(ns * MAX_MOVES) || s.value.alloc(ns) ||
+    if (s.active_list.alloc(ns) || s.active_count.alloc(1) || s.frame_idx.alloc(ns * 8) || s.path.alloc(ns * MCTS_MAX_PATH) || s.pend_moves.alloc(ns * MAX_MOVES) || s.value.alloc(ns) ||
         s.synth_hash.alloc(ns) || s.slots.alloc(ns) || s.planes_act.alloc(act_bytes((int)ns, 128) / 2) || s.planes_i16.alloc(ns * 7616))
         return -1;
     s.expvals.free_();
@@ -517,6 +520,7 @@ int cb_search_set_leaves(cb_ctx* ctx, int leaves) {
     SearchParams& sp = s.sp;
     sp.leaves = leaves; sp.slots = s.slots.p; sp.path = s.path.p; sp.pend_moves = s.pend_moves.p; sp.frame_idx = s.frame_idx.p;
     sp.value = s.value.p; sp.synth_hash = s.synth_hash.p; sp.expvals = nullptr;
+    sp.active_list = s.active_list.p; sp.active_count = s.active_count.p;
     return 0;
 }
 
@@ -557,6 +561,7 @@ int cb_search_begin(cb_ctx* ctx, int n_trees, const void* records_host, const in
     CB_CUDA_OK(cudaMemcpyAsync(s.node_count.p, &zero, 4, cudaMemcpyHostToDevice, st));
     CB_CUDA_OK(cudaMemcpyAsync(s.pos_count.p, &pc, 4, cudaMemcpyHostToDevice, st));
     CB_CUDA_OK(cudaMemsetAsync(s.counters.p, 0, 16, st));
+    CB_CUDA_OK(cudaMemsetAsync(s.active_count.p, 0, 4, st));
     if (noise) CB_CUDA_OK(cudaMemcpyAsync(s.noise.p, noise, (size_t)n_trees * MAX_MOVES * 8, cudaMemcpyHostToDevice, st));
     CB_CUDA_OK(cudaStreamSynchronize(st));  // host staging vectors go out of scope
     s.sp.n_trees = n_trees;
@@ -583,10 +588,13 @@ int cb_search_step(cb_ctx* ctx, void* stream) {
     Search& s = ctx->search;
     cudaStream_t st = (cudaStream_t)stream;
     if (s.eval_mode == CB_EVAL_NET) {
-        if (prof_begin(ctx, CB_PROF_ENCODE, st) || launch_encode(s.pos.p, s.frame_idx.p, s.n_trees * s.leaves, s.planes_act.p, nullptr, st) ||
+        // only the slots that hold a pending leaf are encoded and evaluated (compacted batch, size known on the device only)
+        if (prof_begin(ctx, CB_PROF_ENCODE, st) ||
+            launch_encode(s.pos.p, s.frame_idx.p, s.n_trees * s.leaves, s.planes_act.p, nullptr, st, s.active_list.p, s.active_count.p) ||
             prof_end(ctx, st) || debug_sync(st, "encode"))
             return -1;
-        if (net_tower(ctx, s.planes_act.p, s.n_trees * s.leaves, s.value.p, st) || debug_sync(st, "tower")) return -1;
+        if (net_tower(ctx, s.planes_act.p, s.n_trees * s.leaves, s.value.p, st, s.active_list.p, s.active_count.p) || debug_sync(st, "tower"))
+            return -1;
     } else if (s.eval_mode == CB_EVAL_SYNTH) {
         if (launch_encode(s.pos.p, s.frame_idx.p, s.n_trees * s.leaves, nullptr, s.planes_i16.p, st)) return -1;
         if (launch_synth(s.planes_i16.p, s.n_trees * s.leaves, s.seed, s.synth_hash.p, s.value.p, nullptr, st)) return -1;
@@ -594,6 +602,7 @@ int cb_search_step(cb_ctx* ctx, void* stream) {
         cb_set_error("cb_search_step: external evaluation uses cb_search_step_external");
         return -1;
     }
+    CB_CUDA_OK(cudaMemsetAsync(s.active_count.p, 0, 4, st));  // mcts_step claims the next step's batch
     if (prof_begin(ctx, CB_PROF_MCTS, st) || launch_mcts_step(s.sp, st) || prof_end(ctx, st)) return -1;
     return debug_sync(st, "mcts_step");
 }
@@ -621,6 +630,7 @@ int cb_search_step_external(cb_ctx* ctx, const float* value_host, const float* e
     }
     CB_CUDA_OK(cudaMemcpyAsync(s.value.p, value_host, (size_t)s.n_trees * 4, cudaMemcpyHostToDevice, st));
     CB_CUDA_OK(cudaMemcpyAsync(s.expvals.p, expvals_host, (size_t)s.n_trees * 4672 * 4, cudaMemcpyHostToDevice, st));
+    CB_CUDA_OK(cudaMemsetAsync(s.active_count.p, 0, 4, st));
     if (launch_mcts_step(s.sp, st)) return -1;
     CB_CUDA_OK(cudaStreamSynchronize(st));  // the host buffers may be reused by the caller
     return 0;

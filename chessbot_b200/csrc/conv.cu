@@ -104,7 +104,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = ptx::cluster_ctarank();
     const int cid = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
-    const int units = (p.pairs + 1) / 2;  // one unit = two board pairs = one M=256 accumulator stage
+    // the search loop passes the number of boards of this step on the device (the batch shrinks as trees finish): no host round trip
+    const int pairs = p.n_boards_dev ? min(p.pairs, (*p.n_boards_dev + 1) >> 1) : p.pairs;
+    const int units = (pairs + 1) / 2;  // one unit = two board pairs = one M=256 accumulator stage
     const int n = p.n, nh = n >> 1, nl = p.nl;
     // a weight stage = `tps` taps of one k-chunk (one TMA box of tps * N/2 rows per CTA): three taps for narrow layers, whose
     // single-tap stages (4-8 KB, 32-64 tensor cycles per MMA) would be bound by barrier round trips, not by the tensor pipe
@@ -163,7 +165,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
             if (l != l_loaded) { L = p.layers[l]; l_loaded = l; }
             const CUtensorMap* tm_in = &p.tm_act[L.in_buf];
             const int u = w.unit(k);
-            const int pair = min(2 * u + (int)rank, p.pairs - 1);  // odd tail: the peer re-reads the last pair, its result is dropped
+            const int pair = min(2 * u + (int)rank, pairs - 1);  // odd tail: the peer re-reads the last pair, its result is dropped
             if (l > 0) {
                 // the input of this item is the output of (unit, layer - 1): written by this CTA's epilogue warps, or by
                 // the same-rank CTA of the previous cluster; either way its progress flag says when it is in L2
@@ -287,7 +289,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
                 if (!w.mine(u, l)) continue;
                 const uint32_t st = j & 1;
                 const int pair = 2 * u + (int)rank;
-                const bool active = pair < p.pairs;
+                const bool active = pair < pairs;
                 // the skip tile is the output of (unit, layer - 2): if another cluster wrote it, it is only known to be
                 // complete once this item's own operands have been loaded (the producer waited for the flag)
                 const bool skip_early = has_skip && w.mine(u, l - 2);

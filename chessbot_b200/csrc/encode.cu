@@ -22,13 +22,15 @@ constexpr int ENC_WARPS = 4;
 __global__ void __launch_bounds__(ENC_WARPS * 32) encode_planes_kernel(const Pos* __restrict__ pos_base,
                                                                         const int32_t* __restrict__ frame_idx,  // [n][8], newest first, -1 = absent
                                                                         int n, __nv_bfloat16* __restrict__ planes_act,
-                                                                        int16_t* __restrict__ planes_i16) {
+                                                                        int16_t* __restrict__ planes_i16,
+                                                                        const int32_t* __restrict__ slot_list,  // compacted batch: position i
+                                                                        const int* __restrict__ n_dev) {        // = frames of slot_list[i], i < *n_dev
     __shared__ u64 s_mask[ENC_WARPS][112];
     __shared__ int s_scalar[ENC_WARPS][8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int pos_i = blockIdx.x * ENC_WARPS + warp;
-    if (pos_i >= n) return;
-    const int32_t* fi = frame_idx + (size_t)pos_i * 8;
+    if (pos_i >= n || (n_dev && pos_i >= *n_dev)) return;
+    const int32_t* fi = frame_idx + (size_t)(slot_list ? slot_list[pos_i] : pos_i) * 8;
 
     // ---- phase 1: 112 oriented masks (channel c = 14*slot + plane, slot = 7 - t for t plies back)
     for (int c = lane; c < 112; c += 32) {
@@ -125,9 +127,10 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) encode_planes_kernel(const Pos
 }
 
 int launch_encode(const Pos* pos_base, const int32_t* frame_idx, int n, __nv_bfloat16* planes_act, int16_t* planes_i16,
-                  cudaStream_t stream) {
+                  cudaStream_t stream, const int32_t* slot_list, const int* n_dev) {
     if (n <= 0) return 0;
-    encode_planes_kernel<<<(n + ENC_WARPS - 1) / ENC_WARPS, ENC_WARPS * 32, 0, stream>>>(pos_base, frame_idx, n, planes_act, planes_i16);
+    encode_planes_kernel<<<(n + ENC_WARPS - 1) / ENC_WARPS, ENC_WARPS * 32, 0, stream>>>(pos_base, frame_idx, n, planes_act, planes_i16, slot_list,
+                                                                                    n_dev);
     CB_CUDA_OK(cudaGetLastError());
     return 0;
 }

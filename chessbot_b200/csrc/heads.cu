@@ -19,13 +19,14 @@ __global__ void __launch_bounds__(256) head_features_kernel(HeadParams p, int bo
     __shared__ float v0[64];
     __shared__ float red[8];
     const int b = blockIdx.x;
-    if (b >= boards) return;
+    if (b >= boards || (p.n_boards_dev && b >= *p.n_boards_dev)) return;
+    const int dst = p.slot_list ? p.slot_list[b] : b;  // compacted batch: results go back to the leaf's evaluation slot
     const float* raw = p.head_raw + (size_t)b * 192;
     const int t = threadIdx.x;
     if (t < 64) v0[t] = lrelu(fmaf(raw[t * 3], p.bn[0], p.bn[1]), p.slope);
     if (t < 128) {
         const int sq = t >> 1, c = t & 1;
-        p.pfeat[(size_t)b * 128 + t] = lrelu(fmaf(raw[sq * 3 + 1 + c], p.bn[2 + 2 * c], p.bn[3 + 2 * c]), p.slope);
+        p.pfeat[(size_t)dst * 128 + t] = lrelu(fmaf(raw[sq * 3 + 1 + c], p.bn[2 + 2 * c], p.bn[3 + 2 * c]), p.slope);
     }
     __syncthreads();
     float part = 0.f;
@@ -40,7 +41,7 @@ __global__ void __launch_bounds__(256) head_features_kernel(HeadParams p, int bo
     if (t == 0) {
         float s = 0.f;
         for (int i = 0; i < 8; ++i) s += red[i];
-        p.value[b] = tanhf(s);
+        p.value[dst] = tanhf(s);
     }
 }
 

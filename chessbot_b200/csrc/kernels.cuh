@@ -44,6 +44,7 @@ struct TowerParams {
     float* head_out;            // [boards][64][3]
     double* stats;              // training forward (one layer per launch, no skip): [2][n] per-channel sum / sum of squares of the
                                 // bf16-rounded outputs, accumulated on top of what is there; nullptr otherwise
+    const int* n_boards_dev;    // search loop: number of boards actually in the batch this step (device-side, <= 2 * pairs); nullptr = 2 * pairs
     int* flags;                 // [2 * units] progress of every board pair: epoch * 256 + layers finished
     int epoch;                  // increases with every launch, so flags never need clearing
     int nl;                     // layers to run
@@ -70,6 +71,8 @@ struct HeadParams {
     float slope;
     float* value;            // [boards]
     float* pfeat;            // [boards][128]
+    const int32_t* slot_list;  // search loop: board b of the (compacted) batch belongs to evaluation slot slot_list[b]: results are
+    const int* n_boards_dev;   // scattered there; only *n_boards_dev boards are in the batch.  nullptr = identity / all boards
 };
 
 struct Node {  // 32 bytes; children of a node are contiguous, in legal-move order
@@ -137,6 +140,8 @@ struct SearchParams {
     const float* exp_table;    // [65536] f32 exp indexed by bf16 bits
     int32_t* counters;         // [0] evals, [1] sims, [2] errors
     int32_t* path;             // [slots][MCTS_MAX_PATH] node ids root..leaf of every pending leaf
+    int32_t* active_list;      // [slots] the evaluation slots that hold a pending leaf after this step, in claim order: the next
+    int32_t* active_count;     // step encodes / evaluates only these (a batch shrinks as trees finish their simulations)
 };
 
 // Weight gradient of one 3x3 convolution (wgrad.cu)
@@ -185,7 +190,8 @@ int launch_sgd(float* w, float* v, const float* g, size_t n, size_t n_reg, float
 int launch_pack_conv(const float* w, int cin, int cin_pad, int c, int n, int stem, __nv_bfloat16* fwd, __nv_bfloat16* tr, cudaStream_t st);
 int launch_fill(float* p, size_t n, float v, cudaStream_t st);
 
-int launch_encode(const Pos* pos_base, const int32_t* frame_idx, int n, __nv_bfloat16* planes_act, int16_t* planes_i16, cudaStream_t stream);
+int launch_encode(const Pos* pos_base, const int32_t* frame_idx, int n, __nv_bfloat16* planes_act, int16_t* planes_i16, cudaStream_t stream,
+                  const int32_t* slot_list = nullptr, const int* n_dev = nullptr);
 int launch_head_features(const HeadParams& p, int boards, cudaStream_t stream);
 int launch_policy_dense(const float* pfeat, const float* w, int boards, __nv_bfloat16* logits_bf16, float* logits_f32, cudaStream_t stream);
 int launch_synth(const int16_t* planes_i16, int n, uint32_t seed, uint32_t* hash_out, float* value, __nv_bfloat16* logits_dense, cudaStream_t stream);

@@ -371,6 +371,7 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_step_kernel(SearchParams
             sp.slots[slot] = sl;
             if (vl) sp.nodes[node].term = 3;
             fill_frames(sp, slot, leaf_pos);
+            sp.active_list[atomicAdd(sp.active_count, 1)] = slot;  // this leaf is in the next step's evaluation batch
             __threadfence_block();
         }
         __syncwarp();
@@ -409,6 +410,7 @@ __global__ void __launch_bounds__(128) mcts_begin_kernel(SearchParams sp) {
     uint16_t* pm = sp.pend_moves + (size_t)slot0 * MAX_MOVES;
     for (int i = 0; i < ml.n; ++i) pm[i] = ml.m[i];
     for (int i = 0; i < sp.leaves; ++i) fill_frames(sp, slot0 + i, ts.root_pos);  // every slot of the batch encodes a valid position
+    sp.active_list[atomicAdd(sp.active_count, 1)] = slot0;                        // the root is the first evaluation of the tree
 }
 
 int launch_mcts_begin(const SearchParams& sp, cudaStream_t stream) {

@@ -19,6 +19,33 @@ def calc_search_statistics(config: Config, root, to_play):
     return child_visits
 
 
+_ACTION_LUT = {}
+
+
+def _action_lut(white):
+    """action index of every packed move code (from | to << 6 | promo << 12) for one side to move: actionspace.uci_to_action
+    (actionspace.py:116-180) as a table, -1 where the reference returns None"""
+    lut = _ACTION_LUT.get(bool(white))
+    if lut is None:
+        from ._lib import lib
+        lut = np.array([lib.cb_move_to_action(code, int(bool(white))) for code in range(1 << 15)], dtype=np.int32)
+        _ACTION_LUT[bool(white)] = lut
+    return lut
+
+
+def search_statistics_from_root(config: Config, root, to_play):
+    """calc_search_statistics for a device root without building its children: the read-back move codes and visit counts go
+    through the action table in one gather (same float64 values: N / sum N)."""
+    stats = getattr(root, "_stats", None)
+    if stats is None:
+        return calc_search_statistics(config, root, to_play)
+    codes, counts = stats[0], stats[1]
+    child_visits = np.zeros(config.num_actions)
+    sum_visits = sum(counts.tolist())
+    child_visits[_action_lut(to_play)[codes]] = np.array([n / sum_visits for n in counts.tolist()])
+    return child_visits
+
+
 def playout_cap(config: Config, u: float):
     """train.py:29-31 for one uniform draw u: (do_full_search, num_simulations, CPUCT).  The reference compares
     the BOOL with the probability (`do_full_search < num_mcts_sims_p`), so a full search gets num_mcts_sims[1]
@@ -54,12 +81,14 @@ def play_games(network, n_games=1, config: Config = None, rngs=None, games=None)
             imgs = gameimage.boards_to_images([games[live[k]].board for k in rec], config.T).astype(np.int16)
             for img, k in zip(imgs, rec):
                 g = games[live[k]]
-                stats[live[k]].append(calc_search_statistics(config, roots[k], g.to_play()))
+                stats[live[k]].append(search_statistics_from_root(config, roots[k], g.to_play()))
                 images[live[k]].append(img)
                 on_turn[live[k]].append(g.to_play())
         for k, i in enumerate(live):
             temp = mcts.TEMP if games[i].history_len < config.num_mcts_sampling_moves else 0
-            games[i].make_move(mcts.select_move(roots[k], rngs[i], temp))
+            root = roots[k]                    # device roots: move choice from the read-back counts (same NumPy / RNG calls as select_move)
+            games[i].make_move(mcts._select_move_from_counts(root._stats[0], root._stats[1], rngs[i], temp) if hasattr(root, "_stats")
+                               else mcts.select_move(root, rngs[i], temp))
         live = [i for i in live if not games[i].terminal()]
     out = []
     for i, g in enumerate(games):
