@@ -159,9 +159,10 @@ def run_actors(jobs, device=None):
     as threads of this process: jobs[i] is a callable taking the actor's own `engine.Engine` and returning its result.  Every actor thread gets its own device context and CUDA stream, so
     while one actor waits for its searches (the C ABI releases the GIL) the others do their host work and keep the GPU fed.
     Returns the results in job order; the first exception is re-raised.
-    Measured (bench leg, since removed): two actors of 1024 games each on the 20x256 net give the same evals/s as one - a single
-    actor's queue of 101 steps already keeps the GPU busy, and two towers evict each other's 49 MB of weights from L2; actors
-    pay off when each has too few games to fill the tensor cores, or heavy host work per move (replay images, statistics)."""
+    Measured on one B200, 20x256: no gain.  Two actors of 1024 games each search at the same evals/s as one (a single actor's
+    queue of steps already keeps the GPU busy, and two towers evict each other's 49 MB of weights from L2); in playout-cap
+    self-play 2 actors x 1024 games reach 315 k sims/s against 386 k for ONE actor with 2048 games (scripts/selfplay_soak.py).
+    More games per actor is the better lever; actors remain useful when each has too few games to fill the tensor cores."""
     import threading
 
     import torch
