@@ -313,11 +313,12 @@ def run_gpu_arm(args):
     c2 = eng.search_status()
     nodes1 = int(eng.search_read_roots()["nodes"].sum())
     conv_ms, conv_launches = prof["conv"]
-    conv_flops_launch_total = conv_flops_per_position(filters, blocks) * trees * K   # algorithmic direct-conv FLOPs
+    evals_prof = c2["evals"] - c1["evals"]                                           # boards the tower really evaluated in this pass (terminal
+    conv_flops_launch_total = conv_flops_per_position(filters, blocks) * evals_prof   # leaves need none): algorithmic direct-conv FLOPs
     peak_tf, peak_gbs, peak_src = measured_peaks()
     achieved_tf = conv_flops_launch_total / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     # HBM-bound kernels, algorithmic bytes as stated in DESIGN.md §4
-    enc_bytes = 17152.0 * trees * K                                             # 8 x 96 B frames read + 128 ch bf16 written
+    enc_bytes = 17152.0 * evals_prof                                            # 8 x 96 B frames read + 128 ch bf16 written
     mcts_bytes = (nodes1 - nodes0) * (512 + 32 + 2) + (c2["sims"] - c1["sims"]) * 2700.0   # prior gather + node writes; select/backup
     kernels = {}
     for name, nbytes in (("encode", enc_bytes), ("mcts_step", mcts_bytes), ("heads", None)):
@@ -379,7 +380,7 @@ def run_gpu_arm(args):
             },
             "roofline": {
                 "bound": "tensor", "kernel": "tower_tcgen05_kernel (all 1+2R conv layers, one persistent launch)", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak_tf, "traffic": 3.57e9 if (filters, blocks, trees) == (256, 20, 1024) else None,
+                "frac": achieved_tf / peak_tf, "traffic": 3.50e9 if (filters, blocks, trees) == (256, 20, 1024) else None,
                 "traffic_note": "DRAM read+write bytes per tower launch, ncu --set full capture profiles/r1_ncu_full_raw_encode_tower_mcts.csv", "peak_source": peak_src,
                 "how": f"algorithmic direct-conv FLOPs of {conv_launches} launches / their CUDA-event durations ({conv_ms:.2f} ms), second pass of the same {K} steps",
                 "conv_share_of_step": conv_ms / ms if ms > 0 else None,
