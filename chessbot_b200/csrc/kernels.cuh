@@ -176,7 +176,8 @@ int launch_head_stats(const float* head_raw, int n, double* stats, cudaStream_t 
 int launch_head_features_train(const float* head_raw, int n, const double* stats, const float* vbn, const float* pbn, float* vmoving, float* pmoving,
                                const float* fc1, const float* fc2, int c, float eps, float slope, float momentum, float* hmr, float* vfeat,
                                float* pfeat, float* h1pre, float* value, cudaStream_t st);
-int launch_sgemm(const float* A, const float* B, float* C, int M, int N, int K, int ta, int tb, cudaStream_t st);
+int launch_sgemm(const float* A, const float* B, float* C, int M, int N, int K, int ta, int tb, float* scratch, size_t scratch_floats,
+                 cudaStream_t st);
 int launch_softmax_ce(float* logits, const float* pi, int n, double* losses, cudaStream_t st);
 int launch_value_loss_bwd(const float* value, const float* z, const float* h1pre, const float* fc2, int n, int c, float slope, float* dpre, float* dh1pre,
                           float* dfc2, double* losses, cudaStream_t st);
@@ -185,8 +186,7 @@ int launch_head_bn_bwd_reduce(const float* head_raw, const float* vfeat, const f
 int launch_head_conv_bwd(const __nv_bfloat16* a, __nv_bfloat16* gout, int n, int cj, int c, const float* head_raw, const float* vfeat, const float* pfeat,
                          const float* dvfeat, const float* dpfeat, const float* hmr, const double* hsums, const float* vbn, const float* pbn,
                          const float* wv, const float* wp, float slope, float* dwv, float* dwp, float* dvbn, float* dpbn, cudaStream_t st);
-int launch_sgd(float* w, float* v, const float* g, size_t n, size_t n_reg, float lr, float mom, float l2, float gscale, int nesterov, double* losses,
-               cudaStream_t st);
+int launch_sgd(float* w, float* v, const float* g, size_t n, size_t n_reg, const float* hp_dev, double* losses, cudaStream_t st);
 int launch_pack_conv(const float* w, int cin, int cin_pad, int c, int n, int stem, __nv_bfloat16* fwd, __nv_bfloat16* tr, cudaStream_t st);
 int launch_fill(float* p, size_t n, float v, cudaStream_t st);
 

@@ -368,7 +368,9 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {
 }
 template <int BM, int BN>  // 128 x 128 for the big products, 64 x 64 where the output is small and the reduction long (more CTAs)
 __global__ void __launch_bounds__(256) gemm_tf32_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int M, int N, int K,
-                                                         int ta, int tb) {
+                                                         int ta, int tb, int k_per_split) {
+    // split-K: block z reduces k in [z * k_per_split, (z + 1) * k_per_split) into its own M x N slab of C (summed afterwards in a
+    // fixed order); gridDim.z == 1: the whole product straight into C
     constexpr int BK = 32, LD = BK + 4;  // row stride 36 words: the 8 x 4 fragment reads hit 32 different banks
     constexpr int MI = BM / 32, NJ = BN / 32;  // 16 x 8 MMA tiles per warp (warps 2 x 4)
     __shared__ uint32_t As[BM][LD], Bs[BN][LD];
@@ -376,6 +378,8 @@ __global__ void __launch_bounds__(256) gemm_tf32_kernel(const float* __restrict_
     const int wm = (warp >> 2) * (BM / 2), wn = (warp & 3) * (BN / 4);
     const int g = lane >> 2, t4 = lane & 3;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int k_begin = blockIdx.z * k_per_split, k_end = min(K, k_begin + k_per_split);
+    C += (size_t)blockIdx.z * M * N;
     float acc[MI][NJ][4];
 #pragma unroll
     for (int i = 0; i < MI; ++i)
@@ -383,19 +387,19 @@ __global__ void __launch_bounds__(256) gemm_tf32_kernel(const float* __restrict_
         for (int j = 0; j < NJ; ++j)
 #pragma unroll
             for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
-    for (int k0 = 0; k0 < K; k0 += BK) {
+    for (int k0 = k_begin; k0 < k_end; k0 += BK) {
         // global -> shared in float4 along the operand's contiguous dimension (all of them are multiples of 4 here)
         for (int i = threadIdx.x; i < BM * BK / 4; i += 256) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (ta) {  // A stored [k][m]
                 const int mm = (i % (BM / 4)) * 4, kk = i / (BM / 4);
                 const int gm = m0 + mm, gk = k0 + kk;
-                if (gm < M && gk < K) v = *reinterpret_cast<const float4*>(A + (size_t)gk * M + gm);
+                if (gm < M && gk < k_end) v = *reinterpret_cast<const float4*>(A + (size_t)gk * M + gm);
                 As[mm][kk] = to_tf32(v.x); As[mm + 1][kk] = to_tf32(v.y); As[mm + 2][kk] = to_tf32(v.z); As[mm + 3][kk] = to_tf32(v.w);
             } else {   // A stored [m][k]
                 const int kk = (i % (BK / 4)) * 4, mm = i / (BK / 4);
                 const int gm = m0 + mm, gk = k0 + kk;
-                if (gm < M && gk < K) v = *reinterpret_cast<const float4*>(A + (size_t)gm * K + gk);
+                if (gm < M && gk < k_end) v = *reinterpret_cast<const float4*>(A + (size_t)gm * K + gk);
                 *reinterpret_cast<uint4*>(&As[mm][kk]) = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
             }
         }
@@ -404,12 +408,12 @@ __global__ void __launch_bounds__(256) gemm_tf32_kernel(const float* __restrict_
             if (tb) {  // B stored [n][k]
                 const int kb = (i % (BK / 4)) * 4, nn = i / (BK / 4);
                 const int gn = n0 + nn, gk = k0 + kb;
-                if (gn < N && gk < K) v = *reinterpret_cast<const float4*>(B + (size_t)gn * K + gk);
+                if (gn < N && gk < k_end) v = *reinterpret_cast<const float4*>(B + (size_t)gn * K + gk);
                 *reinterpret_cast<uint4*>(&Bs[nn][kb]) = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
             } else {   // B stored [k][n]
                 const int nn = (i % (BN / 4)) * 4, kb = i / (BN / 4);
                 const int gn = n0 + nn, gk = k0 + kb;
-                if (gn < N && gk < K) v = *reinterpret_cast<const float4*>(B + (size_t)gk * N + gn);
+                if (gn < N && gk < k_end) v = *reinterpret_cast<const float4*>(B + (size_t)gk * N + gn);
                 Bs[nn][kb] = to_tf32(v.x); Bs[nn + 1][kb] = to_tf32(v.y); Bs[nn + 2][kb] = to_tf32(v.z); Bs[nn + 3][kb] = to_tf32(v.w);
             }
         }
@@ -617,9 +621,13 @@ __global__ void __launch_bounds__(128) head_conv_bwd_kernel(const uint8_t* __res
 // SGD(momentum, nesterov=True) of model.py:59 with the l2(4e-4) kernel regularizers folded into the gradient:
 // g = grad * gscale + 2 * l2 * w (first n_reg parameters: the kernels); v = mom * v - lr * g; w += nesterov ? mom * v - lr * g : v.
 // losses[2] += sum of w^2 over the regularized parameters (before the update).
-__global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ w, float* __restrict__ v, const float* __restrict__ g, size_t n, size_t n_reg, float lr,
-                                                   float mom, float l2, float gscale, int nesterov, double* __restrict__ losses) {
+__global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ w, float* __restrict__ v, const float* __restrict__ g, size_t n, size_t n_reg,
+                                                   const float* __restrict__ hp /* lr, momentum, l2, grad scale, nesterov: device memory, so
+                                                   the launch is the same every step and can sit in a CUDA graph */,
+                                                   double* __restrict__ losses) {
     __shared__ float red[8];
+    const float lr = hp[0], mom = hp[1], l2 = hp[2], gscale = hp[3];
+    const bool nesterov = hp[4] != 0.f;
     float sq[1] = {0.f};
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const float wi = w[i];
@@ -712,12 +720,38 @@ int launch_head_features_train(const float* head_raw, int n, const double* stats
                                                   h1pre, value);
     CB_LAUNCH_OK();
 }
-int launch_sgemm(const float* A, const float* B, float* C, int M, int N, int K, int ta, int tb, cudaStream_t st) {
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, size_t mn, float* __restrict__ C) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < mn; i += (size_t)gridDim.x * blockDim.x) {
+        float acc = 0.f;
+        for (int z = 0; z < splits; ++z) acc += part[(size_t)z * mn + i];
+        C[i] = acc;
+    }
+}
+
+// scratch: split-K slabs (scratch_floats capacity); a small output with a long reduction (dpfeat: M = batch, N = 128, K = 4672; dfc1:
+// 64 x C, K = batch) would otherwise run on a handful of CTAs
+int launch_sgemm(const float* A, const float* B, float* C, int M, int N, int K, int ta, int tb, float* scratch, size_t scratch_floats,
+                 cudaStream_t st) {
     if (((ta ? M : K) & 3) || ((tb ? K : N) & 3)) { cb_set_error("gemm: contiguous dimensions must be multiples of 4 (filters % 4 == 0)"); return -1; }
-    if ((size_t)((N + 127) / 128) * ((M + 127) / 128) >= 148)
-        gemm_tf32_kernel<128, 128><<<dim3((N + 127) / 128, (M + 127) / 128), 256, 0, st>>>(A, B, C, M, N, K, ta, tb);
-    else
-        gemm_tf32_kernel<64, 64><<<dim3((N + 63) / 64, (M + 63) / 64), 256, 0, st>>>(A, B, C, M, N, K, ta, tb);
+    const size_t big = (size_t)((N + 127) / 128) * ((M + 127) / 128);
+    if (big >= 148) {
+        gemm_tf32_kernel<128, 128><<<dim3((N + 127) / 128, (M + 127) / 128), 256, 0, st>>>(A, B, C, M, N, K, ta, tb, K);
+        CB_LAUNCH_OK();
+    }
+    const int nb = (N + 63) / 64, mb = (M + 63) / 64;
+    int splits = (296 + nb * mb - 1) / (nb * mb);  // about two CTAs per SM
+    if (splits > K / 128) splits = K / 128;
+    if (scratch && (size_t)splits * M * N > scratch_floats) splits = (int)(scratch_floats / ((size_t)M * N));
+    if (!scratch || splits < 2) {
+        gemm_tf32_kernel<64, 64><<<dim3(nb, mb), 256, 0, st>>>(A, B, C, M, N, K, ta, tb, K);
+        CB_LAUNCH_OK();
+    }
+    const int k_per = ((K + splits - 1) / splits + 31) / 32 * 32;
+    splits = (K + k_per - 1) / k_per;
+    gemm_tf32_kernel<64, 64><<<dim3(nb, mb, splits), 256, 0, st>>>(A, B, scratch, M, N, K, ta, tb, k_per);
+    CB_CUDA_OK(cudaGetLastError());
+    const size_t mn = (size_t)M * N;
+    splitk_reduce_kernel<<<(unsigned)((mn + 255) / 256 < 1184 ? (mn + 255) / 256 : 1184), 256, 0, st>>>(scratch, splits, mn, C);
     CB_LAUNCH_OK();
 }
 int launch_softmax_ce(float* logits, const float* pi, int n, double* losses, cudaStream_t st) {
@@ -747,9 +781,8 @@ int launch_head_conv_bwd(const __nv_bfloat16* a, __nv_bfloat16* gout, int n, int
                                                                  dpfeat, hmr, hsums, vbn, pbn, wv, wp, slope, dwv, dwp, dvbn, dpbn);
     CB_LAUNCH_OK();
 }
-int launch_sgd(float* w, float* v, const float* g, size_t n, size_t n_reg, float lr, float mom, float l2, float gscale, int nesterov, double* losses,
-               cudaStream_t st) {
-    sgd_kernel<<<592, 256, 0, st>>>(w, v, g, n, n_reg, lr, mom, l2, gscale, nesterov, losses);
+int launch_sgd(float* w, float* v, const float* g, size_t n, size_t n_reg, const float* hp_dev, double* losses, cudaStream_t st) {
+    sgd_kernel<<<592, 256, 0, st>>>(w, v, g, n, n_reg, hp_dev, losses);
     CB_LAUNCH_OK();
 }
 int launch_pack_conv(const float* w, int cin, int cin_pad, int c, int n, int stem, __nv_bfloat16* fwd, __nv_bfloat16* tr, cudaStream_t st) {

@@ -83,11 +83,19 @@ struct cb_trainer {
     CUtensorMap map_planes{}, map_dy_conv{}, map_dy_wg{};
     TBuf<CUtensorMap> wmaps;             // [2 * nl]: forward packs, then data-gradient packs
     TBuf<LayerDesc> ldesc;               // [2 * nl]
-    TBuf<float> ones, zeros, mean_rstd, wg_partial;
+    TBuf<float> ones, zeros, mean_rstd, wg_partial, gemm_scratch;
     TBuf<double> stats, bsums, hstats, hsums, losses;
     TBuf<int> flags;
     int epoch = 0, wg_splits_stem = 1, wg_splits_res = 1;
     TBuf<float> head_raw, hmr, vfeat, pfeat, h1pre, value, logits, dpfeat, dvfeat, dh1pre, dpre;
+    // the step's launch sequence is the same every time: after one eager step it is captured into two CUDA graphs (forward +
+    // backward; optimizer + weight packing) and replayed.  Inputs are staged into trainer-owned buffers, the optimizer's
+    // hyper-parameters live in device memory, so no kernel argument changes between steps.
+    TBuf<int16_t> in_img;
+    TBuf<float> in_z, in_pi, hp;
+    cudaStream_t cap_stream = nullptr;
+    cudaGraphExec_t graph_fb = nullptr, graph_apply = nullptr;
+    int fb_calls = 0, apply_calls = 0;
     bool weights_dirty = true;
     bool profile = false;
     std::vector<cudaEvent_t> ev;
@@ -118,11 +126,7 @@ static int tp_end(cb_trainer* t, cudaStream_t st) {
 // one layer of the tower kernel: raw convolution (identity epilogue), optionally + skip
 static int conv_layer(cb_trainer* t, int desc, const CUtensorMap& in_map, const void* in, void* out, const void* skip, double* stats,
                       cudaStream_t st) {
-    if (++t->epoch >= (1 << 22)) {
-        CB_CUDA_OK(cudaMemsetAsync(t->flags.p, 0, t->flags.n * sizeof(int), st));
-        t->epoch = 1;
-    }
-    TowerParams tp{};
+    TowerParams tp{};  // one layer per launch: nothing waits on the progress flags, so the epoch can stay the same (graph replay)
     tp.tm_act[0] = in_map;
     tp.bufs[0] = (uint8_t*)const_cast<void*>(in);
     tp.bufs[1] = (uint8_t*)out;
@@ -133,7 +137,7 @@ static int conv_layer(cb_trainer* t, int desc, const CUtensorMap& in_map, const 
     tp.head_out = nullptr;
     tp.stats = stats;  // forward pass: the epilogue gathers the layer's batch statistics
     tp.flags = t->flags.p;
-    tp.epoch = t->epoch;
+    tp.epoch = 1;
     tp.nl = 1;
     tp.pairs = t->pairs;
     tp.n = t->N;
@@ -226,7 +230,8 @@ cb_trainer* cb_train_create(cb_ctx* ctx, int filters, int blocks, int batch, flo
         t->mean_rstd.alloc((size_t)nl * 4 * N) || t->bsums.alloc((size_t)nl * 2 * N) || t->hstats.alloc(6) || t->hsums.alloc(6) || t->losses.alloc(4) ||
         t->flags.alloc(2 * ((size_t)batch / 4 + 2)) || t->head_raw.alloc(mb * 192) || t->hmr.alloc(6) || t->vfeat.alloc(mb * 64) ||
         t->pfeat.alloc(mb * 128) || t->h1pre.alloc(mb * filters) || t->value.alloc(mb) || t->logits.alloc(mb * 4672) || t->dpfeat.alloc(mb * 128) ||
-        t->dvfeat.alloc(mb * 64) || t->dh1pre.alloc(mb * filters) || t->dpre.alloc(mb))
+        t->dvfeat.alloc(mb * 64) || t->dh1pre.alloc(mb * filters) || t->dpre.alloc(mb) || t->gemm_scratch.alloc((size_t)8 << 20) ||
+        t->in_img.alloc(mb * 7616) || t->in_z.alloc(mb) || t->in_pi.alloc(mb * 4672) || t->hp.alloc(8))
         return fail();
     // Keras initial state of the moving statistics: mean 0, variance 1
     std::vector<float> mv(t->lay.n_moving, 0.f);
@@ -235,6 +240,7 @@ cb_trainer* cb_train_create(cb_ctx* ctx, int filters, int blocks, int batch, flo
     mv[t->lay.vmov.off + 1] = 1.f;
     mv[t->lay.pmov.off + 2] = mv[t->lay.pmov.off + 3] = 1.f;
     if (cudaMemcpy(t->moving.p, mv.data(), mv.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) { cb_set_error("moving statistics upload failed"); return fail(); }
+    if (cudaStreamCreateWithFlags(&t->cap_stream, cudaStreamNonBlocking) != cudaSuccess) { cb_set_error("cb_train_create: stream"); return fail(); }
     if (cudaDeviceSynchronize() != cudaSuccess) { cb_set_error("cb_train_create: device error"); return fail(); }
     return t;
 }
@@ -242,6 +248,9 @@ cb_trainer* cb_train_create(cb_ctx* ctx, int filters, int blocks, int batch, flo
 void cb_train_destroy(cb_trainer* t) {
     if (!t) return;
     for (cudaEvent_t e : t->ev) cudaEventDestroy(e);
+    if (t->graph_fb) cudaGraphExecDestroy(t->graph_fb);
+    if (t->graph_apply) cudaGraphExecDestroy(t->graph_apply);
+    if (t->cap_stream) cudaStreamDestroy(t->cap_stream);
     delete t;
 }
 
@@ -313,14 +322,53 @@ int cb_train_get_tensor(cb_trainer* t, const char* name, int what, float* host, 
     return 0;
 }
 
+static int enqueue_forward_backward(cb_trainer* t, cudaStream_t st);
+static int enqueue_apply(cb_trainer* t, cudaStream_t st);
+
+// runs `enqueue` eagerly the first time (and whenever per-launch profiling is on or CB_TRAIN_NO_GRAPH is set), captures it into a graph
+// on the trainer's own stream the second time (the caller's stream may be the legacy default stream, which cannot capture) and
+// replays that graph on the caller's stream from then on
+static int run_graphed(cb_trainer* t, int (*enqueue)(cb_trainer*, cudaStream_t), cudaGraphExec_t* exec, int* calls, cudaStream_t st) {
+    static const bool no_graph = getenv("CB_TRAIN_NO_GRAPH") != nullptr;
+    if (t->profile || no_graph || (*calls)++ == 0) return enqueue(t, st);
+    if (!*exec) {
+        cudaGraph_t graph = nullptr;
+        CB_CUDA_OK(cudaStreamBeginCapture(t->cap_stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = enqueue(t, t->cap_stream);
+        const cudaError_t e = cudaStreamEndCapture(t->cap_stream, &graph);
+        if (rc || e != cudaSuccess || !graph) {
+            if (graph) cudaGraphDestroy(graph);
+            if (!rc) cb_set_error(std::string("CUDA graph capture of the training step failed: ") + cudaGetErrorString(e));
+            return -1;
+        }
+        const cudaError_t ei = cudaGraphInstantiate(exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ei != cudaSuccess) { cb_set_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ei)); return -1; }
+    }
+    CB_CUDA_OK(cudaGraphLaunch(*exec, st));
+    return 0;
+}
+
 int cb_train_forward_backward(cb_trainer* t, const int16_t* images_dev, const float* z_dev, const float* pi_dev, int n, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (n != t->batch) { cb_set_error("cb_train_forward_backward: n must equal the trainer's batch"); return -1; }
+    if (t->weights_dirty && (tp_begin(t, TP_OPT, st) || pack_weights(t, st) || tp_end(t, st))) return -1;
+    // stage the caller's batch: the step itself only ever reads the trainer's own buffers
+    CB_CUDA_OK(cudaMemcpyAsync(t->in_img.p, images_dev, (size_t)n * 7616 * 2, cudaMemcpyDeviceToDevice, st));
+    CB_CUDA_OK(cudaMemcpyAsync(t->in_z.p, z_dev, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+    CB_CUDA_OK(cudaMemcpyAsync(t->in_pi.p, pi_dev, (size_t)n * 4672 * 4, cudaMemcpyDeviceToDevice, st));
+    return run_graphed(t, enqueue_forward_backward, &t->graph_fb, &t->fb_calls, st);
+}
+
+static int enqueue_forward_backward(cb_trainer* t, cudaStream_t st) {
+    const int n = t->batch;
+    const int16_t* images_dev = t->in_img.p;
+    const float* z_dev = t->in_z.p;
+    const float* pi_dev = t->in_pi.p;
     const int nl = t->nl, N = t->N, C = t->C, cj = N / 8;
     const ParamLayout& L = t->lay;
     float* P = t->params;
     float* G = t->grads;
-    if (t->weights_dirty && (tp_begin(t, TP_OPT, st) || pack_weights(t, st) || tp_end(t, st))) return -1;
     CB_CUDA_OK(cudaMemsetAsync(t->stats.p, 0, t->stats.n * 8, st));
     CB_CUDA_OK(cudaMemsetAsync(t->bsums.p, 0, t->bsums.n * 8, st));
     CB_CUDA_OK(cudaMemsetAsync(t->hstats.p, 0, 48, st));
@@ -351,12 +399,12 @@ int cb_train_forward_backward(cb_trainer* t, const int16_t* images_dev, const fl
         launch_head_features_train(t->head_raw.p, n, t->hstats.p, P + L.vbn.off, P + L.pbn.off, t->moving.p + L.vmov.off, t->moving.p + L.pmov.off,
                                    P + L.vfc1.off, P + L.vfc2.off, C, t->eps, t->slope, t->bn_momentum, t->hmr.p, t->vfeat.p, t->pfeat.p, t->h1pre.p,
                                    t->value.p, st) ||
-        launch_sgemm(t->pfeat.p, P + L.pfc.off, t->logits.p, n, 4672, 128, 0, 0, st) || launch_softmax_ce(t->logits.p, pi_dev, n, t->losses.p, st) ||
+        launch_sgemm(t->pfeat.p, P + L.pfc.off, t->logits.p, n, 4672, 128, 0, 0, t->gemm_scratch.p, t->gemm_scratch.n, st) || launch_softmax_ce(t->logits.p, pi_dev, n, t->losses.p, st) ||
         launch_value_loss_bwd(t->value.p, z_dev, t->h1pre.p, P + L.vfc2.off, n, C, t->slope, t->dpre.p, t->dh1pre.p, G + L.vfc2.off, t->losses.p, st) ||
-        launch_sgemm(t->pfeat.p, t->logits.p, G + L.pfc.off, 128, 4672, n, 1, 0, st) ||            // dWp = pfeat^T dlogits
-        launch_sgemm(t->logits.p, P + L.pfc.off, t->dpfeat.p, n, 128, 4672, 0, 1, st) ||           // dpfeat = dlogits Wp^T
-        launch_sgemm(t->vfeat.p, t->dh1pre.p, G + L.vfc1.off, 64, C, n, 1, 0, st) ||               // dfc1 = vfeat^T dh1pre
-        launch_sgemm(t->dh1pre.p, P + L.vfc1.off, t->dvfeat.p, n, 64, C, 0, 1, st) ||              // dvfeat = dh1pre fc1^T
+        launch_sgemm(t->pfeat.p, t->logits.p, G + L.pfc.off, 128, 4672, n, 1, 0, t->gemm_scratch.p, t->gemm_scratch.n, st) ||            // dWp = pfeat^T dlogits
+        launch_sgemm(t->logits.p, P + L.pfc.off, t->dpfeat.p, n, 128, 4672, 0, 1, t->gemm_scratch.p, t->gemm_scratch.n, st) ||           // dpfeat = dlogits Wp^T
+        launch_sgemm(t->vfeat.p, t->dh1pre.p, G + L.vfc1.off, 64, C, n, 1, 0, t->gemm_scratch.p, t->gemm_scratch.n, st) ||               // dfc1 = vfeat^T dh1pre
+        launch_sgemm(t->dh1pre.p, P + L.vfc1.off, t->dvfeat.p, n, 64, C, 0, 1, t->gemm_scratch.p, t->gemm_scratch.n, st) ||              // dvfeat = dh1pre fc1^T
         launch_head_bn_bwd_reduce(t->head_raw.p, t->vfeat.p, t->pfeat.p, t->dvfeat.p, t->dpfeat.p, n, t->hmr.p, t->slope, t->hsums.p, st) ||
         launch_head_conv_bwd(top, t->g[0].p, n, cj, C, t->head_raw.p, t->vfeat.p, t->pfeat.p, t->dvfeat.p, t->dpfeat.p, t->hmr.p, t->hsums.p,
                              P + L.vbn.off, P + L.pbn.off, P + L.vconv.off, P + L.pconv.off, t->slope, G + L.vconv.off, G + L.pconv.off, G + L.vbn.off,
@@ -399,11 +447,16 @@ int cb_train_forward_backward(cb_trainer* t, const int16_t* images_dev, const fl
 
 int cb_train_apply(cb_trainer* t, float lr, float momentum, int nesterov, float l2, float grad_scale, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    CB_CUDA_OK(cudaMemsetAsync(t->losses.p + 2, 0, 8, st));
     t->last_l2 = l2;
+    const float hp[5] = {lr, momentum, l2, grad_scale, nesterov ? 1.f : 0.f};
+    CB_CUDA_OK(cudaMemcpyAsync(t->hp.p, hp, sizeof(hp), cudaMemcpyHostToDevice, st));  // pageable source: staged before the call returns
+    return run_graphed(t, enqueue_apply, &t->graph_apply, &t->apply_calls, st);
+}
+
+static int enqueue_apply(cb_trainer* t, cudaStream_t st) {
+    CB_CUDA_OK(cudaMemsetAsync(t->losses.p + 2, 0, 8, st));
     if (tp_begin(t, TP_OPT, st) ||
-        launch_sgd(t->params, t->mom, t->grads, t->lay.n_params, t->lay.n_reg, lr, momentum, l2, grad_scale, nesterov, t->losses.p, st) ||
-        pack_weights(t, st) || tp_end(t, st))
+        launch_sgd(t->params, t->mom, t->grads, t->lay.n_params, t->lay.n_reg, t->hp.p, t->losses.p, st) || pack_weights(t, st) || tp_end(t, st))
         return -1;
     return 0;
 }
