@@ -164,10 +164,10 @@ class Board:
                 from ._lib import last_error
                 raise ValueError(last_error())
 
-    def __del__(self):
+    def __del__(self, _free=lib.cb_board_free):      # bound at definition: module globals are gone at interpreter shutdown
         h, self._h = getattr(self, "_h", None), None
         if h:
-            lib.cb_board_free(h)
+            _free(h)
 
     # --- state
     @property

@@ -36,6 +36,21 @@ __device__ __forceinline__ size_t cell_off(int pair, int cj, int j, int cell) { 
 constexpr int SQ_THREADS = 128;
 __device__ __forceinline__ int square_cell(int t) { return ((t >> 4) + 1) * 20 + ((t >> 3) & 1) * 10 + (t & 7) + 1; }
 
+// sum over the 32 lanes of a warp of 32 values per lane, transposed: afterwards lane c holds the total of value c in v[0]
+// (butterfly with halving payload: 31 shuffles instead of 32 x 5; the same helper lives in conv.cu for the BN statistics)
+__device__ __forceinline__ void warp_transpose_sum32_t(float (&v)[32], int lane) {
+#pragma unroll
+    for (int k = 16; k >= 1; k >>= 1) {
+        const bool up = (lane & k) != 0;
+#pragma unroll
+        for (int i = 0; i < k; ++i) {
+            const float send = up ? v[i] : v[i + k];
+            const float recv = __shfl_xor_sync(0xffffffffu, send, k);
+            v[i] = (up ? v[i + k] : v[i]) + recv;
+        }
+    }
+}
+
 // sum `v[0..NV)` over the block, result in thread `i` for value i (i < NV) as double
 template <int NV>
 __device__ __forceinline__ double block_sum(float (&v)[NV], float* red /*[warps][NV]*/) {
@@ -592,20 +607,19 @@ __global__ void __launch_bounds__(128) head_conv_bwd_kernel(const uint8_t* __res
         }
         for (int j = 0; j < cj; ++j) {
             const size_t off = cell_off(pair, cj, j, cell);
-            float x[8], o[8];
+            float x[8], o[8], prod[32];
             unpack8(__ldg(reinterpret_cast<const uint4*>(a + off)), x);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
                 const int ch = j * 8 + e;
                 o[e] = dr[0] * w[0][ch] + dr[1] * w[1][ch] + dr[2] * w[2][ch];
 #pragma unroll
-                for (int h = 0; h < 3; ++h) {
-                    float v = dr[h] * x[e];
-#pragma unroll
-                    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-                    if (lane == 0) atomicAdd(&dw[h][ch], v);
-                }
+                for (int h = 0; h < 3; ++h) prod[h * 8 + e] = dr[h] * x[e];
+                prod[24 + e] = 0.f;
             }
+            // the 24 products of this chunk summed over the warp's 32 squares, transposed: lane h * 8 + e ends up with the total
+            warp_transpose_sum32_t(prod, lane);
+            if (lane < 24) atomicAdd(&dw[lane >> 3][j * 8 + (lane & 7)], prod[0]);
             if (board < n) *reinterpret_cast<uint4*>(gout + off) = pack8(o);
         }
     }

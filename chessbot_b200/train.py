@@ -99,10 +99,10 @@ class Trainer:
         self.steps = 0
         self.rank, self.world = data_parallel_world()
 
-    def __del__(self):
+    def __del__(self, _destroy=lib.cb_train_destroy):
         h, self._h = getattr(self, "_h", None), None
         if h:
-            lib.cb_train_destroy(h)
+            _destroy(h)
 
     # ------------------------------------------------------------------ weights
     def set_weights(self, weights, what=0):
