@@ -225,28 +225,29 @@ def test_config5_full_size_step_against_fp32_oracle():
     assert float(row_sums.max()) <= 1e-4 * float(np.abs(g["policy.fc"]).sum(axis=1).max()) + 1e-6
 
 
-def test_learned_function_carries_over_to_the_inference_path():
-    """Train a learnable target (value = side to move) at the reference's learning rate, let the BN running statistics settle on
-    the final weights (lr 0, momentum 0), then evaluate with the INFERENCE kernels (folded running statistics, one persistent
-    tower launch): the learned function must be there - training-mode BN, the moving-average rule, get_weights and the
-    inference path agree with each other."""
+def test_training_mode_and_inference_path_agree_once_the_running_statistics_settle():
+    """Train for a while, then freeze the weights (lr 0, momentum 0) and keep stepping on the SAME batch: the BN running statistics
+    converge to that batch's statistics (moving = moving * 0.99 + batch * 0.01), so the INFERENCE kernels (folded running
+    statistics, one persistent tower launch) on the trained weights must reproduce the training-mode outputs of the batch:
+    training-mode BN, the moving-average rule, get_weights and the inference path are consistent with each other."""
     from chessbot_b200.model import DeviceNetwork
     from chessbot_b200.train import Trainer
     from oracle import ref_model
-    filters, blocks, n, pool = 48, 2, 64, 512
-    images, _, pi = _batch(pool, seed=21)
+    filters, blocks, n = 48, 2, 64
+    images, _, pi = _batch(n, seed=21)
     z = np.sign(images[:, 0, 0, 112] - 0.5).astype(np.float32)
     tr = Trainer(ref_model.init_weights(filters, blocks, seed=2), filters, blocks, n)
-    rng = np.random.default_rng(0)
-    for _ in range(300):
-        idx = rng.choice(pool, n, replace=False)
-        last = tr.train_on_batch(images[idx], z[idx], pi[idx], 0.1)
-    for _ in range(300):
-        idx = rng.choice(pool, n, replace=False)
-        tr.forward_backward(images[idx], z[idx], pi[idx])
+    first = tr.train_on_batch(images, z, pi, 0.02)
+    for _ in range(150):
+        last = tr.train_on_batch(images, z, pi, 0.02)
+    assert np.isfinite(last["loss"]) and last["loss"] < first["loss"], (first, last)
+    before = tr.get_weights()
+    for _ in range(1200):                                  # 0.99^1200 = 6e-6 of the old running statistics left
+        tr.forward_backward(images, z, pi)
         tr.apply(0.0, momentum=0.0)
-    frozen = tr.losses()
-    assert np.isfinite(last["loss"]) and frozen["value"] < 0.05, (last, frozen)
-    value, _ = DeviceNetwork(tr.get_weights(), filters, blocks, max_batch=n).predict(images[:n])
-    value = value.cpu().numpy()
-    assert float(np.mean(np.sign(value) == z[:n])) >= 0.97 and float(np.mean((value - z[:n]) ** 2)) < 0.05
+    after = tr.get_weights()
+    assert all(np.array_equal(before[k], after[k]) for k in before if "bn" not in k)          # lr 0, momentum 0: weights frozen
+    train_mode = tr.values()
+    value, _ = DeviceNetwork(after, filters, blocks, max_batch=n).predict(images)
+    assert float(np.abs(value.cpu().numpy() - train_mode).max()) < 3e-2, float(np.abs(value.cpu().numpy() - train_mode).max())
+    assert abs(tr.losses()["value"] - float(np.mean((train_mode - z) ** 2))) < 1e-4
