@@ -380,7 +380,7 @@ def run_gpu_arm(args):
             },
             "roofline": {
                 "bound": "tensor", "kernel": "tower_tcgen05_kernel (all 1+2R conv layers, one persistent launch)", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak_tf, "traffic": 3.50e9 if (filters, blocks, trees) == (256, 20, 1024) else None,
+                "frac": achieved_tf / peak_tf, "traffic": 3.06e9 if (filters, blocks, trees) == (256, 20, 1024) else None,
                 "traffic_note": "DRAM read+write bytes per tower launch, ncu --set full capture profiles/r1_ncu_full_raw_encode_tower_mcts.csv", "peak_source": peak_src,
                 "how": f"algorithmic direct-conv FLOPs of {conv_launches} launches / their CUDA-event durations ({conv_ms:.2f} ms), second pass of the same {K} steps",
                 "conv_share_of_step": conv_ms / ms if ms > 0 else None,

@@ -111,8 +111,11 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) encode_planes_kernel(const Pos
                     for (int e = 0; e < 8; ++e)
                         if ((s_mask[warp][chunk * 8 + e] >> sq) & 1) w[e >> 1] |= (e & 1) ? 0x3F800000u : 0x00003F80u;
                 }
-                *reinterpret_cast<uint4*>(out + act_offset_bytes(pair, 16, chunk, act_cell(sq >> 3, bip, sq & 7))) =
-                    make_uint4(w[0], w[1], w[2], w[3]);
+                uint8_t* dst = out + act_offset_bytes(pair, 16, chunk, act_cell(sq >> 3, bip, sq & 7));
+                *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+                // whole 32-B sectors per board row: the first / last column also store the zero border cell next to theirs
+                if ((sq & 7) == 0) *reinterpret_cast<uint4*>(dst - 16) = make_uint4(0u, 0u, 0u, 0u);
+                if ((sq & 7) == 7) *reinterpret_cast<uint4*>(dst + 16) = make_uint4(0u, 0u, 0u, 0u);
             }
         }
     }

@@ -36,6 +36,16 @@ __device__ __forceinline__ size_t cell_off(int pair, int cj, int j, int cell) { 
 constexpr int SQ_THREADS = 128;
 __device__ __forceinline__ int square_cell(int t) { return ((t >> 4) + 1) * 20 + ((t >> 3) & 1) * 10 + (t & 7) + 1; }
 
+// A board row is 8 cells = 128 bytes that start 16 bytes into a 32-byte DRAM sector (the border cell comes first): storing only
+// the squares leaves the first and last sector of every row partially written, and L2 has to fetch them from DRAM before it can
+// write them back.  The threads of the first / last column therefore also store the (zero) border cell next to theirs: every row
+// becomes five whole sectors.
+__device__ __forceinline__ void store_row_cell(uint8_t* base, size_t off, int t, const uint4& v) {
+    *reinterpret_cast<uint4*>(base + off) = v;
+    if ((t & 7) == 0) *reinterpret_cast<uint4*>(base + off - 16) = make_uint4(0u, 0u, 0u, 0u);
+    if ((t & 7) == 7) *reinterpret_cast<uint4*>(base + off + 16) = make_uint4(0u, 0u, 0u, 0u);
+}
+
 // sum over the 32 lanes of a warp of 32 values per lane, transposed: afterwards lane c holds the total of value c in v[0]
 // (butterfly with halving payload: 31 shuffles instead of 32 x 5; the same helper lives in conv.cu for the BN statistics)
 __device__ __forceinline__ void warp_transpose_sum32_t(float (&v)[32], int lane) {
@@ -94,7 +104,7 @@ __global__ void planes_from_images_kernel(const int16_t* __restrict__ img, int n
             const float hm = (float)px[118];
             v[0] = hm - __uint_as_float(__float_as_uint(hm) & 0xFFFF0000u);
         }
-        *reinterpret_cast<uint4*>(planes + cell_off(b >> 1, 16, chunk, act_cell(sq >> 3, b & 1, sq & 7))) = pack8(v);
+        store_row_cell(planes, cell_off(b >> 1, 16, chunk, act_cell(sq >> 3, b & 1, sq & 7)), sq, pack8(v));
     }
 }
 
@@ -171,7 +181,7 @@ __global__ void __launch_bounds__(SQ_THREADS) bn_apply_kernel(const uint8_t* __r
             if (skip) v += s[e];
             x[e] = v > 0.f ? v : v * slope;
         }
-        *reinterpret_cast<uint4*>(out + off) = pack8(x);
+        store_row_cell(out, off, t, pack8(x));
     }
 }
 
@@ -259,8 +269,8 @@ __global__ void __launch_bounds__(SQ_THREADS, 8) bn_bwd_apply_kernel(const uint8
             gv[e] = dz;
             o[e] = k0[e] * (dz - m1[e] - (yv[e] - mean[e]) * rstd[e] * m2[e]);
         }
-        *reinterpret_cast<uint4*>(dy + off) = pack8(o);
-        if (dz_out) *reinterpret_cast<uint4*>(dz_out + off) = pack8(gv);
+        store_row_cell(dy, off, t, pack8(o));
+        if (dz_out) store_row_cell(dz_out, off, t, pack8(gv));
     }
 }
 
@@ -620,7 +630,7 @@ __global__ void __launch_bounds__(128) head_conv_bwd_kernel(const uint8_t* __res
             // the 24 products of this chunk summed over the warp's 32 squares, transposed: lane h * 8 + e ends up with the total
             warp_transpose_sum32_t(prod, lane);
             if (lane < 24) atomicAdd(&dw[lane >> 3][j * 8 + (lane & 7)], prod[0]);
-            if (board < n) *reinterpret_cast<uint4*>(gout + off) = pack8(o);
+            if (board < n) store_row_cell(gout, off, t, pack8(o));
         }
     }
     __syncthreads();
