@@ -20,13 +20,16 @@ import bench
 from chessbot_b200.gameimage import boards_to_images
 from chessbot_b200.model import DeviceNetwork, keras_init_weights
 from chessbot_b200.train import Trainer
-from oracle import ref_train
 
 blocks, filters = (int(x) for x in a.net.split("x"))
 boards = bench.random_positions_device(min(a.pool, 512), seed=7)
 imgs = boards_to_images(boards, 8).astype(np.int16)
 imgs = np.concatenate([imgs] * (a.pool // len(imgs) + 1))[:a.pool]
-z, pi = ref_train.synthetic_targets(a.pool, 3)
+rng0 = np.random.default_rng(3)
+pi = np.zeros((a.pool, 4672), dtype=np.float32)            # sparse visit distributions (train.py:13-19 shapes)
+cols = np.stack([rng0.choice(4672, 30, replace=False) for _ in range(a.pool)])
+np.put_along_axis(pi, cols, rng0.integers(1, 50, (a.pool, 30)).astype(np.float32), axis=1)
+pi /= pi.sum(1, keepdims=True)
 z = np.sign(imgs[:, 0, 0, 112] - 0.5).astype(np.float32)                 # a learnable value target: the side to move
 tr = Trainer(keras_init_weights(filters, blocks, seed=0), filters, blocks, a.batch)
 rng = np.random.default_rng(0)
