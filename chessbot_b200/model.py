@@ -94,6 +94,41 @@ class DeviceNetwork:
         value, logits = self.predict(image)
         return {"value_head": value.cpu().numpy().reshape(-1, 1), "policy_head": logits.cpu().numpy()}
 
+    # ------------------------------------------------------------------ the Keras calls train.py makes on its model
+    def fit(self, x, y, batch_size=None, epochs=1, initial_epoch=0, shuffle=True, callbacks=None, verbose=0, rng=None):
+        """model.fit(x, {"value_head": yv, "policy_head": yp}, initial_epoch=.., epochs=.., callbacks=[lr_callback, ..]) of
+        train.py:150-164 with the compiled losses / optimizer of model.py:59-70 (chessbot_b200.train.Trainer underneath; the
+        optimizer's momentum persists between calls, like the Keras model's).  batch_size defaults to Keras' 32; one learning
+        rate per epoch from a LearningRateScheduler-like callback (anything with .schedule(epoch, lr)), else from
+        config.learning_rate (train.py:112-115).  A last partial minibatch is dropped (Keras would run it at its smaller size).
+        Afterwards this network evaluates with the trained weights.  Returns an object with .history like Keras."""
+        from .train import Trainer, scheduler
+        bs = min(32 if batch_size is None else int(batch_size), len(x))
+        tr = getattr(self, "_trainer", None)
+        if tr is None or tr.batch_size != bs:
+            tr = self._trainer = Trainer(self.weights if tr is None else tr.get_weights(), self.filters, self.blocks, bs,
+                                         device=self.engine.device_index)
+            self._lr = tr.config.learning_rate[0]
+        history = {"loss": [], "value_head_loss": [], "policy_head_loss": []}
+        for epoch in range(initial_epoch, epochs):
+            schedules = [cb.schedule for cb in (callbacks or []) if hasattr(cb, "schedule")]
+            self._lr = schedules[0](epoch, self._lr) if schedules else scheduler(epoch, self._lr, tr.config)
+            logs = tr.fit(x, y, self._lr, batch_size=bs, shuffle=shuffle, rng=rng)
+            if logs:
+                history["loss"].append(logs["loss"])
+                history["value_head_loss"].append(logs["value"])
+                history["policy_head_loss"].append(logs["policy"])
+                if verbose:
+                    print(f"Epoch {epoch + 1}/{epochs} - loss: {logs['loss']:.4f} - value_head_loss: {logs['value']:.4f} - "
+                          f"policy_head_loss: {logs['policy']:.4f} - lr: {self._lr:g}")
+        self.weights = tr.get_weights()
+        self.load()
+        return type("History", (), {"history": history, "epoch": list(range(initial_epoch, epochs))})()
+
+    def save(self, path):
+        """model.save(path) (train.py:146-148): the .npz of save_weights, loadable with load_network(path)"""
+        save_weights(path, self.weights)
+
 
 def save_weights(path, weights):
     """Checkpoint interchange (train.py:88-101,124-136 write Keras / SavedModel files, unreadable without TensorFlow):

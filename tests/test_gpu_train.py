@@ -251,3 +251,34 @@ def test_training_mode_and_inference_path_agree_once_the_running_statistics_sett
     value, _ = DeviceNetwork(after, filters, blocks, max_batch=n).predict(images)
     assert float(np.abs(value.cpu().numpy() - train_mode).max()) < 3e-2, float(np.abs(value.cpu().numpy() - train_mode).max())
     assert abs(tr.losses()["value"] - float(np.mean((train_mode - z) ** 2))) < 1e-4
+
+
+def test_device_network_fit_and_save_like_the_keras_model_in_train_py(tmp_path):
+    """train.py:150-164 calls model.fit(x, {"value_head": yv, "policy_head": yp}, initial_epoch, epochs, callbacks) and model.save on
+    its Keras model; the DeviceNetwork takes the same calls: two minibatches of 32 per epoch (Keras' default batch size on
+    config.batch_size = 64 samples), learning rate from the scheduler callback, trained weights used for inference afterwards."""
+    from chessbot_b200.model import DeviceNetwork, load_network
+    from oracle import ref_model
+    images, z, pi = _batch(64, seed=31)
+    z = np.sign(images[:, 0, 0, 112] - 0.5).astype(np.float64)
+    net = DeviceNetwork(ref_model.init_weights(48, 1, seed=4), 48, 1, max_batch=64)
+    before = net.predict(images)[0].cpu().numpy()
+    seen = []
+
+    class LrCallback:                                   # tf.keras.callbacks.LearningRateScheduler's interface
+        def schedule(self, epoch, lr):
+            seen.append((epoch, lr))
+            return 0.02
+
+    hist = None
+    for i in range(1, 31):
+        hist = net.fit(images, {"value_head": z, "policy_head": pi.astype(np.float64)}, initial_epoch=(i - 1), epochs=i, callbacks=[LrCallback()],
+                       rng=np.random.default_rng(i))
+    assert [e for e, _ in seen] == list(range(30)) and seen[0][1] == 0.1 and seen[1][1] == 0.02
+    assert net._trainer.steps == 60 and len(hist.history["loss"]) == 1
+    after = net.predict(images)[0].cpu().numpy()
+    assert float(np.mean((after - z) ** 2)) < float(np.mean((before - z) ** 2))
+    path = str(tmp_path / "model.npz")
+    net.save(path)
+    again = load_network(path, max_batch=64)
+    assert np.allclose(again.predict(images)[0].cpu().numpy(), after, atol=1e-6)
