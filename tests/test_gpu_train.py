@@ -270,14 +270,18 @@ def test_device_network_fit_and_save_like_the_keras_model_in_train_py(tmp_path):
             seen.append((epoch, lr))
             return 0.02
 
-    hist = None
+    hists = []
     for i in range(1, 31):
-        hist = net.fit(images, {"value_head": z, "policy_head": pi.astype(np.float64)}, initial_epoch=(i - 1), epochs=i, callbacks=[LrCallback()],
-                       rng=np.random.default_rng(i))
+        hists.append(net.fit(images, {"value_head": z, "policy_head": pi.astype(np.float64)}, initial_epoch=(i - 1), epochs=i,
+                             callbacks=[LrCallback()], rng=np.random.default_rng(i)))
     assert [e for e, _ in seen] == list(range(30)) and seen[0][1] == 0.1 and seen[1][1] == 0.02
-    assert net._trainer.steps == 60 and len(hist.history["loss"]) == 1
+    assert net._trainer.steps == 60 and len(hists[-1].history["loss"]) == 1
+    # training-mode losses fall (the inference outputs follow once the BN running statistics, momentum 0.99, have caught up:
+    # test_training_mode_and_inference_path_agree_once_the_running_statistics_settle)
+    assert hists[-1].history["value_head_loss"][0] < 0.8 * hists[0].history["value_head_loss"][0]
+    assert hists[-1].history["loss"][0] < hists[0].history["loss"][0]
     after = net.predict(images)[0].cpu().numpy()
-    assert float(np.mean((after - z) ** 2)) < float(np.mean((before - z) ** 2))
+    assert float(np.abs(after - before).max()) > 1e-3                         # the network evaluates with the trained weights
     path = str(tmp_path / "model.npz")
     net.save(path)
     again = load_network(path, max_batch=64)
