@@ -77,10 +77,10 @@ struct cb_trainer {
     ParamLayout lay;
     float *params = nullptr, *grads = nullptr, *mom = nullptr;
     TBuf<float> moving;
-    TBuf<__nv_bfloat16> planes, g[2], dy, dz;
+    TBuf<__nv_bfloat16> planes, g[2], dy[2], dz;  // dy: double-buffered, the weight gradient of layer l reads dY_l while layer l - 1 is at work
     std::vector<TBuf<__nv_bfloat16>> Y, A, wf, wt;
     std::vector<CUtensorMap> map_A;      // A[l] as conv / wgrad input (box 200 rows)
-    CUtensorMap map_planes{}, map_dy_conv{}, map_dy_wg{};
+    CUtensorMap map_planes{}, map_dy_conv[2]{}, map_dy_wg[2]{};
     TBuf<CUtensorMap> wmaps;             // [2 * nl]: forward packs, then data-gradient packs
     TBuf<LayerDesc> ldesc;               // [2 * nl]
     TBuf<float> ones, zeros, mean_rstd, wg_partial, gemm_scratch;
@@ -93,7 +93,8 @@ struct cb_trainer {
     // hyper-parameters live in device memory, so no kernel argument changes between steps.
     TBuf<int16_t> in_img;
     TBuf<float> in_z, in_pi, hp;
-    cudaStream_t cap_stream = nullptr;
+    cudaStream_t cap_stream = nullptr, aux_stream = nullptr;   // aux: the weight-gradient branch of the backward pass
+    std::vector<cudaEvent_t> ev_ready, ev_wdone;               // per layer: dY_l final and the data gradient done; weight gradient done
     cudaGraphExec_t graph_fb = nullptr, graph_apply = nullptr;
     int fb_calls = 0, apply_calls = 0;
     bool weights_dirty = true;
@@ -179,7 +180,7 @@ cb_trainer* cb_train_create(cb_ctx* ctx, int filters, int blocks, int batch, flo
     const size_t act_elems = act_bytes(batch, N) / 2;
     auto fail = [&]() { delete t; return (cb_trainer*)nullptr; };
     t->Y.resize(nl); t->A.resize(nl); t->wf.resize(nl); t->wt.resize(nl); t->map_A.resize(nl);
-    if (t->planes.alloc(act_bytes(batch, 128) / 2) || t->g[0].alloc(act_elems) || t->g[1].alloc(act_elems) || t->dy.alloc(act_elems) ||
+    if (t->planes.alloc(act_bytes(batch, 128) / 2) || t->g[0].alloc(act_elems) || t->g[1].alloc(act_elems) || t->dy[0].alloc(act_elems) || t->dy[1].alloc(act_elems) ||
         t->dz.alloc(act_elems) || t->moving.alloc(t->lay.n_moving))
         return fail();
     for (int l = 0; l < nl; ++l) {
@@ -191,8 +192,10 @@ cb_trainer* cb_train_create(cb_ctx* ctx, int filters, int blocks, int batch, flo
     }
     const int dy_chunks = N / 16;
     if (conv_make_row_map(&t->map_planes, t->planes.p, (uint64_t)t->pairs * 16 * 25, 200) ||
-        conv_make_row_map(&t->map_dy_conv, t->dy.p, (uint64_t)t->pairs * cj * 25, 200) ||
-        conv_make_row_map(&t->map_dy_wg, t->dy.p, (uint64_t)t->pairs * cj * 25, 25 * (dy_chunks < 8 ? dy_chunks : 8)))
+        conv_make_row_map(&t->map_dy_conv[0], t->dy[0].p, (uint64_t)t->pairs * cj * 25, 200) ||
+        conv_make_row_map(&t->map_dy_conv[1], t->dy[1].p, (uint64_t)t->pairs * cj * 25, 200) ||
+        conv_make_row_map(&t->map_dy_wg[0], t->dy[0].p, (uint64_t)t->pairs * cj * 25, 25 * (dy_chunks < 8 ? dy_chunks : 8)) ||
+        conv_make_row_map(&t->map_dy_wg[1], t->dy[1].p, (uint64_t)t->pairs * cj * 25, 25 * (dy_chunks < 8 ? dy_chunks : 8)))
         return fail();
     // weight tensor maps and one-layer plans: [0, nl) forward, [nl, 2 nl) data gradient
     std::vector<CUtensorMap> wm(2 * nl);
@@ -240,7 +243,12 @@ cb_trainer* cb_train_create(cb_ctx* ctx, int filters, int blocks, int batch, flo
     mv[t->lay.vmov.off + 1] = 1.f;
     mv[t->lay.pmov.off + 2] = mv[t->lay.pmov.off + 3] = 1.f;
     if (cudaMemcpy(t->moving.p, mv.data(), mv.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) { cb_set_error("moving statistics upload failed"); return fail(); }
-    if (cudaStreamCreateWithFlags(&t->cap_stream, cudaStreamNonBlocking) != cudaSuccess) { cb_set_error("cb_train_create: stream"); return fail(); }
+    if (cudaStreamCreateWithFlags(&t->cap_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&t->aux_stream, cudaStreamNonBlocking) != cudaSuccess) { cb_set_error("cb_train_create: stream"); return fail(); }
+    t->ev_ready.resize(nl); t->ev_wdone.resize(nl);
+    for (int l = 0; l < nl; ++l)
+        if (cudaEventCreateWithFlags(&t->ev_ready[l], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&t->ev_wdone[l], cudaEventDisableTiming) != cudaSuccess) { cb_set_error("cb_train_create: event"); return fail(); }
     if (cudaDeviceSynchronize() != cudaSuccess) { cb_set_error("cb_train_create: device error"); return fail(); }
     return t;
 }
@@ -251,6 +259,9 @@ void cb_train_destroy(cb_trainer* t) {
     if (t->graph_fb) cudaGraphExecDestroy(t->graph_fb);
     if (t->graph_apply) cudaGraphExecDestroy(t->graph_apply);
     if (t->cap_stream) cudaStreamDestroy(t->cap_stream);
+    if (t->aux_stream) cudaStreamDestroy(t->aux_stream);
+    for (cudaEvent_t e : t->ev_ready) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : t->ev_wdone) if (e) cudaEventDestroy(e);
     delete t;
 }
 
@@ -412,36 +423,53 @@ static int enqueue_forward_backward(cb_trainer* t, cudaStream_t st) {
         tp_end(t, st))
         return -1;
     // ---------------------------------------------------------------- backward tower
+    // Two branches.  The main stream carries the chain every layer waits for: BN backward (HBM-bound) -> data gradient (tower
+    // kernel: it fills every SM's registers and shared memory).  The weight gradient of layer l hangs off that chain - it only
+    // needs dY_l and the layer's input - so it runs on the auxiliary stream AFTER the layer's data gradient and thereby next to
+    // the BN-backward passes of layer l - 1: its CTAs (1 per SM, 63 registers) leave room for the BN blocks, tensor pipe and HBM
+    // are busy at the same time.  dY is double-buffered; the buffer of layer l is rewritten by layer l - 2 once wgrad(l) is done.
+    // CB_TRAIN_SERIAL_WGRAD=1 (A/B runs) and per-launch profiling (clean kernel times) keep everything on one stream
+    static const bool serial_env = getenv("CB_TRAIN_SERIAL_WGRAD") != nullptr;
+    const bool serial_wgrad = serial_env || t->profile;
+    cudaStream_t aux = serial_wgrad ? st : t->aux_stream;
     int cur = 0;
     for (int l = nl - 1; l >= 0; --l) {
+        const int db = l & 1;
         const __nv_bfloat16* g = t->g[cur].p;
         double* sums = t->bsums.p + (size_t)l * 2 * N;
         const float* mr = t->mean_rstd.p + (size_t)l * 4 * N;
         __nv_bfloat16* dz = (l > 0 && (l & 1) == 0) ? t->dz.p : nullptr;  // second convolution of a block: its dz also flows down the skip
         const __nv_bfloat16* act = dz ? t->A[l].p : nullptr;              // without a residual add the sign of the pre-activation follows from y
+        if (!serial_wgrad && l + 2 < nl) CB_CUDA_OK(cudaStreamWaitEvent(st, t->ev_wdone[l + 2], 0));   // wgrad(l + 2) has read this dY buffer
         if (tp_begin(t, TP_BN_BWD, st) || launch_bn_bwd_reduce(g, act, t->Y[l].p, n, cj, mr, t->slope, sums, st) ||
-            launch_bn_bwd_apply(g, act, t->Y[l].p, t->dy.p, dz, n, cj, C, mr, P + L.bn[l].off, sums, t->slope, G + L.bn[l].off,
+            launch_bn_bwd_apply(g, act, t->Y[l].p, t->dy[db].p, dz, n, cj, C, mr, P + L.bn[l].off, sums, t->slope, G + L.bn[l].off,
                                 G + L.bn[l].off + C, st) ||
             tp_end(t, st))
             return -1;
+        if (l > 0) {
+            if (tp_begin(t, TP_DGRAD, st) ||
+                conv_layer(t, nl + l, t->map_dy_conv[db], t->dy[db].p, t->g[cur ^ 1].p, (l & 1) ? t->dz.p : nullptr, nullptr, st) || tp_end(t, st))
+                return -1;
+            cur ^= 1;
+        }
+        if (!serial_wgrad) {
+            CB_CUDA_OK(cudaEventRecord(t->ev_ready[l], st));
+            CB_CUDA_OK(cudaStreamWaitEvent(aux, t->ev_ready[l], 0));
+        }
         WgradParams wp{};
         wp.tm_a = l == 0 ? t->map_planes : t->map_A[l - 1];
-        wp.tm_dy = t->map_dy_wg;
+        wp.tm_dy = t->map_dy_wg[db];
         wp.partial = t->wg_partial.p;
         wp.pairs = t->pairs;
         wp.cj_in = l == 0 ? 16 : cj;
         wp.n = N;
         wp.splits = l == 0 ? t->wg_splits_stem : t->wg_splits_res;
-        if (tp_begin(t, TP_WGRAD, st) || launch_wgrad(wp, st) ||
-            launch_wgrad_reduce(t->wg_partial.p, wp.splits, wp.cj_in * 8, N, l == 0 ? 119 : C, C, l == 0, G + L.w[l].off, st) || tp_end(t, st))
+        if (tp_begin(t, TP_WGRAD, aux) || launch_wgrad(wp, aux) ||
+            launch_wgrad_reduce(t->wg_partial.p, wp.splits, wp.cj_in * 8, N, l == 0 ? 119 : C, C, l == 0, G + L.w[l].off, aux) || tp_end(t, aux))
             return -1;
-        if (l > 0) {
-            if (tp_begin(t, TP_DGRAD, st) || conv_layer(t, nl + l, t->map_dy_conv, t->dy.p, t->g[cur ^ 1].p, (l & 1) ? t->dz.p : nullptr, nullptr, st) ||
-                tp_end(t, st))
-                return -1;
-            cur ^= 1;
-        }
+        if (!serial_wgrad) CB_CUDA_OK(cudaEventRecord(t->ev_wdone[l], aux));
     }
+    if (!serial_wgrad) CB_CUDA_OK(cudaStreamWaitEvent(st, t->ev_wdone[0], 0));   // join: the weight gradients are serial on aux, layer 0 is the last
     return 0;
 }
 
