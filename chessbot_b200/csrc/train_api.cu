@@ -86,7 +86,7 @@ struct cb_trainer {
     TBuf<float> ones, zeros, mean_rstd, wg_partial, gemm_scratch;
     TBuf<double> stats, bsums, hstats, hsums, losses;
     TBuf<int> flags;
-    int epoch = 0, wg_splits_stem = 1, wg_splits_res = 1;
+    int wg_splits_stem = 1, wg_splits_res = 1;
     TBuf<float> head_raw, hmr, vfeat, pfeat, h1pre, value, logits, dpfeat, dvfeat, dh1pre, dpre;
     // the step's launch sequence is the same every time: after one eager step it is captured into two CUDA graphs (forward +
     // backward; optimizer + weight packing) and replayed.  Inputs are staged into trainer-owned buffers, the optimizer's
