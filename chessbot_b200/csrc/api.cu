@@ -459,8 +459,8 @@ int cb_debug_wgrad(cb_ctx* ctx, const void* in_act_dev, const void* dy_act_dev, 
     WgradParams wp{};
     wp.pairs = pairs; wp.cj_in = cj_in; wp.n = n; wp.splits = wgrad_splits(ctx->sms, cj_in);
     const int dy_chunks = n / 16;
-    if (conv_make_chunk_map(&wp.tm_a, in_act_dev, (uint64_t)pairs * cj_in, WG_A_ROWS, 8) ||
-        conv_make_chunk_map(&wp.tm_dy, dy_act_dev, (uint64_t)pairs * (n / 8), WG_DY_ROWS, dy_chunks < 8 ? dy_chunks : 8))
+    if (conv_make_row_map(&wp.tm_a, in_act_dev, (uint64_t)pairs * cj_in * 25, 200) ||
+        conv_make_row_map(&wp.tm_dy, dy_act_dev, (uint64_t)pairs * (n / 8) * 25, 25 * (dy_chunks < 8 ? dy_chunks : 8)))
         return -1;
     DevBuf<float> partial;
     if (partial.alloc((size_t)wp.splits * 9 * cin_pad * n, false)) return -1;

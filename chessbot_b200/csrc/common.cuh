@@ -154,20 +154,6 @@ __device__ __forceinline__ void tma_load_2d_multicast(void* dst_smem, const void
         "l"(tensor_map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
         : "memory");
 }
-// 3-D variants (wgrad.cu: a sub-range of the 25 rows of several consecutive chunks)
-__device__ __forceinline__ void tma_load_3d(void* dst_smem, const void* tensor_map, int c0, int c1, int c2, uint64_t* bar) {
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-                     smem_u32(dst_smem)),
-                 "l"(tensor_map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-                 : "memory");
-}
-__device__ __forceinline__ void tma_load_3d_multicast(void* dst_smem, const void* tensor_map, int c0, int c1, int c2, uint64_t* bar, uint16_t cta_mask) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(
-            smem_u32(dst_smem)),
-        "l"(tensor_map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask)
-        : "memory");
-}
 __device__ __forceinline__ void tma_prefetch_desc(const void* tensor_map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tensor_map) : "memory");
 }

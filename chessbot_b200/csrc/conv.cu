@@ -493,28 +493,6 @@ static int make_row_map(CUtensorMap* tm, const void* base, uint64_t rows, uint32
 
 int conv_make_row_map(CUtensorMap* tm, const void* base, uint64_t rows, uint32_t box_rows) { return make_row_map(tm, base, rows, box_rows); }
 
-// 3-D tensor map over a tile-native buffer seen as [chunks][25 rows][128 B] (one 8-channel chunk of a board pair = 25 rows of 8
-// cells): a box of `box_rows` rows of `box_chunks` consecutive chunks lands densely in shared memory, chunk stride box_rows * 128 B.
-// wgrad.cu loads HALF a board pair per pipeline stage with it (the rows of four board rows plus the halo).
-int conv_make_chunk_map(CUtensorMap* tm, const void* base, uint64_t chunks, uint32_t box_rows, uint32_t box_chunks) {
-    static EncodeTiledFn encode = nullptr;
-    if (!encode) {
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        CB_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-        if (!fn || qres != cudaDriverEntryPointSuccess) { cb_set_error("cuTensorMapEncodeTiled not available"); return -1; }
-        encode = (EncodeTiledFn)fn;
-    }
-    const cuuint64_t dims[3] = {64, 25, chunks};
-    const cuuint64_t strides[2] = {128, ACT_CHUNK_BYTES};
-    const cuuint32_t box[3] = {64, box_rows, box_chunks};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { cb_set_error("cuTensorMapEncodeTiled (3-D) failed: " + std::to_string((int)r)); return -1; }
-    return 0;
-}
-
 int launch_tower(const TowerParams& p, int num_sms, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {

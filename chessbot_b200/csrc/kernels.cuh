@@ -146,8 +146,8 @@ struct SearchParams {
 
 // Weight gradient of one 3x3 convolution (wgrad.cu)
 struct WgradParams {
-    CUtensorMap tm_a;    // layer input (tile-native, cj_in chunks per board pair): conv_make_chunk_map(.., WG_A_ROWS = 15, 8 chunks)
-    CUtensorMap tm_dy;   // gradient of the layer's raw output (n/8 chunks per pair): conv_make_chunk_map(.., WG_DY_ROWS = 11, min(8, n/16) chunks)
+    CUtensorMap tm_a;    // layer input (tile-native, cj_in chunks per board pair) as rows of 128 B, box = 200 rows (64 channels of a pair)
+    CUtensorMap tm_dy;   // gradient of the layer's raw output (n/8 chunks per pair), box = 25 * min(8, n/16) rows
     float* partial;      // [splits][9][cj_in*8][n] f32 partial sums
     int pairs;           // board pairs in the batch
     int cj_in;           // input channels / 8: 8, 16 or 32
@@ -156,13 +156,11 @@ struct WgradParams {
 };
 
 int launch_tower(const TowerParams& p, int num_sms, cudaStream_t stream);
-constexpr int WG_A_ROWS = 15, WG_DY_ROWS = 11;  // 128-byte rows per chunk in a half-pair stage of wgrad.cu
 int wgrad_splits(int num_sms, int cj_in);
 int launch_wgrad(const WgradParams& p, cudaStream_t stream);
 int launch_wgrad_reduce(const float* partial, int splits, int ci_pad, int n, int cin, int c, int stem, float* out, cudaStream_t stream);
 int launch_wgrad_reference(const __nv_bfloat16* in, const __nv_bfloat16* dy, int pairs, int cj_in, int n, float* out, cudaStream_t stream);
 int conv_make_row_map(CUtensorMap* tm, const void* base, uint64_t rows, uint32_t box_rows);
-int conv_make_chunk_map(CUtensorMap* tm, const void* base, uint64_t chunks, uint32_t box_rows, uint32_t box_chunks);
 int launch_conv3x3_reference(const ConvParams& p, cudaStream_t stream);
 // training step (train.cu)
 int launch_planes_from_images(const int16_t* img, int n, __nv_bfloat16* planes, cudaStream_t st);

@@ -79,9 +79,7 @@ struct cb_trainer {
     TBuf<float> moving;
     TBuf<__nv_bfloat16> planes, g[2], dy[2], dz;  // dy: double-buffered, the weight gradient of layer l reads dY_l while layer l - 1 is at work
     std::vector<TBuf<__nv_bfloat16>> Y, A, wf, wt;
-    std::vector<CUtensorMap> map_A;      // A[l] as conv input (rows of 128 B, box 200 rows)
-    std::vector<CUtensorMap> map_A3;     // A[l] as wgrad input (3-D chunk map, half-pair boxes)
-    CUtensorMap map_planes3{};
+    std::vector<CUtensorMap> map_A;      // A[l] as conv / wgrad input (box 200 rows)
     CUtensorMap map_planes{}, map_dy_conv[2]{}, map_dy_wg[2]{};
     TBuf<CUtensorMap> wmaps;             // [2 * nl]: forward packs, then data-gradient packs
     TBuf<LayerDesc> ldesc;               // [2 * nl]
@@ -181,7 +179,7 @@ cb_trainer* cb_train_create(cb_ctx* ctx, int filters, int blocks, int batch, flo
     const int nl = t->nl, cj = N / 8;
     const size_t act_elems = act_bytes(batch, N) / 2;
     auto fail = [&]() { delete t; return (cb_trainer*)nullptr; };
-    t->Y.resize(nl); t->A.resize(nl); t->wf.resize(nl); t->wt.resize(nl); t->map_A.resize(nl); t->map_A3.resize(nl);
+    t->Y.resize(nl); t->A.resize(nl); t->wf.resize(nl); t->wt.resize(nl); t->map_A.resize(nl);
     if (t->planes.alloc(act_bytes(batch, 128) / 2) || t->g[0].alloc(act_elems) || t->g[1].alloc(act_elems) || t->dy[0].alloc(act_elems) || t->dy[1].alloc(act_elems) ||
         t->dz.alloc(act_elems) || t->moving.alloc(t->lay.n_moving))
         return fail();
@@ -190,17 +188,14 @@ cb_trainer* cb_train_create(cb_ctx* ctx, int filters, int blocks, int batch, flo
         if (t->Y[l].alloc(act_elems) || t->A[l].alloc(act_elems) || t->wf[l].alloc((size_t)kc * 9 * N * 64) ||
             (l > 0 && t->wt[l].alloc((size_t)(N / 64) * 9 * N * 64)))
             return fail();
-        if (conv_make_row_map(&t->map_A[l], t->A[l].p, (uint64_t)t->pairs * cj * 25, 200) ||
-            conv_make_chunk_map(&t->map_A3[l], t->A[l].p, (uint64_t)t->pairs * cj, WG_A_ROWS, 8))
-            return fail();
+        if (conv_make_row_map(&t->map_A[l], t->A[l].p, (uint64_t)t->pairs * cj * 25, 200)) return fail();
     }
     const int dy_chunks = N / 16;
     if (conv_make_row_map(&t->map_planes, t->planes.p, (uint64_t)t->pairs * 16 * 25, 200) ||
         conv_make_row_map(&t->map_dy_conv[0], t->dy[0].p, (uint64_t)t->pairs * cj * 25, 200) ||
         conv_make_row_map(&t->map_dy_conv[1], t->dy[1].p, (uint64_t)t->pairs * cj * 25, 200) ||
-        conv_make_chunk_map(&t->map_planes3, t->planes.p, (uint64_t)t->pairs * 16, WG_A_ROWS, 8) ||
-        conv_make_chunk_map(&t->map_dy_wg[0], t->dy[0].p, (uint64_t)t->pairs * cj, WG_DY_ROWS, dy_chunks < 8 ? dy_chunks : 8) ||
-        conv_make_chunk_map(&t->map_dy_wg[1], t->dy[1].p, (uint64_t)t->pairs * cj, WG_DY_ROWS, dy_chunks < 8 ? dy_chunks : 8))
+        conv_make_row_map(&t->map_dy_wg[0], t->dy[0].p, (uint64_t)t->pairs * cj * 25, 25 * (dy_chunks < 8 ? dy_chunks : 8)) ||
+        conv_make_row_map(&t->map_dy_wg[1], t->dy[1].p, (uint64_t)t->pairs * cj * 25, 25 * (dy_chunks < 8 ? dy_chunks : 8)))
         return fail();
     // weight tensor maps and one-layer plans: [0, nl) forward, [nl, 2 nl) data gradient
     std::vector<CUtensorMap> wm(2 * nl);
@@ -462,7 +457,7 @@ static int enqueue_forward_backward(cb_trainer* t, cudaStream_t st) {
             CB_CUDA_OK(cudaStreamWaitEvent(aux, t->ev_ready[l], 0));
         }
         WgradParams wp{};
-        wp.tm_a = l == 0 ? t->map_planes3 : t->map_A3[l - 1];
+        wp.tm_a = l == 0 ? t->map_planes : t->map_A[l - 1];
         wp.tm_dy = t->map_dy_wg[db];
         wp.partial = t->wg_partial.p;
         wp.pairs = t->pairs;

@@ -20,13 +20,9 @@
 namespace cb {
 
 constexpr int WG_THREADS = 192;  // warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..5 = epilogue (one per TMEM lane quarter)
-// A pipeline stage holds HALF a board pair: the cells of four board rows of both boards, i.e. of every 8-channel chunk the
-// 128-byte rows [10 h, 10 h + 15) of the input (two halo rows included) and [10 h + 2, 10 h + 13) of dY (3-D tensor maps,
-// conv_make_chunk_map).  Four stages of 52 KB instead of two of 102 KB: twice as many loads in flight per SM.
-constexpr int WG_STAGES = 4;
-constexpr int WG_A_CHUNK = WG_A_ROWS * 128, WG_DY_CHUNK = WG_DY_ROWS * 128;  // bytes per chunk in shared memory: 1920 / 1408
-constexpr int WG_A_BYTES = 16 * WG_A_CHUNK;   // 128 input channels
-constexpr int WG_B_BYTES = 16 * WG_DY_CHUNK;  // up to 128 output channels
+constexpr int WG_STAGES = 2;
+constexpr int WG_A_BYTES = 2 * ACT_K64_BYTES;  // 128 input channels of a board pair
+constexpr int WG_B_BYTES = 2 * ACT_K64_BYTES;  // up to 128 output channels of the pair
 constexpr int WG_STAGE_BYTES = WG_A_BYTES + WG_B_BYTES;
 struct WgradSmem {
     uint64_t full[WG_STAGES], empty[WG_STAGES], acc_full;
@@ -48,9 +44,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WG_THREADS, 1) wgrad
     const int a_blocks = p.cj_in >= 16 ? 2 : 1;  // 64-channel blocks in the input tile (a 64-channel layer has one)
     const int dy_chunks = nh >> 3;               // 8-channel chunks of this CTA's dY half: 16, 8 or 4
     const int dy_copies = (dy_chunks + 7) >> 3;
-    const int dy_box = dy_chunks < 8 ? dy_chunks : 8;  // chunks per dY copy (the tensor map's box)
-    const uint32_t stage_tx = (uint32_t)(a_blocks * 8 * WG_A_CHUNK + dy_chunks * WG_DY_CHUNK);
-    const int n_stages = 2 * (hi - lo);  // half pairs
+    const uint32_t stage_tx = (uint32_t)(a_blocks * ACT_K64_BYTES + dy_chunks * ACT_CHUNK_BYTES);
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < WG_STAGES; ++i) { ptx::mbar_init(&s->full[i], 1); ptx::mbar_init(&s->empty[i], 2); }
@@ -70,30 +64,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WG_THREADS, 1) wgrad
     if (warp == 0) {
         // ---------------------------------------------------------------- TMA producer
         if (lane == 0) { ptx::tma_prefetch_desc(&p.tm_a); ptx::tma_prefetch_desc(&p.tm_dy); }
-        for (int k = 0; k < n_stages; ++k) {
-            const int it = lo + (k >> 1), h = k & 1, st = k % WG_STAGES;
+        for (int it = lo; it < hi; ++it) {
+            const int k = it - lo, st = k % WG_STAGES;
             ptx::mbar_wait(&s->empty[st], ((k / WG_STAGES) & 1) ^ 1);
             if (ptx::elect_one()) {
                 uint8_t* a_dst = stages + st * WG_STAGE_BYTES;
                 uint8_t* b_dst = a_dst + WG_A_BYTES;
                 ptx::mbar_expect_tx(&s->full[st], stage_tx);
-                // coordinates: (element, row within the chunk, chunk); a chunk of 8 channels of a board pair = 25 rows of 128 B
+                // rows of 128 B: one 8-channel chunk of a board pair = 25 rows
                 if (a_blocks == 2)
-                    ptx::tma_load_3d_multicast(a_dst + rank * 8 * WG_A_CHUNK, &p.tm_a, 0, 10 * h, it * p.cj_in + 16 * ci_block + 8 * (int)rank,
+                    ptx::tma_load_2d_multicast(a_dst + rank * ACT_K64_BYTES, &p.tm_a, 0, (it * p.cj_in + 16 * ci_block + 8 * (int)rank) * 25,
                                                &s->full[st], 3);
                 else if (rank == 0)
-                    ptx::tma_load_3d_multicast(a_dst, &p.tm_a, 0, 10 * h, it * p.cj_in, &s->full[st], 3);
+                    ptx::tma_load_2d_multicast(a_dst, &p.tm_a, 0, it * p.cj_in * 25, &s->full[st], 3);
                 for (int c = 0; c < dy_copies; ++c)
-                    ptx::tma_load_3d(b_dst + c * 8 * WG_DY_CHUNK, &p.tm_dy, 0, 10 * h + 2, it * (p.n >> 3) + (int)rank * dy_chunks + dy_box * c,
-                                     &s->full[st]);
+                    ptx::tma_load_2d(b_dst + c * ACT_K64_BYTES, &p.tm_dy, 0, (it * (p.n >> 3) + (int)rank * dy_chunks + 8 * c) * 25, &s->full[st]);
             }
             __syncwarp();
         }
     } else if (warp == 1) {
         // ---------------------------------------------------------------- MMA issuer
         const uint32_t idesc = ptx::idesc_bf16_f32_mn(128, nh);
-        for (int k = 0; k < n_stages; ++k) {
-            const int st = k % WG_STAGES;
+        for (int it = lo; it < hi; ++it) {
+            const int k = it - lo, st = k % WG_STAGES;
             ptx::mbar_wait(&s->full[st], (k / WG_STAGES) & 1);
             ptx::tc_fence_after();
             const uint32_t a_base = ptx::smem_u32(stages + st * WG_STAGE_BYTES), b_base = a_base + WG_A_BYTES;
@@ -101,9 +94,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WG_THREADS, 1) wgrad
 #pragma unroll
                 for (int t = 0; t < 3; ++t) {
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {  // K = 16 squares: one board row of both boards; cells relative to the stage's first row
-                        const uint64_t a_desc = ptx::smem_desc(a_base + (uint32_t)(trow * 20 + t + ks * 20) * 16, 160, WG_A_CHUNK);
-                        const uint64_t b_desc = ptx::smem_desc(b_base + (uint32_t)(5 + ks * 20) * 16, 160, WG_DY_CHUNK);
+                    for (int ks = 0; ks < 8; ++ks) {  // K = 16 squares: board row ks of both boards
+                        const uint64_t a_desc = ptx::smem_desc(a_base + (uint32_t)(trow * 20 + t + ks * 20) * 16, 160, ACT_CHUNK_BYTES);
+                        const uint64_t b_desc = ptx::smem_desc(b_base + (uint32_t)(21 + ks * 20) * 16, 160, ACT_CHUNK_BYTES);
                         ptx::umma_bf16(tmem + (uint32_t)(t * nh), a_desc, b_desc, idesc, (k | ks) != 0);
                     }
                 }
