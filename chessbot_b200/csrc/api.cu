@@ -353,6 +353,7 @@ static int net_tower(cb_ctx* ctx, const void* planes_act_dev, int n, float* valu
     tp.head_w = net.head_w.p;
     tp.head_out = net.head_raw.p;
     tp.n_boards_dev = n_dev;
+    tp.full_sectors = 3 * act_bytes(n, net.cpad) > ((size_t)96 << 20);  // three rotating activation buffers that do not fit the 126 MB L2
     tp.flags = net.flags.p;
     tp.epoch = net.epoch;
     tp.nl = (int)net.layers.size();

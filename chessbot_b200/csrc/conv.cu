@@ -360,9 +360,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
                                 *reinterpret_cast<uint4*>(dst) = o;
                                 // a board row (8 cells, 128 B) starts 16 B into a 32-B sector: the first / last column also store the zero
                                 // border cell next to theirs, so every row is five WHOLE sectors and L2 never has to fetch a partially
-                                // written sector from DRAM before writing it back
-                                if (col == 0) *reinterpret_cast<uint4*>(dst - 16) = make_uint4(0u, 0u, 0u, 0u);
-                                if (col == 7) *reinterpret_cast<uint4*>(dst + 16) = make_uint4(0u, 0u, 0u, 0u);
+                                // written sector from DRAM before writing it back (only where the tensors overflow L2: TowerParams::full_sectors)
+                                if (p.full_sectors) {
+                                    if (col == 0) *reinterpret_cast<uint4*>(dst - 16) = make_uint4(0u, 0u, 0u, 0u);
+                                    if (col == 7) *reinterpret_cast<uint4*>(dst + 16) = make_uint4(0u, 0u, 0u, 0u);
+                                }
                                 if constexpr (STATS) {  // statistics of what was stored (bf16), as the BN pass will read it back
                                     const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll

@@ -44,6 +44,8 @@ struct TowerParams {
     float* head_out;            // [boards][64][3]
     double* stats;              // training forward (one layer per launch, no skip): [2][n] per-channel sum / sum of squares of the
                                 // bf16-rounded outputs, accumulated on top of what is there; nullptr otherwise
+    int full_sectors;           // epilogue also stores the zero border cells beside the first / last column (whole 32-B DRAM sectors per board
+                                // row): set when the activations do not stay in L2 anyway; costs store issue slots narrow layers cannot spare
     const int* n_boards_dev;    // search loop: number of boards actually in the batch this step (device-side, <= 2 * pairs); nullptr = 2 * pairs
     int* flags;                 // [2 * units] progress of every board pair: epoch * 256 + layers finished
     int epoch;                  // increases with every launch, so flags never need clearing

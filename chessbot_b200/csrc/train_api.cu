@@ -137,6 +137,7 @@ static int conv_layer(cb_trainer* t, int desc, const CUtensorMap& in_map, const 
     tp.head_w = nullptr;
     tp.head_out = nullptr;
     tp.stats = stats;  // forward pass: the epilogue gathers the layer's batch statistics
+    tp.full_sectors = act_bytes(t->batch, t->N) > ((size_t)32 << 20);  // a layer's tensors are read back after ~10 other tensors were streamed
     tp.flags = t->flags.p;
     tp.epoch = 1;
     tp.nl = 1;
