@@ -46,12 +46,37 @@ def conv_flops_per_position(filters, blocks, in_channels=119):
     return 2 * 64 * 9 * filters * (in_channels + 2 * blocks * filters)
 
 
-def measured_peaks():
+def measured_peaks(timed_s=None):
+    """(bf16 TFLOP/s peak to compare with, HBM GB/s, source, {"burst": .., "sustained": ..}).  MEASURED_PEAKS.json holds two bf16
+    figures: the burst one (a kernel timed alone / a timed region under ~1 s, before the power cap pulls the clock down) and the
+    sustained one (a kernel inside a long step).  The one used follows the DURATION of the timed region."""
     try:
         p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        return float(p["bf16_tflops_sustained"]), float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json, sustained bf16)"
+        both = {"burst": float(p["bf16_tflops"]), "sustained": float(p["bf16_tflops_sustained"])}
+        hbm, src = float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
-        return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+        both, hbm, src = {"burst": 1650.0, "sustained": 1400.0}, 6650.0, "fallback (B200_PROFILING.md)"
+    kind = "sustained" if (timed_s is None or timed_s >= 1.0) else "burst"
+    return both[kind], hbm, f"{src}, {kind} bf16 figure (timed region {timed_s if timed_s is None else round(timed_s, 3)} s)", both
+
+
+def profiled_traffic(kernel_substr, pattern="r*_ncu_full_raw*tower*.csv"):
+    """DRAM read + write bytes per launch of a kernel from the newest committed `ncu --set full` raw page under profiles/ (a number
+    taken under the profiler, on an earlier run of the same kernel: labelled as such, never measured inside this run)."""
+    import csv
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", pattern)), reverse=True):
+        try:
+            rows = list(csv.reader(open(path)))
+            hdr, units = rows[0], rows[1]
+            ir, iw, ik = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
+            mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            for r in rows[2:]:
+                if kernel_substr in r[ik]:
+                    return float(r[ir]) * mult[units[ir]] + float(r[iw]) * mult[units[iw]], os.path.relpath(path, ROOT)
+        except Exception:
+            continue
+    return None, None
 
 
 # ------------------------------------------------------------------------------------------ inputs
@@ -209,6 +234,28 @@ def cpu_baseline_leg(filters, blocks, budget_s=12.0, sims=16):
                       f"1 process, {dt:.1f} s (python-chess/TensorFlow replaced by the oracle shims)"}
 
 
+def parity_leg(eng, net, records, n):
+    """Checker leg, outside every timed region (the oracle is test infrastructure: it checks, it is never what is measured): the
+    network and the positions this run timed, device logits / values against the torch-fp32 oracle (oracle/ref_model.py, TF32 off,
+    on the GPU through torch).  north_star tolerance: 2e-2 abs."""
+    import torch
+    from oracle import ref_model
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    net.ensure_loaded()
+    pos, fi = eng.upload_records(records)
+    act, i16 = eng.encode(pos, fi, want_act=True, want_i16=True)
+    value, _, lf = eng.forward(act, n, want_bf16=False, want_f32=True)
+    torch.cuda.synchronize()
+    v_ref, p_ref = ref_model.forward(net.weights, i16.cpu().numpy(), device="cuda")
+    dp, dv = np.abs(lf.cpu().numpy() - p_ref), np.abs(value.cpu().numpy() - v_ref)
+    return {"n": int(n), "max_dlogit": float(dp.max()), "p999_dlogit": float(np.quantile(dp, 0.999)), "rms_dlogit": float(np.sqrt(np.mean(dp ** 2))),
+            "max_dvalue": float(dv.max()), "top1_agree": float((lf.cpu().numpy().argmax(1) == p_ref.argmax(1)).mean()), "tolerance_abs": 2e-2,
+            "holds": bool(dp.max() <= 2e-2 and dv.max() <= 2e-2),
+            "against": "oracle/ref_model.py (torch fp32, TF32 off) on the positions and weights of the timed run; residual stream "
+                       + ("bf16 hi + lo" if net.stream_hi_lo else "bf16")}
+
+
 def run_reference_arm(args):
     """`--impl reference`: the reference CPU path on all host cores: P independent processes (the
     reference's own scaling axis is num_actors processes, train.py:173,198-201), each step = P bounded
@@ -269,7 +316,7 @@ def run_gpu_arm(args):
     W, K = args.warmup, args.steps
     eng = Engine.get(local_rank)
     net = DeviceNetwork(trained_like_bn(keras_init_weights(filters, blocks, seed=0), filters, blocks), filters, blocks,
-                        max_batch=trees, device=local_rank)
+                        max_batch=trees, device=local_rank, stream_hi_lo=args.stream == "hilo")
     boards = random_positions_device(trees, seed=1000 + rank)   # every rank searches its own shard of games
     records = [b.export_record() for b in boards]
     total_steps = W + 2 * K + 4
@@ -304,18 +351,24 @@ def run_gpu_arm(args):
     if c1["errors"]:
         raise RuntimeError("search pool exhausted during the bench")
 
-    # roofline leg: the same K steps again with CUDA events (on the launching stream) around every kernel launch
+    # roofline leg: the same K steps again with CUDA events (on the launching stream) around every kernel launch; the pass is also
+    # timed as a whole, so the kernels' shares refer to THIS pass (per-launch events cost it a few per cent against the timed one)
     nodes0 = int(eng.search_read_roots()["nodes"].sum())
     eng.profile(True)
+    pv0, pv1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    pv0.record(stream)
     eng.search_run(K)
+    pv1.record(stream)
     prof = eng.profile_read()
+    prof_pass_ms = pv0.elapsed_time(pv1)
     eng.profile(False)
     c2 = eng.search_status()
     nodes1 = int(eng.search_read_roots()["nodes"].sum())
     conv_ms, conv_launches = prof["conv"]
     evals_prof = c2["evals"] - c1["evals"]                                           # boards the tower really evaluated in this pass (terminal
     conv_flops_launch_total = conv_flops_per_position(filters, blocks) * evals_prof   # leaves need none): algorithmic direct-conv FLOPs
-    peak_tf, peak_gbs, peak_src = measured_peaks()
+    peak_tf, peak_gbs, peak_src, peak_both = measured_peaks(ms * 1e-3)
     achieved_tf = conv_flops_launch_total / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     # HBM-bound kernels, algorithmic bytes as stated in DESIGN.md §4
     enc_bytes = 17152.0 * evals_prof                                            # 8 x 96 B frames read + 128 ch bf16 written
@@ -323,47 +376,72 @@ def run_gpu_arm(args):
     kernels = {}
     for name, nbytes in (("encode", enc_bytes), ("mcts_step", mcts_bytes), ("heads", None)):
         ms_k, n_k = prof["heads" if name == "heads" else name]
-        kernels[name] = {"launches": n_k, "avg_us": 1e3 * ms_k / max(n_k, 1), "share_of_step": ms_k / sum(v[0] for v in prof.values())}
+        kernels[name] = {"launches": n_k, "avg_us": 1e3 * ms_k / max(n_k, 1), "share_of_step": ms_k / prof_pass_ms}
         if nbytes:
             gbs = nbytes / (ms_k * 1e-3) / 1e9
             kernels[name].update({"bound": "hbm", "achieved_gbs": gbs, "peak_gbs": peak_gbs, "frac": gbs / peak_gbs})
-    kernels["tower"] = {"launches": conv_launches, "avg_us": 1e3 * conv_ms / max(conv_launches, 1),
-                          "share_of_step": conv_ms / sum(v[0] for v in prof.values())}
+    kernels["tower"] = {"launches": conv_launches, "avg_us": 1e3 * conv_ms / max(conv_launches, 1), "share_of_step": conv_ms / prof_pass_ms}
+    traffic, traffic_src = profiled_traffic("tower_tcgen05_kernel") if (filters, blocks, trees) == (256, 20, 1024) else (None, None)
 
-    # end-to-end leg: complete searches through the public API (mcts.run_mcts_batch) from host game objects:
-    # host rules export the game records, H2D, e2e_sims+1 device steps, D2H of the root statistics, move choice.
+    # end-to-end leg: complete searches through the public API from host game objects: host rules export the game records, H2D,
+    # e2e_sims+1 device steps, D2H of the root statistics, move choice.  (a) mcts.SearchStream, the call selfplay.play_games makes:
+    # two groups of `trees` games alternate on the device, the host work of one group overlaps the search of the other;
+    # (b) one mcts.run_mcts_batch call at a time (nothing overlaps).
     cfg = Config()
-    games = [Game(cfg, board=b) for b in boards]
     e2e_sims = args.e2e_sims
-    cb_mcts.run_mcts_batch(games, net, e2e_sims, 30, True, None, rng=np.random.default_rng(3))   # warm
+    groups = [[Game(cfg, board=b) for b in boards], [Game(cfg, board=b) for b in random_positions_device(trees, seed=5000 + rank)]]
+    rng_e = np.random.default_rng(3)
+
+    def caller_share(res):
+        # play_game reads the root's children (visit distribution, train.py:13-19,43-47) on its full searches only, a quarter of
+        # the moves (config.num_mcts_sims_p); the other moves just take the move
+        return sum(sum(c.N for c in root.children.values()) for _, root in res[::4])
+
+    ss = cb_mcts.SearchStream(net, 2)
+    for g in groups:                                     # warm both lanes (allocations, first-touch)
+        ss.collect(ss.submit(g, e2e_sims, True, None, rng=rng_e))
     barrier()
+    rounds, touched, e2e_evals_exact = 3, 0, 0
     t0 = time.perf_counter()
-    reps = 2
-    touched = 0
-    for _ in range(reps):
-        res = cb_mcts.run_mcts_batch(games, net, e2e_sims, 30, True, None, rng=np.random.default_rng(3))
-        # the caller's share of the work: play_game reads the root's children (visit distribution, train.py:13-19,43-47) on
-        # its full searches only, a quarter of the moves (config.num_mcts_sims_p); the other moves just take the move
-        for _, root in res[::4]:
-            touched += sum(c.N for c in root.children.values())
+    tickets = [ss.submit(g, e2e_sims, True, None, rng=rng_e) for g in groups]
+    for r in range(rounds):
+        for gi, g in enumerate(groups):
+            res = ss.collect_moves(tickets[gi], g, 30, rng_e)
+            e2e_evals_exact += ss.last_counters["evals"]
+            touched += caller_share(res)
+            if r + 1 < rounds:
+                tickets[gi] = ss.submit(g, e2e_sims, True, None, rng=rng_e)
     torch.cuda.synchronize()
     e2e_dt = time.perf_counter() - t0
-    e2e_evals_exact = eng.search_status()["evals"] * reps
-    h2d = sum(r.nbytes for r in records) + trees * (64 + 224 * 8)
-    d2h = trees * 224 * (2 + 4 + 4 + 4 + 8) + trees * 12
+    # (b) single calls
+    cb_mcts.run_mcts_batch(groups[0], net, e2e_sims, 30, True, None, rng=rng_e)
+    barrier()
+    t1 = time.perf_counter()
+    reps = 2
+    for _ in range(reps):
+        touched += caller_share(cb_mcts.run_mcts_batch(groups[0], net, e2e_sims, 30, True, None, rng=rng_e))
+    torch.cuda.synchronize()
+    single_dt = time.perf_counter() - t1
+    single_evals = net.engine.search_status()["evals"] * reps
+    n_children = sum(len(b.legal_moves) for b in boards)
+    h2d = sum(r.nbytes for r in records) + trees * (80 + 4 + 4) + n_children * 8 + (trees + 1) * 4
+    d2h = n_children * 22 + trees * 16 + 16
 
     if world > 1:
-        t = torch.tensor([ms, e2e_dt, conv_ms], device="cuda", dtype=torch.float64)
+        t = torch.tensor([ms, e2e_dt, conv_ms, single_dt], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        s = torch.tensor([evals, sims, e2e_evals_exact], device="cuda", dtype=torch.float64)
+        s = torch.tensor([evals, sims, e2e_evals_exact, single_evals], device="cuda", dtype=torch.float64)
         dist.all_reduce(s, op=dist.ReduceOp.SUM)
-        ms, e2e_dt, conv_ms_max = t.tolist()
-        evals, sims, e2e_evals_exact = s.tolist()
+        ms, e2e_dt, conv_ms_max, single_dt = t.tolist()
+        evals, sims, e2e_evals_exact, single_evals = s.tolist()
     value = evals / (ms * 1e-3)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_baseline = cpu_baseline_leg(filters, blocks)
+    parity = None
+    if rank == 0 and not args.no_parity:
+        parity = parity_leg(eng, net, records, trees)
 
     if rank == 0:
         steps_per_search = e2e_sims + 1
@@ -375,25 +453,35 @@ def run_gpu_arm(args):
                 "workload": f"batched MCTS leaf evaluation + tree update: {trees} concurrent games per GPU, {blocks}x{filters} "
                             f"ResNet (glorot kernels, trained-like BN statistics), one leaf per game per step (encode + forward + legal-move softmax + backup + select)",
                 "net": args.net, "trees_per_gpu": trees, "parallelism": f"games sharded over {world} GPU(s), no collective",
-                "l2": "working set per step (49 MB weights + 3x52 MB activations + node pool) exceeds the 126 MB L2; no flush",
+                "residual_stream": "bf16 hi + lo" if args.stream == "hilo" else "bf16",
+                "l2": "working set per step (49 MB weights + 3-4 x 52 MB activations + node pool) exceeds the 126 MB L2; no flush",
                 "fwd_gflop_per_position": flops_per_position(filters, blocks) / 1e9,
             },
             "roofline": {
                 "bound": "tensor", "kernel": "tower_tcgen05_kernel (all 1+2R conv layers, one persistent launch)", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak_tf, "traffic": 3.06e9 if (filters, blocks, trees) == (256, 20, 1024) else None,
-                "traffic_note": "DRAM read+write bytes per tower launch, ncu --set full capture profiles/r1_ncu_full_raw_encode_tower_mcts.csv", "peak_source": peak_src,
-                "how": f"algorithmic direct-conv FLOPs of {conv_launches} launches / their CUDA-event durations ({conv_ms:.2f} ms), second pass of the same {K} steps",
-                "conv_share_of_step": conv_ms / ms if ms > 0 else None,
+                "frac": achieved_tf / peak_tf, "frac_of_burst_peak": achieved_tf / peak_both["burst"], "frac_of_sustained_peak": achieved_tf / peak_both["sustained"],
+                "peaks": peak_both, "peak_source": peak_src,
+                "traffic": traffic, "traffic_source": (f"NOT measured in this run: dram__bytes_read.sum + dram__bytes_write.sum of one tower launch of this workload in the committed "
+                                                       f"ncu --set full capture {traffic_src}") if traffic_src else None,
+                "how": f"algorithmic direct-conv FLOPs of {conv_launches} launches / their CUDA-event durations ({conv_ms:.2f} ms) in a second, per-launch-"
+                       f"instrumented pass of the same {K} steps ({prof_pass_ms / K:.3f} ms per step in that pass, {ms / K:.3f} in the timed one)",
+                "conv_share_of_step": conv_ms / prof_pass_ms if prof_pass_ms > 0 else None,
+                "profiled_pass_ms_per_step": prof_pass_ms / K,
             },
             "e2e": {"value": e2e_evals_exact / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": h2d / steps_per_search,
                     "d2h_bytes_per_step": d2h / steps_per_search,
-                    "what": f"{reps} x mcts.run_mcts_batch({trees} games, {e2e_sims} sims): host game records -> H2D -> {steps_per_search} steps -> D2H root "
-                            "statistics -> move choice for every game, children read for every 4th (playout cap); "
-                            f"bytes are per search / {steps_per_search} steps"},
+                    "fraction_of_device_rate": (e2e_evals_exact / e2e_dt) / value,
+                    "what": f"mcts.SearchStream (the call selfplay.play_games makes): 2 groups of {trees} games alternate, {rounds} searches of {e2e_sims} sims "
+                            f"each; per search: host game records -> H2D -> {steps_per_search} steps -> packed D2H of the root statistics -> move choice for "
+                            "every game, children read for every 4th (playout cap); wall clock from the first submit to the last move, incl. the "
+                            f"un-overlapped first export and last move choice; bytes are per search / {steps_per_search} steps",
+                    "single_call": {"value": single_evals / single_dt, "fraction_of_device_rate": (single_evals / single_dt) / value,
+                                    "what": f"{reps} x mcts.run_mcts_batch({trees} games, {e2e_sims} sims), one call at a time: nothing overlaps the host work"}},
             "kernels": kernels,
             "gpu_launches": K * 4,   # encode, tower, heads, mcts_step
             "clocks": clocks,
             "cpu_baseline": cpu_baseline,
+            "parity": parity,
         }
         emit(json.dumps(line))
     if world > 1:
@@ -457,7 +545,7 @@ def run_leaf_eval_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_dt = t.tolist()
     if rank == 0:
-        peak_tf, peak_gbs, peak_src = measured_peaks()
+        peak_tf, peak_gbs, peak_src, peak_both = measured_peaks(ms * 1e-3)
         conv_ms = prof["conv"][0]
         tf = conv_flops_per_position(filters, blocks) * n * K / (conv_ms * 1e-3) / 1e12
         tot = sum(v[0] for v in prof.values())
@@ -467,7 +555,7 @@ def run_leaf_eval_arm(args):
             "config": {"workload": f"batched leaf eval: {blocks}x{filters} ResNet, {n} synthetic positions per GPU, encode + forward + legal-move mask/softmax",
                        "net": args.net, "positions_per_gpu": n, "l2": "inputs resident; activations 3 x %.0f MB per pass" % (n * 32 * filters * 1.6 / 1e6)},
             "roofline": {"bound": "tensor", "kernel": "tower_tcgen05_kernel", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf,
-                         "traffic": None, "peak_source": peak_src},
+                         "frac_of_burst_peak": tf / peak_both["burst"], "frac_of_sustained_peak": tf / peak_both["sustained"], "traffic": None, "peak_source": peak_src},
             "kernels": {k: {"launches": v[1], "avg_us": 1e3 * v[0] / max(v[1], 1), "share_of_step": v[0] / tot} for k, v in prof.items() if v[1]},
             "e2e": {"value": world * n * reps / e2e_dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": K * 6, "clocks": clocks, "cpu_baseline": None}))
@@ -545,7 +633,7 @@ def run_train_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_dt = t.tolist()
     if rank == 0:
-        peak_tf, peak_gbs, peak_src = measured_peaks()
+        peak_tf, peak_gbs, peak_src, peak_both = measured_peaks(ms * 1e-3)
         mma_ms = prof["conv_fwd"][0] + prof["wgrad"][0] + prof["dgrad"][0]
         tf = train_flops_per_sample(filters, blocks) * B * prof_steps / (mma_ms * 1e-3) / 1e12
         tot = sum(v[0] for v in prof.values())
@@ -569,7 +657,8 @@ def run_train_arm(args):
                                    f"SGD nesterov + l2, gradients all-reduced over NCCL ({world} GPU(s))", "net": args.net, "batch_per_gpu": B,
                        "l2": "every layer's activation tensor (%.0f MB) exceeds the 126 MB L2; no flush" % act_mb},
             "roofline": {"bound": "tensor", "kernel": "tower_tcgen05_kernel (forward, data gradient) + wgrad_tcgen05_kernel", "achieved": tf,
-                         "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf, "traffic": None, "peak_source": peak_src,
+                         "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf, "frac_of_burst_peak": tf / peak_both["burst"],
+                         "frac_of_sustained_peak": tf / peak_both["sustained"], "traffic": None, "peak_source": peak_src,
                          "how": f"algorithmic FLOPs of the three 3x3-convolution passes / CUDA-event time of their launches over {prof_steps} steps",
                          "mma_share_of_step": mma_ms / tot},
             "kernels": kernels, "losses": losses,
@@ -655,6 +744,8 @@ def main():
     ap.add_argument("--e2e-sims", type=int, default=100, help="simulations per search of the end-to-end leg (run_mcts default, mcts.py:38)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the untimed checker leg (device network vs the torch-fp32 oracle)")
+    ap.add_argument("--stream", default="hilo", choices=["hilo", "bf16"], help="residual stream between blocks: bf16 hi + lo (default) or bf16 (round-1 datapath)")
     ap.add_argument("--workload", default="search", choices=["search", "leaf_eval", "train"],
                     help="search = the headline (batched MCTS, BASELINE north_star); leaf_eval = BASELINE config 2 (use --net 6x128); "
                          "train = BASELINE config 5 (train.py step, --batch per GPU)")

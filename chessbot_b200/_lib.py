@@ -41,18 +41,25 @@ _SIGS = {
     "cb_ctx_create": (vp, [i32]),
     "cb_ctx_destroy": (None, [vp]),
     "cb_ctx_sm_count": (i32, [vp]),
+    "cb_ctx_device": (i32, [vp]),
     "cb_set_exp_table": (i32, [vp, vp]),
     "cb_planes_act_bytes": (C.c_size_t, [i32]),
     "cb_encode": (i32, [vp, vp, vp, i32, vp, vp, vp]),
     "cb_net_create": (i32, [vp, i32, i32, i32, C.c_float, C.c_float]),
     "cb_net_set_tensor": (i32, [vp, C.c_char_p, vp, C.c_size_t]),
     "cb_net_finalize": (i32, [vp]),
+    "cb_net_set_stream_precision": (i32, [vp, i32]),
     "cb_net_forward": (i32, [vp, vp, i32, vp, vp, vp, vp]),
     "cb_synth_forward": (i32, [vp, vp, i32, u32, vp, vp, vp]),
     "cb_policy_softmax": (i32, [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]),
     "cb_search_create": (i32, [vp, i32, i32, i32, i32]),
     "cb_search_set_leaves": (i32, [vp, i32]),
     "cb_search_begin": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, i32, i32, u32, vp]),
+    "cb_search_begin_csr": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, i32, i32, u32, vp]),
+    "cb_search_roots_compact_bytes": (C.c_size_t, [i32, i32]),
+    "cb_search_read_roots_compact_sync": (i32, [vp, vp, vp, vp]),
+    "cb_search_read_roots_compact_async": (i32, [vp, vp, vp]),
+    "cb_search_read_roots_compact_wait": (i32, [vp, vp, vp]),
     "cb_search_step": (i32, [vp, vp]),
     "cb_search_run": (i32, [vp, i32, vp]),
     "cb_search_pending_planes_sync": (i32, [vp, vp, vp, vp]),

@@ -268,8 +268,9 @@ class Board:
         return f"Board({self.fen()!r})"
 
 
-def export_records(boards):
-    """Game records of many boards in one C call: (list of uint8 [k_i, 96] views, int32 legal-move counts)."""
+def export_records(boards, flat=False):
+    """Game records of many boards in one C call: (list of uint8 [k_i, 96] views, int32 legal-move counts); flat=True returns
+    (uint8 [sum k_i, 96], int32 lens, int32 legal-move counts) without cutting the buffer into per-board views."""
     n = len(boards)
     handles = (C.c_void_p * n)(*[b._h for b in boards])
     lens = np.empty(n, dtype=np.int32)
@@ -281,6 +282,8 @@ def export_records(boards):
         if total <= cap:
             break
         cap = total
+    if flat:
+        return buf[:total], lens, n_legal
     ends = np.cumsum(lens)
     return [buf[e - k:e] for e, k in zip(ends.tolist(), lens.tolist())], n_legal
 

@@ -26,6 +26,32 @@ __global__ void read_roots_kernel(SearchParams sp, uint16_t* moves, int32_t* n, 
         p[o] = ts.noisy ? sp.root_p64[o] : (double)c.P;
     }
 }
+// compact variant: the children of tree t go to [child_off[t], child_off[t] + n_children) of every section (the caller knows the
+// number of legal moves of every root); sections: P f64 | N i32 | W f32 | Q f32 | n_children, root_N, tree_nodes, state i32 [n] | moves u16
+// (state = TreeState::status | error << 8)
+__global__ void read_roots_compact_kernel(SearchParams sp, const int32_t* child_off, uint8_t* out, int total) {
+    const int tree = blockIdx.x;
+    if (tree >= sp.n_trees) return;
+    const TreeState& ts = sp.trees[tree];
+    const Node& r = sp.nodes[ts.root_node];
+    double* P = reinterpret_cast<double*>(out);
+    int32_t* N = reinterpret_cast<int32_t*>(P + total);
+    float* W = reinterpret_cast<float*>(N + total);
+    float* Q = W + total;
+    int32_t* hdr = reinterpret_cast<int32_t*>(Q + total);
+    uint16_t* mv = reinterpret_cast<uint16_t*>(hdr + 4 * sp.n_trees);
+    const int off = child_off[tree], cap = child_off[tree + 1] - off;
+    if (threadIdx.x == 0) {
+        hdr[tree] = r.n_children; hdr[sp.n_trees + tree] = r.N; hdr[2 * sp.n_trees + tree] = ts.n_nodes;
+        hdr[3 * sp.n_trees + tree] = ts.status | (ts.error ? 256 : 0);
+    }
+    const int k = min((int)r.n_children, cap);
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        const Node& c = sp.nodes[r.first_child + i];
+        mv[off + i] = c.move; N[off + i] = c.N; W[off + i] = c.W; Q[off + i] = c.Q;
+        P[off + i] = ts.noisy ? sp.root_p64[(size_t)tree * MAX_MOVES + i] : (double)c.P;
+    }
+}
 __global__ void waiting_flags_kernel(const TreeState* trees, int n, uint8_t* flags) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) flags[i] = trees[i].status == 1 || trees[i].status == 2;
@@ -53,6 +79,33 @@ struct DevBuf {
     }
     void free_() { if (p) cudaFree(p); p = nullptr; n = 0; }
     ~DevBuf() { free_(); }
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {  // `net = Net()` on a reload frees the previous network's buffers
+        if (this != &o) { free_(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
+};
+
+// pinned host staging owned by the context: asynchronous copies need no host synchronisation and no pageable bounce buffer
+struct PinBuf {
+    uint8_t* p = nullptr;
+    size_t n = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= n) return 0;
+        if (p) cudaFreeHost(p);
+        p = nullptr; n = 0;
+        bytes = bytes * 5 / 4 + 4096;
+        CB_CUDA_OK(cudaMallocHost((void**)&p, bytes));
+        n = bytes;
+        return 0;
+    }
+    ~PinBuf() { if (p) cudaFreeHost(p); }
+    PinBuf() = default;
+    PinBuf(const PinBuf&) = delete;
+    PinBuf& operator=(const PinBuf&) = delete;
 };
 
 struct ConvLayer {
@@ -67,7 +120,8 @@ struct Net {
     std::map<std::string, std::vector<float>> host;  // staged Keras-layout tensors
     std::vector<ConvLayer> layers;                   // stem + 2 per block
     DevBuf<float> head_w, head_bn, fc1, fc2, wp, wpt;
-    DevBuf<__nv_bfloat16> act[3];
+    DevBuf<__nv_bfloat16> act[3], act_lo;            // act_lo: low half of the residual stream (stream_hi_lo)
+    bool stream_hi_lo = true;
     DevBuf<float> head_raw, pfeat;
     DevBuf<LayerDesc> layer_desc, dbg_desc;          // tower kernel: per-layer descriptors (dbg_desc: cb_debug_conv_layer)
     DevBuf<CUtensorMap> wmaps;                       // tensor maps of the packed weights, one per layer
@@ -97,6 +151,11 @@ struct Search {
     DevBuf<uint8_t> flags;
     // read-back staging
     DevBuf<uint16_t> r_moves; DevBuf<int32_t> r_n, r_nc, r_rootn, r_nodes; DevBuf<float> r_w, r_q; DevBuf<double> r_p;
+    DevBuf<uint8_t> r_pack; DevBuf<int32_t> r_off;   // compact read-back: one packed device buffer, one D2H
+    PinBuf h_begin, h_read;                          // pinned staging of cb_search_begin / cb_search_read_roots_compact_sync
+    cudaEvent_t begin_copied = nullptr;              // the previous begin's H2D copies have left h_begin
+    cudaEvent_t read_done = nullptr;                 // the packed read-back queued by cb_search_read_roots_compact_async has landed in h_read
+    size_t read_bytes = 0, read_cnt_off = 0;
     SearchParams sp{};
 };
 }  // namespace
@@ -132,6 +191,13 @@ static int prof_end(cb_ctx* ctx, cudaStream_t st) {
     return 0;
 }
 
+// every entry point runs on its context's device, whatever the caller's current device is (several contexts per process)
+#define CB_ENTER(ctx)                                                                                                 \
+    do {                                                                                                              \
+        if (!(ctx)) { cb_set_error("null context"); return -1; }                                                      \
+        if (cudaSetDevice((ctx)->device) != cudaSuccess) { cb_set_error("cudaSetDevice(context device) failed"); return -1; } \
+    } while (0)
+
 static int upload(void* dst, const void* src, size_t bytes) {
     CB_CUDA_OK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
     return 0;
@@ -165,12 +231,20 @@ cb_ctx* cb_ctx_create(int device) {
     if (ctx->exp_table.alloc(65536) != 0 || upload(ctx->exp_table.p, tab.data(), 65536 * 4) != 0) { delete ctx; return nullptr; }
     return ctx;
 }
-void cb_ctx_destroy(cb_ctx* ctx) { delete ctx; }
+void cb_ctx_destroy(cb_ctx* ctx) {
+    if (ctx) cudaSetDevice(ctx->device);
+    delete ctx;
+}
 int cb_ctx_sm_count(const cb_ctx* ctx) { return ctx->sms; }
-int cb_set_exp_table(cb_ctx* ctx, const float* table_host) { return upload(ctx->exp_table.p, table_host, 65536 * 4); }
+int cb_ctx_device(const cb_ctx* ctx) { return ctx->device; }
+int cb_set_exp_table(cb_ctx* ctx, const float* table_host) {
+    CB_ENTER(ctx);
+    return upload(ctx->exp_table.p, table_host, 65536 * 4);
+}
 
 size_t cb_planes_act_bytes(int n) { return act_bytes(n, 128); }
 int cb_encode(cb_ctx* ctx, const void* pos_dev, const int32_t* frame_idx_dev, int n, void* planes_act_dev, int16_t* planes_i16_dev, void* stream) {
+    CB_ENTER(ctx);
     cudaStream_t st = (cudaStream_t)stream;
     if (prof_begin(ctx, CB_PROF_ENCODE, st) ||
         launch_encode((const Pos*)pos_dev, frame_idx_dev, n, (__nv_bfloat16*)planes_act_dev, planes_i16_dev, st) || prof_end(ctx, st))
@@ -189,6 +263,11 @@ int cb_net_create(cb_ctx* ctx, int filters, int blocks, int max_batch, float lea
     net.max_batch = max_batch;
     net.slope = leaky_slope;
     net.eps = bn_eps;
+    return 0;
+}
+int cb_net_set_stream_precision(cb_ctx* ctx, int hi_lo) {
+    ctx->net.stream_hi_lo = hi_lo != 0;
+    ctx->net.ready = false;
     return 0;
 }
 int cb_net_set_tensor(cb_ctx* ctx, const char* name, const float* host, size_t count) {
@@ -239,6 +318,7 @@ static int pack_conv(Net& net, ConvLayer& L, const std::vector<float>& w, int ci
 }
 
 int cb_net_finalize(cb_ctx* ctx) {
+    CB_ENTER(ctx);
     Net& net = ctx->net;
     const int C = net.filters, N = net.cpad;
     auto need = [&](const std::string& k) -> const std::vector<float>* {
@@ -292,6 +372,7 @@ int cb_net_finalize(cb_ctx* ctx) {
     const size_t act_elems = act_bytes(net.max_batch, N) / 2;
     for (int i = 0; i < 3; ++i)
         if (net.act[i].alloc(act_elems)) return -1;  // zeroed: border cells stay zero forever
+    if (net.stream_hi_lo ? net.act_lo.alloc(act_elems) : (net.act_lo.free_(), 0)) return -1;
     const size_t mb = (size_t)(net.max_batch + 3) / 4 * 4;
     if (net.head_raw.alloc(mb * 192) || net.pfeat.alloc(mb * 128)) return -1;
     // tower kernel: weight tensor maps, layer descriptors (buffer 0 = input planes, 1..3 = act[0..2]), progress flags
@@ -352,8 +433,9 @@ static int net_tower(cb_ctx* ctx, const void* planes_act_dev, int n, float* valu
     tp.layers = net.layer_desc.p;
     tp.head_w = net.head_w.p;
     tp.head_out = net.head_raw.p;
+    tp.lo_buf = (uint8_t*)net.act_lo.p;
     tp.n_boards_dev = n_dev;
-    tp.full_sectors = 3 * act_bytes(n, net.cpad) > ((size_t)96 << 20);  // three rotating activation buffers that do not fit the 126 MB L2
+    tp.full_sectors = (net.stream_hi_lo ? 4 : 3) * act_bytes(n, net.cpad) > ((size_t)96 << 20);  // the rotating activation buffers (+ lo) do not fit the 126 MB L2
     tp.flags = net.flags.p;
     tp.epoch = net.epoch;
     tp.nl = (int)net.layers.size();
@@ -367,6 +449,7 @@ static int net_tower(cb_ctx* ctx, const void* planes_act_dev, int n, float* valu
 }
 
 int cb_net_forward(cb_ctx* ctx, const void* planes_act_dev, int n, float* value_dev, void* logits_bf16_dev, float* logits_f32_dev, void* stream) {
+    CB_ENTER(ctx);
     cudaStream_t st = (cudaStream_t)stream;
     if (net_tower(ctx, planes_act_dev, n, value_dev, st)) return -1;
     if (logits_bf16_dev || logits_f32_dev) {
@@ -378,6 +461,7 @@ int cb_net_forward(cb_ctx* ctx, const void* planes_act_dev, int n, float* value_
 }
 
 int cb_synth_forward(cb_ctx* ctx, const int16_t* planes_i16_dev, int n, uint32_t seed, float* value_dev, void* logits_bf16_dev, void* stream) {
+    CB_ENTER(ctx);
     (void)ctx;
     static thread_local DevBuf<uint32_t> hash;  // scratch of the stand-alone call (the search owns its own per-slot hashes)
     if (hash.n < (size_t)n && hash.alloc(n)) return -1;
@@ -386,6 +470,7 @@ int cb_synth_forward(cb_ctx* ctx, const int16_t* planes_i16_dev, int n, uint32_t
 
 int cb_policy_softmax(cb_ctx* ctx, const void* pos_dev, const int32_t* cur_idx_dev, int n, const void* logits_bf16_dev,
                       uint16_t* out_moves_dev, int16_t* out_actions_dev, float* out_priors_dev, int32_t* out_n_dev, void* stream) {
+    CB_ENTER(ctx);
     cudaStream_t st = (cudaStream_t)stream;
     if (prof_begin(ctx, CB_PROF_POLICY_SOFTMAX, st) ||
         launch_policy_softmax((const Pos*)pos_dev, cur_idx_dev, n, (const __nv_bfloat16*)logits_bf16_dev, ctx->exp_table.p,
@@ -400,6 +485,7 @@ int cb_profile(cb_ctx* ctx, int enable) {
     return 0;
 }
 int cb_profile_read_sync(cb_ctx* ctx, double* total_ms, int* launches) {
+    CB_ENTER(ctx);
     CB_CUDA_OK(cudaDeviceSynchronize());
     for (int k = 0; k < CB_PROF_STAGES; ++k) { total_ms[k] = 0; launches[k] = 0; }
     for (size_t i = 0; i + 1 < ctx->prof_used; i += 2) {
@@ -414,6 +500,7 @@ int cb_profile_read_sync(cb_ctx* ctx, double* total_ms, int* launches) {
 
 int cb_debug_conv_layer(cb_ctx* ctx, int layer, const void* in_act_dev, const void* skip_act_dev, void* out_act_dev, int n_boards,
                         int use_reference, void* stream) {
+    CB_ENTER(ctx);
     Net& net = ctx->net;
     cudaStream_t st = (cudaStream_t)stream;
     if (!net.ready || layer < 0 || layer >= (int)net.layers.size()) { cb_set_error("bad layer"); return -1; }
@@ -453,6 +540,7 @@ int cb_debug_conv_layer(cb_ctx* ctx, int layer, const void* in_act_dev, const vo
 // weight gradient of one 3x3 convolution on tile-native buffers: out_dev f32 [9][cin_pad][n] (padded channels included)
 int cb_debug_wgrad(cb_ctx* ctx, const void* in_act_dev, const void* dy_act_dev, int n_boards, int cin_pad, int n, float* out_dev,
                    int use_reference, void* stream) {
+    CB_ENTER(ctx);
     cudaStream_t st = (cudaStream_t)stream;
     const int pairs = (n_boards + 1) / 2, cj_in = cin_pad / 8;
     if (use_reference)
@@ -473,6 +561,7 @@ int cb_debug_wgrad(cb_ctx* ctx, const void* in_act_dev, const void* dy_act_dev, 
 
 // ------------------------------------------------------------------------------------ search
 int cb_search_create(cb_ctx* ctx, int max_trees, int max_nodes, int max_positions, int max_sims) {
+    CB_ENTER(ctx);
     Search& s = ctx->search;
     s.max_trees = max_trees;
     s.max_sims = max_sims;
@@ -508,6 +597,7 @@ int cb_search_create(cb_ctx* ctx, int max_trees, int max_nodes, int max_position
 
 // Buffers indexed by evaluation slot (tree * leaves + i): the batch of a step is max_trees * leaves positions.
 int cb_search_set_leaves(cb_ctx* ctx, int leaves) {
+    CB_ENTER(ctx);
     Search& s = ctx->search;
     if (leaves < 1 || leaves > 32) { cb_set_error("leaves per tree must be 1..32"); return -1; }
     if (s.max_trees <= 0) { cb_set_error("cb_search_create first"); return -1; }
@@ -525,11 +615,14 @@ int cb_search_set_leaves(cb_ctx* ctx, int leaves) {
     return 0;
 }
 
-int cb_search_begin(cb_ctx* ctx, int n_trees, const void* records_host, const int32_t* rec_len, const int32_t* sims,
-                    const double* cpuct, const uint8_t* has_noise, const double* noise, int max_game_length, int eval_mode,
-                    uint32_t synth_seed, void* stream) {
+// Roots + per-tree settings -> device, and the root expansion is queued.  Everything the asynchronous copies read lies in pinned
+// staging owned by the context (no pageable bounce, no host synchronisation here); the staging is reused once the event recorded
+// behind the copies has passed.  noise_flat / noise_off: CSR (tree t's samples at noise_flat[noise_off[t] .. noise_off[t+1]), an empty
+// range = no root noise for that tree); noise_off == nullptr = no noise at all.
+static int search_begin_impl(cb_ctx* ctx, int n_trees, const void* records_host, const int32_t* rec_len, const int32_t* sims, const double* cpuct,
+                             const double* noise_flat, const int64_t* noise_off, int max_game_length, int eval_mode, uint32_t synth_seed,
+                             cudaStream_t st) {
     Search& s = ctx->search;
-    cudaStream_t st = (cudaStream_t)stream;
     if (n_trees > s.max_trees) { cb_set_error("n_trees > max_trees"); return -1; }
     if (eval_mode == CB_EVAL_NET && !ctx->net.ready) { cb_set_error("CB_EVAL_NET without a finalized network"); return -1; }
     if (eval_mode == CB_EVAL_NET && n_trees * s.leaves > ctx->net.max_batch) { cb_set_error("n_trees * leaves > network max_batch"); return -1; }
@@ -538,39 +631,78 @@ int cb_search_begin(cb_ctx* ctx, int n_trees, const void* records_host, const in
     s.eval_mode = eval_mode;
     s.seed = synth_seed;
     size_t total = 0;
-    for (int i = 0; i < n_trees; ++i) total += rec_len[i];
-    if ((int64_t)total >= s.sp.max_pos) { cb_set_error("root records exceed the position pool"); return -1; }
-    std::vector<Pos> rec((const Pos*)records_host, (const Pos*)records_host + total);
-    std::vector<TreeState> ts(n_trees);
-    size_t off = 0;
     for (int i = 0; i < n_trees; ++i) {
         if (rec_len[i] < 1) { cb_set_error("empty game record"); return -1; }
         if (sims[i] > s.max_sims) { cb_set_error("sims > max_sims"); return -1; }
+        total += rec_len[i];
+    }
+    if ((int64_t)total >= s.sp.max_pos) { cb_set_error("root records exceed the position pool"); return -1; }
+    const size_t n_noise = noise_off ? (size_t)noise_off[n_trees] : 0;
+    if (n_noise > s.noise.n) { cb_set_error("more root noise samples than n_trees * CB_MAX_MOVES"); return -1; }
+    // staging layout: positions | tree states | noise | two counters
+    const size_t b_pos = total * sizeof(Pos), b_ts = (size_t)n_trees * sizeof(TreeState), b_noise = n_noise * 8;
+    const size_t o_ts = (b_pos + 15) & ~(size_t)15, o_noise = (o_ts + b_ts + 15) & ~(size_t)15, o_cnt = (o_noise + b_noise + 15) & ~(size_t)15;
+    if (!s.begin_copied) CB_CUDA_OK(cudaEventCreateWithFlags(&s.begin_copied, cudaEventDisableTiming));
+    else CB_CUDA_OK(cudaEventSynchronize(s.begin_copied));
+    if (s.h_begin.reserve(o_cnt + 16)) return -1;
+    Pos* rec = reinterpret_cast<Pos*>(s.h_begin.p);
+    TreeState* ts = reinterpret_cast<TreeState*>(s.h_begin.p + o_ts);
+    memcpy(rec, records_host, b_pos);
+    memset(ts, 0, b_ts);
+    size_t off = 0;
+    for (int i = 0; i < n_trees; ++i) {
         for (int k = 0; k < rec_len[i]; ++k) rec[off + k].pad_[0] = k ? (uint32_t)(off + k - 1) : 0xFFFFFFFFu;  // predecessor link
-        memset(&ts[i], 0, sizeof(TreeState));
         ts[i].root_pos = (int32_t)(off + rec_len[i] - 1);
         ts[i].sims_target = sims[i];
         ts[i].status = 1;
-        ts[i].noisy = has_noise && has_noise[i] && noise;
+        ts[i].noisy = noise_off && noise_off[i + 1] > noise_off[i];
+        ts[i].noise_off = noise_off ? (int32_t)noise_off[i] : 0;
         ts[i].max_len = max_game_length;
         ts[i].cpuct = cpuct ? cpuct[i] : -1.0;
         off += rec_len[i];
     }
-    const int32_t zero = 0, pc = (int32_t)total;
-    CB_CUDA_OK(cudaMemcpyAsync(s.pos.p, rec.data(), total * sizeof(Pos), cudaMemcpyHostToDevice, st));
-    CB_CUDA_OK(cudaMemcpyAsync(s.trees.p, ts.data(), n_trees * sizeof(TreeState), cudaMemcpyHostToDevice, st));
-    CB_CUDA_OK(cudaMemcpyAsync(s.node_count.p, &zero, 4, cudaMemcpyHostToDevice, st));
-    CB_CUDA_OK(cudaMemcpyAsync(s.pos_count.p, &pc, 4, cudaMemcpyHostToDevice, st));
+    if (b_noise) memcpy(s.h_begin.p + o_noise, noise_flat, b_noise);
+    int32_t* cnt = reinterpret_cast<int32_t*>(s.h_begin.p + o_cnt);
+    cnt[0] = 0;
+    cnt[1] = (int32_t)total;
+    CB_CUDA_OK(cudaMemcpyAsync(s.pos.p, rec, b_pos, cudaMemcpyHostToDevice, st));
+    CB_CUDA_OK(cudaMemcpyAsync(s.trees.p, ts, b_ts, cudaMemcpyHostToDevice, st));
+    if (b_noise) CB_CUDA_OK(cudaMemcpyAsync(s.noise.p, s.h_begin.p + o_noise, b_noise, cudaMemcpyHostToDevice, st));
+    CB_CUDA_OK(cudaMemcpyAsync(s.node_count.p, &cnt[0], 4, cudaMemcpyHostToDevice, st));
+    CB_CUDA_OK(cudaMemcpyAsync(s.pos_count.p, &cnt[1], 4, cudaMemcpyHostToDevice, st));
+    CB_CUDA_OK(cudaEventRecord(s.begin_copied, st));
     CB_CUDA_OK(cudaMemsetAsync(s.counters.p, 0, 16, st));
     CB_CUDA_OK(cudaMemsetAsync(s.active_count.p, 0, 4, st));
-    if (noise) CB_CUDA_OK(cudaMemcpyAsync(s.noise.p, noise, (size_t)n_trees * MAX_MOVES * 8, cudaMemcpyHostToDevice, st));
-    CB_CUDA_OK(cudaStreamSynchronize(st));  // host staging vectors go out of scope
     s.sp.n_trees = n_trees;
     s.sp.eval_mode = eval_mode;
     s.sp.pfeat = ctx->net.pfeat.p;
     s.sp.wpt = ctx->net.wpt.p;
     s.sp.expvals = s.expvals.p;
     return launch_mcts_begin(s.sp, st);
+}
+
+int cb_search_begin(cb_ctx* ctx, int n_trees, const void* records_host, const int32_t* rec_len, const int32_t* sims,
+                    const double* cpuct, const uint8_t* has_noise, const double* noise, int max_game_length, int eval_mode,
+                    uint32_t synth_seed, void* stream) {
+    CB_ENTER(ctx);
+    if (!noise || !has_noise)
+        return search_begin_impl(ctx, n_trees, records_host, rec_len, sims, cpuct, nullptr, nullptr, max_game_length, eval_mode, synth_seed, (cudaStream_t)stream);
+    // dense [n][CB_MAX_MOVES] rows -> CSR with full-length rows for the noisy trees
+    std::vector<int64_t> off(n_trees + 1, 0);
+    std::vector<double> flat;
+    flat.reserve((size_t)n_trees * MAX_MOVES);
+    for (int i = 0; i < n_trees; ++i) {
+        if (has_noise[i]) flat.insert(flat.end(), noise + (size_t)i * MAX_MOVES, noise + (size_t)(i + 1) * MAX_MOVES);
+        off[i + 1] = (int64_t)flat.size();
+    }
+    return search_begin_impl(ctx, n_trees, records_host, rec_len, sims, cpuct, flat.data(), off.data(), max_game_length, eval_mode, synth_seed,
+                             (cudaStream_t)stream);
+}
+int cb_search_begin_csr(cb_ctx* ctx, int n_trees, const void* records_host, const int32_t* rec_len, const int32_t* sims, const double* cpuct,
+                        const double* noise_flat, const int64_t* noise_off, int max_game_length, int eval_mode, uint32_t synth_seed, void* stream) {
+    CB_ENTER(ctx);
+    return search_begin_impl(ctx, n_trees, records_host, rec_len, sims, cpuct, noise_flat, noise_flat ? noise_off : nullptr, max_game_length, eval_mode,
+                             synth_seed, (cudaStream_t)stream);
 }
 
 // CB_DEBUG_SYNC=1: synchronise after every stage of a search step and name the stage that faulted
@@ -586,6 +718,7 @@ static int debug_sync(cudaStream_t st, const char* stage) {
 }
 
 int cb_search_step(cb_ctx* ctx, void* stream) {
+    CB_ENTER(ctx);
     Search& s = ctx->search;
     cudaStream_t st = (cudaStream_t)stream;
     if (s.eval_mode == CB_EVAL_NET) {
@@ -613,6 +746,7 @@ int cb_search_run(cb_ctx* ctx, int steps, void* stream) {
     return 0;
 }
 int cb_search_pending_planes_sync(cb_ctx* ctx, int16_t* planes_host, uint8_t* waiting_host, void* stream) {
+    CB_ENTER(ctx);
     Search& s = ctx->search;
     cudaStream_t st = (cudaStream_t)stream;
     if (launch_encode(s.pos.p, s.frame_idx.p, s.n_trees, nullptr, s.planes_i16.p, st)) return -1;
@@ -623,6 +757,7 @@ int cb_search_pending_planes_sync(cb_ctx* ctx, int16_t* planes_host, uint8_t* wa
     return 0;
 }
 int cb_search_step_external(cb_ctx* ctx, const float* value_host, const float* expvals_host, void* stream) {
+    CB_ENTER(ctx);
     Search& s = ctx->search;
     cudaStream_t st = (cudaStream_t)stream;
     if (s.expvals.n < (size_t)s.n_trees * 4672) {
@@ -637,6 +772,7 @@ int cb_search_step_external(cb_ctx* ctx, const float* value_host, const float* e
     return 0;
 }
 int cb_search_status_sync(cb_ctx* ctx, int64_t* counters, void* stream) {
+    CB_ENTER(ctx);
     Search& s = ctx->search;
     cudaStream_t st = (cudaStream_t)stream;
     CB_CUDA_OK(cudaMemsetAsync(s.scratch_i32.p, 0, 4, st));
@@ -650,6 +786,7 @@ int cb_search_status_sync(cb_ctx* ctx, int64_t* counters, void* stream) {
 }
 int cb_search_read_roots_sync(cb_ctx* ctx, uint16_t* moves, int32_t* n, float* w, float* q, double* p, int32_t* n_children,
                               int32_t* root_n, int32_t* tree_nodes, void* stream) {
+    CB_ENTER(ctx);
     Search& s = ctx->search;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t mm = (size_t)s.n_trees * MAX_MOVES, mt = s.n_trees;
@@ -665,6 +802,68 @@ int cb_search_read_roots_sync(cb_ctx* ctx, uint16_t* moves, int32_t* n, float* w
     CB_CUDA_OK(cudaMemcpyAsync(tree_nodes, s.r_nodes.p, mt * 4, cudaMemcpyDeviceToHost, st));
     CB_CUDA_OK(cudaStreamSynchronize(st));
     return 0;
+}
+
+size_t cb_search_roots_compact_bytes(int n_trees, int total_children) {
+    return (size_t)total_children * (8 + 4 + 4 + 4) + (size_t)n_trees * 16 + (size_t)total_children * 2;
+}
+// Root statistics of all trees in ONE packed buffer and ONE device-to-host copy: the children of tree t at [child_off[t], child_off[t+1])
+// of every section (the caller knows every root's legal-move count from the record export).  Sections, in this order:
+// P f64[T] | N i32[T] | W f32[T] | Q f32[T] | n_children i32[n] | root_N i32[n] | tree_nodes i32[n] | state i32[n] | moves u16[T],  T = child_off[n].
+// _async queues kernel + copy + an event behind the search steps already on the stream and returns; _wait blocks on that event only,
+// so the host can pick up one search's results while the next one (another context, same stream) already runs.
+int cb_search_read_roots_compact_async(cb_ctx* ctx, const int32_t* child_off, void* stream) {
+    CB_ENTER(ctx);
+    Search& s = ctx->search;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = s.n_trees, total = child_off[n];
+    if (n < 1) { cb_set_error("read_roots_compact: no search"); return -1; }
+    if (total < 0 || (size_t)total > (size_t)s.max_trees * MAX_MOVES) { cb_set_error("read_roots_compact: bad offsets"); return -1; }
+    const size_t bytes = cb_search_roots_compact_bytes(n, total), b_off = (size_t)(n + 1) * 4;
+    if (s.r_pack.n < bytes && s.r_pack.alloc(cb_search_roots_compact_bytes(s.max_trees, s.max_trees * MAX_MOVES), false)) return -1;
+    if (s.r_off.n < (size_t)n + 1 && s.r_off.alloc(s.max_trees + 1, false)) return -1;
+    const size_t o_cnt = (bytes + 15) & ~(size_t)15, o_off = o_cnt + 16;
+    if (!s.read_done) CB_CUDA_OK(cudaEventCreateWithFlags(&s.read_done, cudaEventDisableTiming));
+    else CB_CUDA_OK(cudaEventSynchronize(s.read_done));   // an earlier read-back nobody waited for still owns the staging
+    if (s.h_read.reserve(o_off + b_off)) return -1;
+    memcpy(s.h_read.p + o_off, child_off, b_off);
+    CB_CUDA_OK(cudaMemcpyAsync(s.r_off.p, s.h_read.p + o_off, b_off, cudaMemcpyHostToDevice, st));
+    read_roots_compact_kernel<<<n, 64, 0, st>>>(s.sp, s.r_off.p, s.r_pack.p, total);
+    CB_CUDA_OK(cudaGetLastError());
+    CB_CUDA_OK(cudaMemcpyAsync(s.h_read.p, s.r_pack.p, bytes, cudaMemcpyDeviceToHost, st));
+    CB_CUDA_OK(cudaMemcpyAsync(s.h_read.p + o_cnt, s.counters.p, 16, cudaMemcpyDeviceToHost, st));
+    CB_CUDA_OK(cudaEventRecord(s.read_done, st));
+    s.read_bytes = bytes;
+    s.read_cnt_off = o_cnt;
+    return 0;
+}
+// counters[4] like cb_search_status_sync: trees not finished, evaluations, simulations, errors
+int cb_search_read_roots_compact_wait(cb_ctx* ctx, void* out_host, int64_t* counters) {
+    CB_ENTER(ctx);
+    Search& s = ctx->search;
+    if (!s.read_done || !s.read_bytes) { cb_set_error("read_roots_compact_wait: nothing queued"); return -1; }
+    CB_CUDA_OK(cudaEventSynchronize(s.read_done));
+    memcpy(out_host, s.h_read.p, s.read_bytes);
+    if (counters) {
+        const int32_t* c = reinterpret_cast<const int32_t*>(s.h_read.p + s.read_cnt_off);
+        const int n = s.n_trees;
+        // the state section sits behind P | N | W | Q and three header rows: recover T from the byte count
+        const size_t T = (s.read_bytes - (size_t)n * 16) / 22;
+        const int32_t* state = reinterpret_cast<const int32_t*>(s.h_read.p + T * 20) + 3 * (size_t)n;
+        int64_t unfinished = 0, errors = c[2];
+        for (int i = 0; i < n; ++i) {
+            const int stt = state[i] & 255;
+            if (stt != TREE_DONE && stt != TREE_IDLE) ++unfinished;
+            if (state[i] & 256) errors = errors ? errors : 1;
+        }
+        counters[0] = unfinished; counters[1] = c[0]; counters[2] = c[1]; counters[3] = errors;
+    }
+    s.read_bytes = 0;
+    return 0;
+}
+int cb_search_read_roots_compact_sync(cb_ctx* ctx, const int32_t* child_off, void* out_host, void* stream) {
+    if (cb_search_read_roots_compact_async(ctx, child_off, stream)) return -1;
+    return cb_search_read_roots_compact_wait(ctx, out_host, nullptr);
 }
 
 }  // extern "C"

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <string>
 
 void cb_set_error(const std::string& s);
@@ -17,6 +18,20 @@ void cb_set_error(const std::string& s);
             return -1;                                                                        \
         }                                                                                     \
     } while (0)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel: opt in once per (kernel, device) — a process
+// may hold contexts on several GPUs (engine.Engine.get(device)) and launch from several actor threads.  `done` is the kernel's own
+// bit mask of devices already set (a lost race only repeats the idempotent call).
+inline int cb_opt_in_dynamic_smem(const void* kernel, int bytes, std::atomic<uint64_t>& done) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cb_set_error("cudaGetDevice failed"); return -1; }
+    const uint64_t bit = 1ull << (dev & 63);
+    if (done.load(std::memory_order_acquire) & bit) return 0;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) { cb_set_error(std::string("cudaFuncSetAttribute(MaxDynamicSharedMemorySize): ") + cudaGetErrorString(e)); return -1; }
+    done.fetch_or(bit, std::memory_order_release);
+    return 0;
+}
 
 namespace cb {
 

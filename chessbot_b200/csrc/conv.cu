@@ -21,18 +21,25 @@
 //   cluster walks its range layer by layer over its units, and a unit shared between two neighbouring
 //   clusters is handed over through a per-board-pair progress flag in global memory.  The same flag
 //   orders "epilogue wrote layer l" before "TMA reads layer l as the input of layer l+1".
-// * Warp roles per CTA: warp 0 = TMA producer of the activations, warp 10 = TMA producer of the weights (independent of the
-//   progress flags), warp 11 = publisher of the progress flags, warp 1 = MMA issuer (leader CTA), warps 2..9 = epilogue
+// * Warp roles per CTA: warp 0 = TMA producer of the activations, warp 2 = TMA producer of the weights (independent of the
+//   progress flags), warp 3 = publisher of the progress flags, warp 1 = MMA issuer (leader CTA), warps 4..11 = epilogue
 //   (tcgen05.ld -> BN scale/shift -> +skip -> LeakyReLU -> bf16 -> HBM in the same tile-native layout; on
 //   the last layer also the three 1x1 head convolutions of model.py:43,52 as dot products over the fp32
-//   row).  Two epilogue warps share a TMEM lane quarter and split the channel batches.
+//   row).  Two epilogue warps share a TMEM lane quarter and split the channel batches.  The four control warps are one
+//   warpgroup and hand most of their registers to the two epilogue warpgroups (setmaxnreg), which hold the prefetched
+//   skip tiles of a whole item in registers.
+// * The residual stream x_{i+1} = LReLU(x_i + branch) crosses all blocks: rounding it to bf16 at every block is the largest
+//   error term of a bf16 tower (profiles/r2_precision_variants.json: max |dvalue| 3.3e-2 -> 1.2e-2 at 20x256).  So the stream
+//   is kept as bf16 hi (the tile the next convolution's TMA reads) + bf16 lo = bf16(x - hi) in a second buffer of the same
+//   layout that only the epilogue touches, in place (TowerParams::lo_buf): the skip add sees ~16 mantissa bits.
 #include <stdlib.h>
 
 #include "kernels.cuh"
 
 namespace cb {
 
-constexpr int CONV_THREADS = 384;  // activation producer, MMA issuer, 8 epilogue warps, weight producer, flag publisher
+constexpr int CONV_THREADS = 384;  // activation producer, MMA issuer, weight producer, flag publisher, 8 epilogue warps
+constexpr int CTRL_REGS = 56, EPI_REGS = 224;  // setmaxnreg split: 128 * 56 + 256 * 224 <= 64 K registers
 constexpr int PUB_SLOTS = 8;
 constexpr int A_SLOTS = 3, B_SLOTS = 16;  // weight ring: up to 16 stages inside B_RING_BYTES
 constexpr int A_SLOT_BYTES = ACT_K64_BYTES;  // one board pair x 64 channels
@@ -144,6 +151,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
     ptx::tc_fence_after();
     const uint32_t tmem = s->tmem_base;
 
+    if (warp < 4) {
+    // the inference epilogue keeps hi + lo skip tiles of a whole item in registers: the control warpgroup gives its own away
+    if constexpr (!STATS) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CTRL_REGS));
     if (warp == 0) {
         // ------------------------------------------------------------------ activation producer (both CTAs; whole warp, one elected lane issues)
         uint32_t a_it = 0;
@@ -189,7 +199,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
             l = nl_;
             k = nk_;
         }
-    } else if (warp == 10) {
+    } else if (warp == 2) {
         // ------------------------------------------------------------------ weight producer (both CTAs): the weight stream does not depend on
         // any activation, so it runs ahead of the progress flags the activation producer has to wait for
         uint32_t b_it = 0;
@@ -264,13 +274,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
                 }
             }
         }
-    } else if (warp < 10) {
-        // ------------------------------------------------------------------ epilogue (warps 2..9, both CTAs)
+    } else if (warp == 3) {
+        // ------------------------------------------------------------------ flag publisher (both CTAs): when all eight epilogue warps have
+        // stored item j, release-store the progress flag of its board pair (the release is cumulative over the mbarrier)
+        // for the activation producer of (unit, l + 1), here or in the next cluster
+        if (lane == 0) {
+            uint32_t j = 0;
+            for (int l = 0; l < nl; ++l)
+                for (int k = 0; k < w.nu; ++k) {
+                    const int u = w.unit(k);
+                    if (!w.mine(u, l)) continue;
+                    ptx::mbar_wait(&s->pub_full[j % PUB_SLOTS], (j / PUB_SLOTS) & 1);
+                    ptx::mbar_arrive(&s->pub_empty[j % PUB_SLOTS]);
+                    fence_proxy_async();  // the epilogue's generic stores (observed through the mbarrier) before the TMA reads that follow the flag
+                    st_release_gpu(p.flags + 2 * u + rank, flag_base + l + 1);
+                    ++j;
+                }
+        }
+    }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 4..11, both CTAs)
+        if constexpr (!STATS) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(EPI_REGS));
         // Two warps per TMEM lane quarter (a warp may only read lanes 32*(warp%4)..+31) split the 32-channel
         // batches of the row: warp half h takes batches h, h+2, ...  The skip tile is read through a 4-deep
         // register ring whose first loads are issued BEFORE the accumulator is ready.
         const int q = warp & 3;          // TMEM lane quarter this warp may read
-        const int h = (warp - 2) >> 2;   // which half of the channel batches
+        const int h = (warp - 4) >> 2;   // which half of the channel batches
         const int m = q * 32 + lane;     // accumulator row
         const int g = m >> 3, col = m & 7, row = g >> 1, bip = g & 1;
         const int cell = act_cell(row, bip, col);
@@ -283,6 +312,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
             const uint8_t* skip_buf = (!STATS && L.skip_buf >= 0) ? p.bufs[L.skip_buf] : nullptr;
             uint8_t* out_buf = p.bufs[L.out_buf];
             const bool has_skip = !STATS && skip_buf != nullptr;
+            // residual stream in two bf16 halves: layers whose output IS the stream (stem, second conv of a block) also store
+            // lo = bf16(x - hi); the skip add of the next block reads hi + lo.  Same thread, same cell: updated in place.
+            uint8_t* lo_buf = STATS ? nullptr : p.lo_buf;
+            const bool skip_lo = has_skip && lo_buf != nullptr;
+            const bool write_lo = lo_buf != nullptr && (has_skip || l == 0) && !(nl == 1);
             const bool heads = !STATS && p.head_w != nullptr && l == nl - 1;
             for (int k = 0; k < w.nu; ++k) {
                 const int u = w.unit(k);
@@ -293,23 +327,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
                 // the skip tile is the output of (unit, layer - 2): if another cluster wrote it, it is only known to be
                 // complete once this item's own operands have been loaded (the producer waited for the flag)
                 const bool skip_early = has_skip && w.mine(u, l - 2);
-                uint4 sk[4][4];
-                auto load_skip = [&](uint4 (&dst)[4], int cb) {
+                uint4 sk[4][4], sl[4][4];
+                auto load_skip = [&](int r, int cb) {
 #pragma unroll
-                    for (int jj = 0; jj < 4; ++jj)
-                        dst[jj] = __ldcg(reinterpret_cast<const uint4*>(skip_buf + act_offset_bytes(pair, cjo, cb * 4 + jj, cell)));
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const size_t off = act_offset_bytes(pair, cjo, cb * 4 + jj, cell);
+                        sk[r][jj] = __ldcg(reinterpret_cast<const uint4*>(skip_buf + off));
+                        if (skip_lo) sl[r][jj] = __ldcg(reinterpret_cast<const uint4*>(lo_buf + off));
+                    }
                 };
                 if (active && skip_early) {
 #pragma unroll
                     for (int r = 0; r < 4; ++r)
-                        if (r < nk) load_skip(sk[r], h + 2 * r);
+                        if (r < nk) load_skip(r, h + 2 * r);
                 }
                 ptx::mbar_wait(&s->acc_full[st], (j >> 1) & 1);
                 ptx::tc_fence_after();
                 if (active && has_skip && !skip_early) {
 #pragma unroll
                     for (int r = 0; r < 4; ++r)
-                        if (r < nk) load_skip(sk[r], h + 2 * r);
+                        if (r < nk) load_skip(r, h + 2 * r);
                 }
                 float h0 = 0.f, h1 = 0.f, h2 = 0.f;
                 if (active) {
@@ -329,6 +366,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
                             for (int jj = 0; jj < 4; ++jj) {
                                 float v[8];
                                 const uint32_t* skw = reinterpret_cast<const uint32_t*>(&sk[r][jj]);
+                                const uint32_t* slw = reinterpret_cast<const uint32_t*>(&sl[r][jj]);
                                 const float4 sa = __ldg(sc4 + jj * 2), sb = __ldg(sc4 + jj * 2 + 1);
                                 const float4 ha = __ldg(sh4 + jj * 2), hb = __ldg(sh4 + jj * 2 + 1);
                                 const float scl[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
@@ -339,7 +377,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
                                     float x = fmaf(__uint_as_float(acc[jj * 8 + e]), scl[e], shf[e]);
                                     if (has_skip) {
                                         const uint32_t wv = skw[e >> 1];
-                                        x += __uint_as_float((e & 1) ? (wv & 0xFFFF0000u) : (wv << 16));
+                                        float sv = __uint_as_float((e & 1) ? (wv & 0xFFFF0000u) : (wv << 16));
+                                        if (skip_lo) {
+                                            const uint32_t lv = slw[e >> 1];
+                                            sv += __uint_as_float((e & 1) ? (lv & 0xFFFF0000u) : (lv << 16));
+                                        }
+                                        x += sv;
                                     }
                                     x = x > 0.f ? x : x * p.slope;
                                     v[e] = x;
@@ -356,8 +399,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
                                 o.y = *reinterpret_cast<uint32_t*>(&t1);
                                 o.z = *reinterpret_cast<uint32_t*>(&t2);
                                 o.w = *reinterpret_cast<uint32_t*>(&t3);
-                                uint8_t* dst = out_buf + act_offset_bytes(pair, cjo, cb * 4 + jj, cell);
+                                const size_t ooff = act_offset_bytes(pair, cjo, cb * 4 + jj, cell);
+                                uint8_t* dst = out_buf + ooff;
                                 *reinterpret_cast<uint4*>(dst) = o;
+                                if (write_lo) {
+                                    const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+                                    float d[8];
+#pragma unroll
+                                    for (int e = 0; e < 8; ++e)
+                                        d[e] = v[e] - __uint_as_float((e & 1) ? (ow[e >> 1] & 0xFFFF0000u) : (ow[e >> 1] << 16));
+                                    uint4 ol;
+                                    __nv_bfloat162 u0 = __floats2bfloat162_rn(d[0], d[1]), u1 = __floats2bfloat162_rn(d[2], d[3]);
+                                    __nv_bfloat162 u2 = __floats2bfloat162_rn(d[4], d[5]), u3 = __floats2bfloat162_rn(d[6], d[7]);
+                                    ol.x = *reinterpret_cast<uint32_t*>(&u0);
+                                    ol.y = *reinterpret_cast<uint32_t*>(&u1);
+                                    ol.z = *reinterpret_cast<uint32_t*>(&u2);
+                                    ol.w = *reinterpret_cast<uint32_t*>(&u3);
+                                    uint8_t* dl = lo_buf + ooff;
+                                    *reinterpret_cast<uint4*>(dl) = ol;
+                                    if (p.full_sectors) {
+                                        if (col == 0) *reinterpret_cast<uint4*>(dl - 16) = make_uint4(0u, 0u, 0u, 0u);
+                                        if (col == 7) *reinterpret_cast<uint4*>(dl + 16) = make_uint4(0u, 0u, 0u, 0u);
+                                    }
+                                }
                                 // a board row (8 cells, 128 B) starts 16 B into a 32-B sector: the first / last column also store the zero
                                 // border cell next to theirs, so every row is five WHOLE sectors and L2 never has to fetch a partially
                                 // written sector from DRAM before writing it back (only where the tensors overflow L2: TowerParams::full_sectors)
@@ -381,7 +445,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
                                 atomicAdd(&s_head[cb * 32 + lane], rsum[0]);        // 4 lane quarters x item after item: little contention
                                 atomicAdd(&s_head[256 + cb * 32 + lane], rsq[0]);
                             }
-                            if (has_skip && kk + 4 < nk) load_skip(sk[r], h + 2 * (kk + 4));
+                            if (has_skip && kk + 4 < nk) load_skip(r, h + 2 * (kk + 4));
                         }
                     }
                 }
@@ -399,7 +463,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
                         ho[0] = h0 + hp[0]; ho[1] = h1 + hp[1]; ho[2] = h2 + hp[2];
                     }
                 }
-                // "layer l of this board pair is in memory": the warp reports to the flag publisher (warp 11), which issues
+                // "layer l of this board pair is in memory": the warp reports to the flag publisher (warp 3), which issues
                 // the generic->async proxy fence and the device-scope release.  Both cost microseconds; on an epilogue warp
                 // they would bound the item rate of narrow layers (measured: 2,000 cycles of accumulator hand-back wait
                 // per item at N = 64).
@@ -411,23 +475,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
                 __syncwarp();
                 ++j;
             }
-        }
-    } else if (warp == 11) {
-        // ------------------------------------------------------------------ flag publisher (both CTAs): when all eight epilogue warps have
-        // stored item j, release-store the progress flag of its board pair (the release is cumulative over the mbarrier)
-        // for the activation producer of (unit, l + 1), here or in the next cluster
-        if (lane == 0) {
-            uint32_t j = 0;
-            for (int l = 0; l < nl; ++l)
-                for (int k = 0; k < w.nu; ++k) {
-                    const int u = w.unit(k);
-                    if (!w.mine(u, l)) continue;
-                    ptx::mbar_wait(&s->pub_full[j % PUB_SLOTS], (j / PUB_SLOTS) & 1);
-                    ptx::mbar_arrive(&s->pub_empty[j % PUB_SLOTS]);
-                    fence_proxy_async();  // the epilogue's generic stores (observed through the mbarrier) before the TMA reads that follow the flag
-                    st_release_gpu(p.flags + 2 * u + rank, flag_base + l + 1);
-                    ++j;
-                }
         }
     }
     ptx::tc_fence_before();
@@ -496,12 +543,10 @@ static int make_row_map(CUtensorMap* tm, const void* base, uint64_t rows, uint32
 int conv_make_row_map(CUtensorMap* tm, const void* base, uint64_t rows, uint32_t box_rows) { return make_row_map(tm, base, rows, box_rows); }
 
 int launch_tower(const TowerParams& p, int num_sms, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        CB_CUDA_OK(cudaFuncSetAttribute(tower_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV_SMEM_BYTES));
-        CB_CUDA_OK(cudaFuncSetAttribute(tower_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CONV_SMEM_BYTES));
-        attr_set = true;
-    }
+    static std::atomic<uint64_t> smem_set[2];
+    if (cb_opt_in_dynamic_smem((const void*)tower_tcgen05_kernel<false>, (int)CONV_SMEM_BYTES, smem_set[0]) ||
+        cb_opt_in_dynamic_smem((const void*)tower_tcgen05_kernel<true>, (int)CONV_SMEM_BYTES, smem_set[1]))
+        return -1;
     if (p.n % 64 != 0 || p.n > 256 || p.n < 64 || p.nl < 1 || p.nl > 255 || p.pairs < 1) {
         cb_set_error("tower: unsupported shape");
         return -1;

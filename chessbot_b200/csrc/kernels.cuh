@@ -42,6 +42,8 @@ struct TowerParams {
     uint8_t* bufs[4];           // raw pointers of the same four buffers (epilogue stores, skip reads)
     const float* head_w;        // [3][n] 1x1 head conv weights fused into the LAST layer, or nullptr
     float* head_out;            // [boards][64][3]
+    uint8_t* lo_buf;            // low half of the residual stream (bf16(x - bf16(x)), same tile-native layout as the activation buffers, only the
+                                // epilogue reads / writes it, in place), or nullptr: stream rounded to bf16 at every block
     double* stats;              // training forward (one layer per launch, no skip): [2][n] per-channel sum / sum of squares of the
                                 // bf16-rounded outputs, accumulated on top of what is there; nullptr otherwise
     int full_sectors;           // epilogue also stores the zero border cells beside the first / last column (whole 32-B DRAM sectors per board
@@ -100,7 +102,8 @@ struct TreeState {  // 80 bytes
     int32_t root_node, root_pos;
     int32_t sims_done, sims_target;
     int32_t n_pending;   // leaves of this tree waiting for their evaluation (slots tree * leaves + 0 .. n_pending - 1)
-    int32_t pad0_, pad1_;
+    int32_t noise_off;   // first of this root's Gamma samples in SearchParams::noise (root children follow in legal-move order)
+    int32_t pad1_;
     int32_t status;
     int32_t n_nodes, n_evals;
     int32_t noisy;       // add_exploration_noise applied at the root (P held in f64)
@@ -129,7 +132,7 @@ struct SearchParams {
     uint16_t* pend_moves;      // [slots][MAX_MOVES]
     int32_t* frame_idx;        // [slots][8] newest first
     double* root_p64;          // [n_trees][MAX_MOVES]
-    const double* noise;       // [n_trees][MAX_MOVES] Gamma(0.3,1) samples drawn by the host (mcts.py:158)
+    const double* noise;       // Gamma(0.3,1) samples drawn by the host (mcts.py:158), tree t's at [trees[t].noise_off ..]
     const double* cpuct_tab;   // [tab_len] log((N+19653)/19652)+1.25 from the host libm
     const double* sqrt_tab;    // [tab_len] pow(N, 0.5) from the host libm
     int tab_len;

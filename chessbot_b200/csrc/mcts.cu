@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_step_kernel(SearchParams
                 // mcts.py:161: P*(1-frac) in f32, noise*frac in f64, sum in f64
                 const float p75 = __fmul_rn(c.P, 0.75f);
                 sp.root_p64[(size_t)tree * MAX_MOVES + i] =
-                    __dadd_rn((double)p75, __dmul_rn(sp.noise[(size_t)tree * MAX_MOVES + i], 0.25));
+                    __dadd_rn((double)p75, __dmul_rn(sp.noise[(size_t)ts.noise_off + i], 0.25));
             }
         }
         __syncwarp();

@@ -192,11 +192,8 @@ int wgrad_splits(int num_sms, int cj_in) {
 }
 
 int launch_wgrad(const WgradParams& p, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        CB_CUDA_OK(cudaFuncSetAttribute(wgrad_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM_BYTES));
-        attr_set = true;
-    }
+    static std::atomic<uint64_t> smem_set;
+    if (cb_opt_in_dynamic_smem((const void*)wgrad_tcgen05_kernel, (int)WG_SMEM_BYTES, smem_set)) return -1;
     if ((p.n != 64 && p.n != 128 && p.n != 256) || (p.cj_in != 8 && p.cj_in != 16 && p.cj_in != 32) || p.pairs < 1 || p.splits < 1) {
         cb_set_error("wgrad: channels (padded) must be 64, 128 or 256");
         return -1;

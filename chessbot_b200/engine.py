@@ -111,8 +111,10 @@ class Engine:
         return act, i16
 
     # ------------------------------------------------------------------ model
-    def load_network(self, weights, filters, blocks, max_batch, slope=0.3, eps=1e-3):
+    def load_network(self, weights, filters, blocks, max_batch, slope=0.3, eps=1e-3, stream_hi_lo=True):
+        """stream_hi_lo: residual stream kept as bf16 hi + lo between blocks (cb_net_set_stream_precision)"""
         check(lib.cb_net_create(self._h, filters, blocks, max_batch, slope, eps), "net_create")
+        check(lib.cb_net_set_stream_precision(self._h, int(bool(stream_hi_lo))), "net_set_stream_precision")
         for name, arr in weights.items():
             a = np.ascontiguousarray(arr, dtype=np.float32)
             check(lib.cb_net_set_tensor(self._h, name.encode(), a.ctypes.data, a.size), "net_set_tensor")
@@ -192,34 +194,40 @@ class Engine:
         self.search_leaves = 1
 
     def search_begin(self, records, sims, cpuct=None, noise=None, max_game_length=512, eval_mode=EVAL_NET, seed=0, leaves=1):
-        """records: list of uint8 [k_i,96]; sims: int or list; cpuct: None / float / list (None = AlphaZero
-        schedule); noise: None or list (per tree) of None / float64 arrays of Gamma(0.3,1) samples.
+        """records: list of uint8 [k_i,96], or (flat uint8 [sum k_i,96], int32 lens) as board.export_records(flat=True) returns them;
+        sims: int or list; cpuct: None / float / list (None = AlphaZero schedule); noise: None, a list (per tree) of None / float64
+        arrays of Gamma(0.3,1) samples, or CSR (flat float64, int64 offsets [n+1]).
         leaves: leaves of a tree evaluated per step — 1 = the reference's sequential simulations (exact visit
-        counts), > 1 = throughput mode with virtual loss (evaluation batch = trees * leaves)."""
-        n = len(records)
+        counts), > 1 = throughput mode with virtual loss (evaluation batch = trees * leaves).
+        Does not synchronise with the device (the library stages the inputs in pinned memory)."""
+        if isinstance(records, tuple):
+            flat, lens = records
+            flat, lens = np.ascontiguousarray(flat), np.ascontiguousarray(lens, dtype=np.int32)
+        else:
+            lens = np.array([len(r) for r in records], dtype=np.int32)
+            flat = np.ascontiguousarray(np.concatenate(records, axis=0))
+        n = len(lens)
         if leaves != getattr(self, "search_leaves", 1):
             check(lib.cb_search_set_leaves(self._h, int(leaves)), "search_set_leaves")
             self.search_leaves = int(leaves)
-        lens = np.array([len(r) for r in records], dtype=np.int32)
-        flat = np.ascontiguousarray(np.concatenate(records, axis=0))
         sims_a = np.full(n, sims, dtype=np.int32) if np.isscalar(sims) else np.asarray(sims, dtype=np.int32)
         if cpuct is None or np.isscalar(cpuct):
             cp = np.full(n, -1.0 if cpuct is None else float(cpuct), dtype=np.float64)
         else:
             cp = np.array([-1.0 if c is None else float(c) for c in cpuct], dtype=np.float64)
-        has_noise = np.zeros(n, dtype=np.uint8)
-        noise_a = None
-        if noise is not None:
-            noise_a = np.zeros((n, CB_MAX_MOVES), dtype=np.float64)
-            for i, z in enumerate(noise):
-                if z is not None:
-                    z = np.asarray(z, dtype=np.float64)[:CB_MAX_MOVES]
-                    noise_a[i, : len(z)] = z
-                    has_noise[i] = 1
+        nz_flat = nz_off = None
+        if isinstance(noise, tuple):
+            nz_flat, nz_off = np.ascontiguousarray(noise[0], dtype=np.float64), np.ascontiguousarray(noise[1], dtype=np.int64)
+        elif noise is not None:
+            parts = [np.zeros(0) if z is None else np.asarray(z, dtype=np.float64)[:CB_MAX_MOVES] for z in noise]
+            nz_off = np.zeros(n + 1, dtype=np.int64)
+            np.cumsum([len(z) for z in parts], out=nz_off[1:])
+            nz_flat = np.ascontiguousarray(np.concatenate(parts)) if nz_off[-1] else None
         self._n_trees = n
-        check(lib.cb_search_begin(self._h, n, flat.ctypes.data, lens.ctypes.data, sims_a.ctypes.data, cp.ctypes.data,
-                                  has_noise.ctypes.data, noise_a.ctypes.data if noise_a is not None else None,
-                                  max_game_length, eval_mode, seed, _stream()), "search_begin")
+        check(lib.cb_search_begin_csr(self._h, n, flat.ctypes.data, lens.ctypes.data, sims_a.ctypes.data, cp.ctypes.data,
+                                      nz_flat.ctypes.data if nz_flat is not None and len(nz_flat) else None,
+                                      nz_off.ctypes.data if nz_off is not None else None,
+                                      max_game_length, eval_mode, seed, _stream()), "search_begin")
 
     def search_run(self, steps):
         check(lib.cb_search_run(self._h, steps, _stream()), "search_run")
@@ -256,12 +264,51 @@ class Engine:
               "read_roots")
         return {"moves": moves, "N": N, "W": W, "Q": Q, "P": P, "n_children": nc, "root_N": root_n, "nodes": nodes}
 
-    def search(self, records, sims, **kw):
-        """Complete batched search on the device network / synthetic network: returns read_roots() + counters."""
+    def search_read_roots_compact_async(self, n_legal):
+        """Queues the packed read-back of the root statistics behind the steps already on the stream (no synchronisation); returns
+        the ticket search_read_roots_compact_wait() takes."""
+        n = self._n_trees
+        off = np.zeros(n + 1, dtype=np.int32)
+        np.cumsum(n_legal, out=off[1:])
+        check(lib.cb_search_read_roots_compact_async(self._h, off.ctypes.data, _stream()), "read_roots_compact_async")
+        return n, off
+
+    def search_read_roots_compact_wait(self, ticket):
+        """Blocks until that read-back has landed (only that: later work on the stream keeps running).  Flat arrays + "off" [n+1]:
+        the children of tree t are [off[t], off[t] + n_children[t]); plus the counters of search_status()."""
+        n, off = ticket
+        T = int(off[-1])
+        buf = np.empty(lib.cb_search_roots_compact_bytes(n, T), dtype=np.uint8)
+        c = np.zeros(4, dtype=np.int64)
+        check(lib.cb_search_read_roots_compact_wait(self._h, buf.ctypes.data, c.ctypes.data), "read_roots_compact_wait")
+        o = 0
+        out = {"off": off, "unfinished": int(c[0]), "evals": int(c[1]), "sims": int(c[2]), "errors": int(c[3])}
+        for key, dt, cnt in (("P", np.float64, T), ("N", np.int32, T), ("W", np.float32, T), ("Q", np.float32, T), ("n_children", np.int32, n),
+                             ("root_N", np.int32, n), ("nodes", np.int32, n), ("state", np.int32, n), ("moves", np.uint16, T)):
+            nb = cnt * np.dtype(dt).itemsize
+            out[key] = buf[o:o + nb].view(dt)
+            o += nb
+        return out
+
+    def search_read_roots_compact(self, n_legal):
+        """Root statistics packed by the roots' legal-move counts: one device-to-host copy."""
+        return self.search_read_roots_compact_wait(self.search_read_roots_compact_async(n_legal))
+
+    def search(self, records, sims, compact_counts=None, **kw):
+        """Complete batched search on the device network / synthetic network: returns read_roots() + counters
+        (compact_counts = the roots' legal-move counts: search_read_roots_compact() instead)."""
         self.search_begin(records, sims, **kw)
         max_sims = int(np.max(sims))
         leaves = self.search_leaves
         self.search_run((max_sims + leaves - 1) // leaves + 1)
+        if compact_counts is not None and leaves == 1:
+            # sequential simulations finish in exactly max_sims + 1 steps: status and root statistics come back in one copy
+            out = self.search_read_roots_compact(compact_counts)
+            if out["errors"]:
+                raise RuntimeError("search: node or position pool exhausted (raise max_nodes / max_positions)")
+            if out["unfinished"]:
+                raise RuntimeError("search did not finish")
+            return out
         st = self.search_status()
         extra = 0
         while st["unfinished"] and not st["errors"] and leaves > 1 and extra < max_sims:
@@ -272,6 +319,6 @@ class Engine:
             raise RuntimeError("search: node or position pool exhausted (raise max_nodes / max_positions)")
         if st["unfinished"]:
             raise RuntimeError("search did not finish")
-        out = self.search_read_roots()
+        out = self.search_read_roots() if compact_counts is None else self.search_read_roots_compact(compact_counts)
         out.update(st)
         return out

@@ -51,19 +51,30 @@ def keras_init_weights(filters, blocks, in_channels=119, seed=None):
 class DeviceNetwork:
     """model.py:30-56 forward graph resident on one B200."""
 
-    def __init__(self, weights, filters, blocks, max_batch=1024, device=None, engine=None):
+    def __init__(self, weights, filters, blocks, max_batch=1024, device=None, engine=None, stream_hi_lo=True):
         """engine: a device context of its own (engine.Engine(device)) instead of the per-GPU default one - one per actor
         thread when several actors share a GPU (the reference runs num_actors processes per GPU, train.py:173,198-201)."""
         from .engine import Engine
         self.weights = {k: np.asarray(v, dtype=np.float32) for k, v in weights.items()}
         self.filters, self.blocks, self.max_batch = filters, blocks, max_batch
+        self.stream_hi_lo = bool(stream_hi_lo)          # residual stream as bf16 hi + lo between blocks (engine.load_network)
         self.engine = Engine.get(device) if engine is None else engine
         self.load()
 
     def load(self):
         """(Re)installs these weights as the engine's network (one network per device context)."""
-        self.engine.load_network(self.weights, self.filters, self.blocks, self.max_batch)
+        self.engine.load_network(self.weights, self.filters, self.blocks, self.max_batch, stream_hi_lo=self.stream_hi_lo)
         self.engine.loaded_network = self
+
+    def sibling(self, index):
+        """The same network resident in extra device context number `index` of this GPU (Engine.actor): lets several batched
+        searches be in flight at once (mcts.SearchStream), each with its own node pool and activations."""
+        sibs = self.__dict__.setdefault("_siblings", {})
+        if index not in sibs:
+            from .engine import Engine
+            sibs[index] = DeviceNetwork(self.weights, self.filters, self.blocks, self.max_batch,
+                                        engine=Engine.actor(index, self.engine.device_index), stream_hi_lo=self.stream_hi_lo)
+        return sibs[index]
 
     def ensure_loaded(self):
         if getattr(self.engine, "loaded_network", None) is not self:

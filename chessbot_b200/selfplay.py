@@ -55,12 +55,16 @@ def playout_cap(config: Config, u: float):
     return do_full_search, num_simulations, (None if do_full_search else 1.0)
 
 
-def play_games(network, n_games=1, config: Config = None, rngs=None, games=None):
+def play_games(network, n_games=1, config: Config = None, rngs=None, games=None, lanes=None):
     """train.py:21-52 for n_games games at once.  rngs: one np.random.Generator per game (default: unseeded,
     like the reference); game i consumes its own stream in the reference's order — playout-cap draw, root noise
     (full searches), move choice — so a game does not depend on which other games share its batch.
+    lanes: on a DeviceNetwork the games are split into that many groups (default 2 from 64 games up) whose searches alternate on
+    the device through mcts.SearchStream: while one group is being searched the host records samples, chooses and plays the
+    moves of the other and exports its next positions.  Results do not depend on `lanes`.
     Returns, per game, the reference's play_game tuple:
     (images, (terminal_values, search_statistics), outcome_str, history_len)."""
+    import torch
     config = Config() if config is None else config
     games = [Game(config) for _ in range(n_games)] if games is None else list(games)
     n_games = len(games)
@@ -68,17 +72,36 @@ def play_games(network, n_games=1, config: Config = None, rngs=None, games=None)
     stats = [[] for _ in range(n_games)]
     images = [[] for _ in range(n_games)]
     on_turn = [[] for _ in range(n_games)]
-    live = [i for i in range(n_games) if not games[i].terminal()]
-    while live:
+    device_net = isinstance(network, mcts.DeviceNetwork)
+    if lanes is None:
+        lanes = 2 if device_net and n_games >= 64 else 1
+    lanes = max(1, lanes if device_net else 1)
+    stream = mcts.SearchStream(network, lanes) if lanes > 1 else None
+    side = torch.cuda.Stream() if stream is not None else None      # sample images are encoded beside the queued searches, not behind them
+    groups = [[i for i in range(g, n_games, lanes) if not games[i].terminal()] for g in range(lanes)]
+
+    def submit(live):
+        """playout-cap draw and root noise of every live game of a group, then the group's search (queued, or run to completion)"""
         full, sims, cpuct, noise = [], [], [], []
         for i in live:
             f, s, c = playout_cap(config, rngs[i].random())
             full.append(f); sims.append(s); cpuct.append(c)
             noise.append(rngs[i].gamma(mcts.ROOT_DIRICHLET_ALPHA, 1, len(games[i].board.legal_moves)) if f else None)
-        roots = mcts.search_batch([games[i] for i in live], network, sims, full, cpuct, noise=noise)
-        rec = [k for k, f in enumerate(full) if f]          # only full-search moves are training samples (train.py:43-47)
+        batch = [games[i] for i in live]
+        if stream is None:
+            return full, mcts.search_batch(batch, network, sims, full, cpuct, noise=noise)
+        return full, stream.submit(batch, sims, full, cpuct, noise=noise)
+
+    def finish(live, full, roots):
+        """samples of the full searches (train.py:43-47), move choice, moves played; returns the games still running"""
+        rec = [k for k, f in enumerate(full) if f]
         if rec:
-            imgs = gameimage.boards_to_images([games[live[k]].board for k in rec], config.T).astype(np.int16)
+            if side is not None:
+                side.wait_stream(torch.cuda.current_stream())       # nothing to wait for in practice: orders allocator reuse
+                with torch.cuda.stream(side):
+                    imgs = gameimage.boards_to_images([games[live[k]].board for k in rec], config.T).astype(np.int16)
+            else:
+                imgs = gameimage.boards_to_images([games[live[k]].board for k in rec], config.T).astype(np.int16)
             for img, k in zip(imgs, rec):
                 g = games[live[k]]
                 stats[live[k]].append(search_statistics_from_root(config, roots[k], g.to_play()))
@@ -89,7 +112,17 @@ def play_games(network, n_games=1, config: Config = None, rngs=None, games=None)
             root = roots[k]                    # device roots: move choice from the read-back counts (same NumPy / RNG calls as select_move)
             games[i].make_move(mcts._select_move_from_counts(root._stats[0], root._stats[1], rngs[i], temp) if hasattr(root, "_stats")
                                else mcts.select_move(root, rngs[i], temp))
-        live = [i for i in live if not games[i].terminal()]
+        return [i for i in live if not games[i].terminal()]
+
+    pending = [submit(g) if g else None for g in groups]
+    while any(p is not None for p in pending):
+        for gi in range(lanes):
+            if pending[gi] is None:
+                continue
+            full, res = pending[gi]
+            roots = res if stream is None else stream.collect(res)
+            groups[gi] = finish(groups[gi], full, roots)
+            pending[gi] = submit(groups[gi]) if groups[gi] else None
     out = []
     for i, g in enumerate(games):
         terminal_values = [g.terminal_value(player) for player in on_turn[i]]

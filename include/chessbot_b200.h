@@ -68,6 +68,7 @@ typedef struct cb_ctx cb_ctx;
 cb_ctx* cb_ctx_create(int device);                 /* one per GPU / process; NULL + cb_last_error() on failure */
 void cb_ctx_destroy(cb_ctx* ctx);
 int cb_ctx_sm_count(const cb_ctx* ctx);
+int cb_ctx_device(const cb_ctx* ctx);             /* the CUDA device of this context; every entry point makes it current */
 /* exp() used for priors (mcts.py:94): f32 table indexed by the bf16 bit pattern of the logit.  The Python
  * host fills it with np.exp so priors are bit-identical to NumPy on that host; default = expf. */
 int cb_set_exp_table(cb_ctx* ctx, const float* table_host /*[65536]*/);
@@ -88,6 +89,11 @@ int cb_net_create(cb_ctx* ctx, int filters, int blocks, int max_batch, float lea
  * "value.fc2" [C,1], "policy.conv" [C,2], "policy.bn" [4,2], "policy.fc" [128,4672]. */
 int cb_net_set_tensor(cb_ctx* ctx, const char* name, const float* host, size_t count);
 int cb_net_finalize(cb_ctx* ctx);                  /* fold BN, pack bf16 weights, upload */
+/* How the residual stream x_{i+1} = LReLU(x_i + branch_i) of model.py:19-28 is kept between blocks.  1 (default): bf16 hi + bf16 lo
+ * (~16 mantissa bits: at 20x256 the 2e-2 tolerance on the value holds with margin, profiles/r2_precision_variants.json);
+ * 0: rounded to bf16 at every block (round-1 behaviour, one activation buffer less).  The reference's TF-TRT FP32 graph has no
+ * counterpart (it never rounds).  Call between cb_net_create and cb_net_finalize. */
+int cb_net_set_stream_precision(cb_ctx* ctx, int hi_lo);
 /* planes (tile-native bf16) -> value f32[n] and policy logits [n][4672] (bf16 and/or f32, either may be NULL) */
 int cb_net_forward(cb_ctx* ctx, const void* planes_act_dev, int n, float* value_dev, void* logits_bf16_dev,
                    float* logits_f32_dev, void* stream);
@@ -118,6 +124,12 @@ int cb_search_set_leaves(cb_ctx* ctx, int leaves);
 int cb_search_begin(cb_ctx* ctx, int n_trees, const void* records_host, const int32_t* rec_len, const int32_t* sims,
                     const double* cpuct, const uint8_t* has_noise, const double* noise, int max_game_length, int eval_mode,
                     uint32_t synth_seed, void* stream);
+/* the same with the root noise in CSR form: tree t's samples are noise_flat[noise_off[t] .. noise_off[t+1]) (an empty range = no noise
+ * for that tree; noise_flat NULL = none at all).  Neither variant synchronises with the device: inputs are copied to pinned staging
+ * owned by the context before the call returns. */
+int cb_search_begin_csr(cb_ctx* ctx, int n_trees, const void* records_host, const int32_t* rec_len, const int32_t* sims,
+                        const double* cpuct, const double* noise_flat, const int64_t* noise_off, int max_game_length, int eval_mode,
+                        uint32_t synth_seed, void* stream);
 /* one batch step: encode pending leaves, evaluate them, expand + backup, select the next leaves */
 int cb_search_step(cb_ctx* ctx, void* stream);
 int cb_search_run(cb_ctx* ctx, int steps, void* stream);     /* `steps` x cb_search_step, no host sync */
@@ -129,6 +141,18 @@ int cb_search_status_sync(cb_ctx* ctx, int64_t* counters, void* stream);
 /* root statistics of every tree: [n_trees][CB_MAX_MOVES] arrays + n_children[n_trees], root_n[n_trees], nodes[n_trees] (host) */
 int cb_search_read_roots_sync(cb_ctx* ctx, uint16_t* moves, int32_t* n, float* w, float* q, double* p, int32_t* n_children,
                               int32_t* root_n, int32_t* tree_nodes, void* stream);
+/* the same, packed: the children of tree t at [child_off[t], child_off[t+1]) of every section (child_off[n_trees + 1], host; the caller
+ * knows every root's legal-move count from cb_boards_export_records), one device-to-host copy into pinned staging.  out_host holds
+ * cb_search_roots_compact_bytes(n_trees, T = child_off[n_trees]) bytes:
+ * P f64[T] | N i32[T] | W f32[T] | Q f32[T] | n_children i32[n] | root_N i32[n] | tree_nodes i32[n] | state i32[n] | moves u16[T]
+ * (state = tree status | error << 8; train.py:13-19 reads child.N of the root; mcts.select_move, mcts.py:142-153, the visit counts).
+ * _async queues the read-back (+ an event) behind the search steps already on the stream and returns at once; _wait blocks on that
+ * event only and also delivers the counters of cb_search_status_sync, so a host can collect one search while the next one (another
+ * context on the same stream) is already running - no device-wide or stream-wide synchronisation. */
+size_t cb_search_roots_compact_bytes(int n_trees, int total_children);
+int cb_search_read_roots_compact_sync(cb_ctx* ctx, const int32_t* child_off, void* out_host, void* stream);
+int cb_search_read_roots_compact_async(cb_ctx* ctx, const int32_t* child_off, void* stream);
+int cb_search_read_roots_compact_wait(cb_ctx* ctx, void* out_host, int64_t* counters /*[4] or NULL*/);
 
 /* ---- train.py training step (train.py:150-164 -> model.fit; loss / optimizer of model.py:59-70) ------------------------ */
 /* One SGD step on a batch of replay samples (train.py:104-110: int16 images, terminal values z, visit distributions pi):

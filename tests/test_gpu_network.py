@@ -106,6 +106,82 @@ def test_forward_keras_random_init_relative(engine, filters, blocks, n):
     assert (p32.argmax(1) == p_ref.argmax(1)).mean() > 0.9
 
 
+def _parity_report(tag, v, p, v_ref, p_ref):
+    dp, dv = np.abs(p - p_ref), np.abs(v - v_ref)
+    rep = {"case": tag, "n": int(len(v)), "max_dlogit": float(dp.max()), "p999_dlogit": float(np.quantile(dp, 0.999)),
+           "rms_dlogit": float(np.sqrt(np.mean(dp ** 2))), "max_dvalue": float(dv.max()), "rms_dvalue": float(np.sqrt(np.mean(dv ** 2))),
+           "logit_absmax": float(np.abs(p_ref).max()), "top1_agree": float((p.argmax(1) == p_ref.argmax(1)).mean())}
+    print("\nPARITY " + __import__("json").dumps(rep))
+    try:                                     # kept with the run's artefacts (profiles/r2_parity_*.json are copies of these lines)
+        import os
+        os.makedirs("gpurun_out", exist_ok=True)
+        with open("gpurun_out/parity_network.jsonl", "a") as f:
+            f.write(__import__("json").dumps(rep) + "\n")
+    except OSError:
+        pass
+    return rep
+
+
+def _bench_positions(engine, n, seed):
+    """The bench's own inputs (bench.random_positions_device): device int16 planes for the oracle, checked against the oracle's
+    encoder on a subset (the full encoder parity is tests/test_gpu_encode.py)."""
+    import bench
+    from gpu_util import oracle_board
+    from oracle import pychess_shim as ochess, ref_gameimage
+    boards = bench.random_positions_device(n, seed=seed)
+    pos, fi = engine.upload_records([b.export_record() for b in boards])
+    act, i16 = engine.encode(pos, fi, want_act=True, want_i16=True)
+    images = i16.cpu().numpy()
+    for i in range(0, n, max(1, n // 48)):
+        ob = oracle_board(ochess.STARTING_FEN, " ".join(m.uci() for m in boards[i].move_stack))
+        assert np.array_equal(images[i], ref_gameimage.board_to_image(ob, 8)), i
+    return act, images
+
+
+@pytest.mark.parametrize("filters,blocks,n,hi_lo", [(256, 20, 1024, True), (256, 20, 1024, False), (128, 6, 1024, True), (48, 4, 1024, True)])
+def test_forward_at_the_benched_shape(engine, filters, blocks, n, hi_lo):
+    """the network bench.py times (bench.trained_like_bn weights, seeded random-playout positions, batch 1024)
+    against the torch-fp32 oracle, north_star bar 2e-2 abs on logits AND value.  hi_lo=False is the round-1 datapath (residual
+    stream rounded to bf16 at every block): it misses the bar on the value at 20x256 (emulated 3.3e-2,
+    profiles/r2_precision_variants.json) - kept as a measured comparison with a 5e-2 bar; the shipped default keeps the stream
+    as bf16 hi + lo and must hold 2e-2."""
+    import bench
+    from chessbot_b200.model import keras_init_weights
+    from oracle import ref_model
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    w = bench.trained_like_bn(keras_init_weights(filters, blocks, seed=0), filters, blocks)
+    engine.load_network(w, filters, blocks, max_batch=n, stream_hi_lo=hi_lo)
+    act, images = _bench_positions(engine, n, seed=1000)
+    value, _, lf = engine.forward(act, n, want_bf16=False, want_f32=True)
+    torch.cuda.synchronize()
+    v_ref, p_ref = ref_model.forward(w, images, device="cuda")
+    rep = _parity_report(f"bench weights {blocks}x{filters} stream={'hi+lo' if hi_lo else 'bf16'}", value.cpu().numpy(), lf.cpu().numpy(), v_ref, p_ref)
+    bar = TOL if hi_lo else 5e-2
+    assert rep["max_dlogit"] <= bar and rep["max_dvalue"] <= bar
+    assert rep["top1_agree"] > 0.98
+
+
+@pytest.mark.parametrize("filters,blocks", [(256, 20), (128, 6)])
+def test_forward_calibrated_on_disjoint_positions(engine, filters, blocks):
+    """BN statistics fitted on one seeded set of 1024 positions, parity measured on a DISJOINT set of 1024 (round 1 measured on the
+    16 positions the statistics were fitted to)."""
+    from oracle import ref_model
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    n = 1024
+    _, fit_images = _bench_positions(engine, n, seed=77)
+    w = ref_model.calibrate_bn(ref_model.init_weights(filters, blocks, seed=3), fit_images, device="cuda")
+    engine.load_network(w, filters, blocks, max_batch=n)
+    act, images = _bench_positions(engine, n, seed=78)
+    value, _, lf = engine.forward(act, n, want_bf16=False, want_f32=True)
+    torch.cuda.synchronize()
+    v_ref, p_ref = ref_model.forward(w, images, device="cuda")
+    rep = _parity_report(f"calibrated on disjoint positions {blocks}x{filters}", value.cpu().numpy(), lf.cpu().numpy(), v_ref, p_ref)
+    assert rep["max_dlogit"] <= TOL and rep["max_dvalue"] <= TOL
+    assert rep["top1_agree"] > 0.98
+
+
 def test_forward_is_batch_invariant(engine):
     # the search relies on a position's outputs not depending on its batch slot
     from oracle import ref_model
