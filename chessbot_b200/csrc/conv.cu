@@ -54,7 +54,7 @@ struct ConvSmem {
     uint32_t tmem_base;
 };
 static_assert(sizeof(ConvSmem) <= 1024, "barrier block");
-constexpr int CONV_SMEM_PARAM_FLOATS = 256 * 3 + 2 * 128 * 3;
+constexpr int CONV_SMEM_PARAM_FLOATS = 256 * 3 + 2 * 128 * 3 + EPI_WARPS * 256;  // head weights, head partials, per-warp BN scale / shift
 constexpr size_t CONV_SMEM_BYTES = 1024 + A_SLOTS * A_SLOT_BYTES + B_RING_BYTES + CONV_SMEM_PARAM_FLOATS * 4;
 
 // This cluster's share of the flattened (unit, layer) items i = unit * nl + layer: the range [lo, hi).
@@ -93,6 +93,34 @@ __device__ __forceinline__ void warp_transpose_sum32(float (&v)[32], int lane) {
             const float recv = __shfl_xor_sync(0xffffffffu, send, k);
             v[i] = (up ? v[i + k] : v[i]) + recv;
         }
+    }
+}
+
+// One k-chunk (64 input channels) of one item: the 9 / TPS weight stages of TPS taps each, four K = 16 MMAs per tap.  Unrolled: the tap's
+// start cell (1 + dy) * 20 + 1 + dx inside the activation tile and the K steps are immediates added to the descriptors.
+template <int TPS>
+__device__ __forceinline__ void mma_k_chunk(ConvSmem* s, uint32_t d, uint64_t a_desc, uint64_t b_desc0, uint32_t idesc, uint32_t slot16, uint32_t tap16,
+                                            uint32_t b_ks, int nbs, uint32_t& bs, uint32_t& bph, uint32_t accumulate) {
+    constexpr uint32_t a_ks = 2 * ACT_CHUNK_BYTES / 16;
+#pragma unroll
+    for (int sg = 0; sg < 9 / TPS; ++sg) {
+        ptx::mbar_wait(&s->b_full[bs], bph);
+        ptx::tc_fence_after();
+        const uint64_t bd_slot = b_desc0 + (uint64_t)(bs * slot16);
+        if (ptx::elect_one()) {
+#pragma unroll
+            for (int t = 0; t < TPS; ++t) {
+                const int tap = sg * TPS + t;
+                const uint64_t ad0 = a_desc + (uint64_t)((tap / 3) * 20 + (tap % 3));
+                const uint64_t bd0 = bd_slot + (uint64_t)(t * tap16);  // one tap = N/2 rows x 128 B
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                    ptx::umma2_bf16(d, ad0 + ks * a_ks, bd0 + ks * b_ks, idesc, (tap | ks) != 0 ? 1u : accumulate);
+            }
+            ptx::umma2_commit_mc(&s->b_empty[bs]);  // weight stage of BOTH CTAs is free when these MMAs retire
+        }
+        __syncwarp();
+        if (++bs == (uint32_t)nbs) { bs = 0; bph ^= 1; }
     }
 }
 
@@ -156,7 +184,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
     if constexpr (!STATS) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(CTRL_REGS));
     if (warp == 0) {
         // ------------------------------------------------------------------ activation producer (both CTAs; whole warp, one elected lane issues)
-        uint32_t a_it = 0;
+        uint32_t as = 0, aph = 1;
         // operands of BOTH CTAs complete on the leader's "full" barriers (the MMA issuer lives there)
         const uint32_t a_full0 = ptx::mapa(ptx::smem_u32(&s->a_full[0]), 0);
         // flat walk over this cluster's items with one item of look-ahead: the progress flag of the NEXT item is read
@@ -187,14 +215,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
             advance(nl_, nk_);
             if (nl_ < nl && nl_ > 0) seen = ld_acquire_gpu(p.flags + 2 * w.unit(nk_) + rank);  // consumed at the top of the next item
             for (int kc = 0; kc < L.kc; ++kc) {
-                const int as = a_it % A_SLOTS;
-                ptx::mbar_wait(&s->a_empty[as], ((a_it / A_SLOTS) & 1) ^ 1);
+                ptx::mbar_wait(&s->a_empty[as], aph);
                 if (ptx::elect_one()) {
                     if (rank == 0) ptx::mbar_expect_tx(&s->a_full[as], 2 * ACT_K64_BYTES);
                     ptx::tma_load_2d_pair(a_buf + as * A_SLOT_BYTES, tm_in, 0, (pair * L.cj_in + 8 * (kc % L.kc_in)) * (ACT_CHUNK_BYTES / 128),
                                           a_full0 + as * 8);
                 }
-                ++a_it;
+                if (++as == A_SLOTS) { as = 0; aph ^= 1; }
             }
             l = nl_;
             k = nk_;
@@ -202,7 +229,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
     } else if (warp == 2) {
         // ------------------------------------------------------------------ weight producer (both CTAs): the weight stream does not depend on
         // any activation, so it runs ahead of the progress flags the activation producer has to wait for
-        uint32_t b_it = 0;
+        uint32_t bs = 0, bph = 1;  // ring slot and the parity of its "empty" barrier (a fresh barrier passes a wait on parity 1)
         const uint32_t b_full0 = ptx::mapa(ptx::smem_u32(&s->b_full[0]), 0);
         for (int l = 0; l < nl; ++l) {
             const int kcs = p.layers[l].kc;
@@ -213,13 +240,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
                 for (int kc = 0; kc < kcs; ++kc) {
                     const int wrow = (kc * 2 + (int)rank) * 9 * nh;  // [kc][half][tap][8][N/2][8]
                     for (int sg = 0; sg < stages; ++sg) {
-                        const int bs = b_it % nbs;
-                        ptx::mbar_wait(&s->b_empty[bs], ((b_it / nbs) & 1) ^ 1);
+                        ptx::mbar_wait(&s->b_empty[bs], bph);
                         if (ptx::elect_one()) {
                             if (rank == 0) ptx::mbar_expect_tx(&s->b_full[bs], 2 * slot_bytes);
                             ptx::tma_load_2d_pair(b_buf + bs * slot_bytes, tm_w, 0, wrow + sg * tps * nh, b_full0 + bs * 8);
                         }
-                        ++b_it;
+                        if (++bs == (uint32_t)nbs) { bs = 0; bph ^= 1; }
                     }
                 }
             }
@@ -227,12 +253,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
     } else if (warp == 1) {
         if (rank == 0) {
             // -------------------------------------------------------------- MMA issuer (leader CTA; whole warp, one elected lane issues)
+            // The loop that feeds the tensor pipe must itself stay well under the 512 tensor cycles a weight stage of four N = 256 MMAs
+            // lasts (ncu: with runtime `% nbs` ring arithmetic it took ~70 dependent instructions per stage and the issuing warp was busy
+            // three quarters of the time): ring slots and phases are counters, the nine taps are unrolled so that their descriptor
+            // offsets are immediates.
             const uint32_t idesc = ptx::idesc_bf16_f32(256, n);
             // K-major / no-swizzle descriptors: hi word = SBO | version, lo word = address | LBO; a K=16 step adds to the address field only
             const uint64_t a_desc0 = ptx::smem_desc(ptx::smem_u32(a_buf), ACT_CHUNK_BYTES, 160);
             const uint64_t b_desc0 = ptx::smem_desc(ptx::smem_u32(b_buf), (uint32_t)nh * 16, 128);
-            const uint32_t a_ks = 2 * ACT_CHUNK_BYTES / 16, b_ks = 2 * nh;  // descriptor address units of 16 B
-            uint32_t a_it = 0, b_it = 0, j = 0;
+            const uint32_t b_ks = 2 * nh;  // descriptor address units of 16 B
+            const uint32_t slot16 = slot_bytes / 16, tap16 = (uint32_t)nh * 8;
+            uint32_t as = 0, aph = 0, bs = 0, bph = 0, j = 0;
             for (int l = 0; l < nl; ++l) {
                 const int kcs = p.layers[l].kc;
                 for (int k = 0; k < w.nu; ++k) {
@@ -242,31 +273,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
                     ptx::tc_fence_after();
                     const uint32_t d = tmem + st * 256;
                     for (int kc = 0; kc < kcs; ++kc) {
-                        const int as = a_it % A_SLOTS;
-                        ptx::mbar_wait(&s->a_full[as], (a_it / A_SLOTS) & 1);
+                        ptx::mbar_wait(&s->a_full[as], aph);
                         const uint64_t a_desc = a_desc0 + (uint64_t)(as * (A_SLOT_BYTES / 16));
-                        for (int sg = 0; sg < stages; ++sg) {
-                            const int bs = b_it % nbs;
-                            ptx::mbar_wait(&s->b_full[bs], (b_it / nbs) & 1);
-                            ptx::tc_fence_after();
-                            const uint64_t bd_slot = b_desc0 + (uint64_t)(bs * (slot_bytes / 16));
-                            if (ptx::elect_one()) {
-                                for (int t = 0; t < tps; ++t) {
-                                    const int tap = sg * tps + t;
-                                    const uint64_t ad0 = a_desc + (uint64_t)((tap / 3) * 20 + (tap % 3));  // tap (dy, dx): start cell (1+dy)*20 + 1+dx
-                                    const uint64_t bd0 = bd_slot + (uint64_t)(t * nh * 8);                   // one tap = N/2 rows x 128 B
-#pragma unroll
-                                    for (int ks = 0; ks < 4; ++ks)
-                                        ptx::umma2_bf16(d, ad0 + ks * a_ks, bd0 + ks * b_ks, idesc, (kc | tap | ks) != 0);
-                                }
-                                ptx::umma2_commit_mc(&s->b_empty[bs]);  // weight stage of BOTH CTAs is free when these MMAs retire
-                            }
-                            __syncwarp();
-                            ++b_it;
-                        }
+                        if (tps == 1) mma_k_chunk<1>(s, d, a_desc, b_desc0, idesc, slot16, tap16, b_ks, nbs, bs, bph, kc != 0);
+                        else mma_k_chunk<3>(s, d, a_desc, b_desc0, idesc, slot16, tap16, b_ks, nbs, bs, bph, kc != 0);
                         if (ptx::elect_one()) ptx::umma2_commit_mc(&s->a_empty[as]);
                         __syncwarp();
-                        ++a_it;
+                        if (++as == A_SLOTS) { as = 0; aph ^= 1; }
                     }
                     if (ptx::elect_one()) ptx::umma2_commit_mc(&s->acc_full[st]);
                     __syncwarp();
@@ -303,12 +316,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
         const int m = q * 32 + lane;     // accumulator row
         const int g = m >> 3, col = m & 7, row = g >> 1, bip = g & 1;
         const int cell = act_cell(row, bip, col);
+        const int edge = col == 0 ? -16 : (col == 7 ? 16 : 0);  // byte offset of the zero border cell beside this lane's, if any (one store for both)
         const int cjo = n >> 3, ncb = n >> 5;
         const int nk = (ncb - h + 1) >> 1;  // batches of this warp: cb = h + 2k
         const uint32_t acc_empty0 = ptx::mapa(ptx::smem_u32(&s->acc_empty[0]), 0);
+        // folded BN scale / shift of THIS warp's channel batches, staged in a warp-private slice of shared memory once per layer: read
+        // from global memory in the batch loop they cost an L1 / L2 round trip in front of every group of FFMAs (ncu: half of the
+        // epilogue's stall samples), and the epilogue is what bounds the layers with a residual add
+        float* s_bn = s_hpart + 768 + (warp - 4) * 256;  // [0..127] scale, [128..255] shift of batches h, h + 2, ...
         uint32_t j = 0;
         for (int l = 0; l < nl; ++l) {
             const LayerDesc L = p.layers[l];
+            __syncwarp();
+            for (int k = 0; k < nk; ++k) {
+                s_bn[k * 32 + lane] = __ldg(L.scale + (h + 2 * k) * 32 + lane);
+                s_bn[128 + k * 32 + lane] = __ldg(L.shift + (h + 2 * k) * 32 + lane);
+            }
+            __syncwarp();
             const uint8_t* skip_buf = (!STATS && L.skip_buf >= 0) ? p.bufs[L.skip_buf] : nullptr;
             uint8_t* out_buf = p.bufs[L.out_buf];
             const bool has_skip = !STATS && skip_buf != nullptr;
@@ -358,8 +382,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
                             const int cb = h + 2 * kk;
                             uint32_t acc[32];
                             ptx::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + st * 256 + cb * 32, acc);
-                            const float4* sc4 = reinterpret_cast<const float4*>(L.scale + cb * 32);
-                            const float4* sh4 = reinterpret_cast<const float4*>(L.shift + cb * 32);
+                            const float4* sc4 = reinterpret_cast<const float4*>(s_bn + kk * 32);
+                            const float4* sh4 = reinterpret_cast<const float4*>(s_bn + 128 + kk * 32);
                             ptx::tmem_wait_ld();
                             float rsum[32], rsq[32];  // STATS only
 #pragma unroll
@@ -367,8 +391,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
                                 float v[8];
                                 const uint32_t* skw = reinterpret_cast<const uint32_t*>(&sk[r][jj]);
                                 const uint32_t* slw = reinterpret_cast<const uint32_t*>(&sl[r][jj]);
-                                const float4 sa = __ldg(sc4 + jj * 2), sb = __ldg(sc4 + jj * 2 + 1);
-                                const float4 ha = __ldg(sh4 + jj * 2), hb = __ldg(sh4 + jj * 2 + 1);
+                                const float4 sa = sc4[jj * 2], sb = sc4[jj * 2 + 1];
+                                const float4 ha = sh4[jj * 2], hb = sh4[jj * 2 + 1];
                                 const float scl[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
                                 const float shf[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
 #pragma unroll
@@ -417,18 +441,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
                                     ol.w = *reinterpret_cast<uint32_t*>(&u3);
                                     uint8_t* dl = lo_buf + ooff;
                                     *reinterpret_cast<uint4*>(dl) = ol;
-                                    if (p.full_sectors) {
-                                        if (col == 0) *reinterpret_cast<uint4*>(dl - 16) = make_uint4(0u, 0u, 0u, 0u);
-                                        if (col == 7) *reinterpret_cast<uint4*>(dl + 16) = make_uint4(0u, 0u, 0u, 0u);
-                                    }
+                                    if (p.full_sectors && edge) *reinterpret_cast<uint4*>(dl + edge) = make_uint4(0u, 0u, 0u, 0u);
                                 }
                                 // a board row (8 cells, 128 B) starts 16 B into a 32-B sector: the first / last column also store the zero
                                 // border cell next to theirs, so every row is five WHOLE sectors and L2 never has to fetch a partially
                                 // written sector from DRAM before writing it back (only where the tensors overflow L2: TowerParams::full_sectors)
-                                if (p.full_sectors) {
-                                    if (col == 0) *reinterpret_cast<uint4*>(dst - 16) = make_uint4(0u, 0u, 0u, 0u);
-                                    if (col == 7) *reinterpret_cast<uint4*>(dst + 16) = make_uint4(0u, 0u, 0u, 0u);
-                                }
+                                if (p.full_sectors && edge) *reinterpret_cast<uint4*>(dst + edge) = make_uint4(0u, 0u, 0u, 0u);
                                 if constexpr (STATS) {  // statistics of what was stored (bf16), as the BN pass will read it back
                                     const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
