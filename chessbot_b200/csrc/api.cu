@@ -382,7 +382,7 @@ int cb_net_finalize(cb_ctx* ctx) {
     int cur = 0;
     for (int l = 0; l < nl; ++l) {
         ConvLayer& L = net.layers[l];
-        if (conv_make_row_map(&wm[l], L.w.p, (uint64_t)L.kc * 9 * N, conv_taps_per_stage(N) * N / 2)) return -1;
+        if (conv_make_row_map(&wm[l], L.w.p, (uint64_t)L.kc * 9 * N, conv_taps_per_box(N) * N / 2)) return -1;
         LayerDesc& d = ld[l];
         d.scale = L.scale.p; d.shift = L.shift.p; d.kc = L.kc; d.kc_in = L.kc_in; d.cj_in = L.cj_in; d.w_map = l; d.pad_ = 0;
         if (l == 0) { d.in_buf = 0; d.out_buf = 1; d.skip_buf = -1; }

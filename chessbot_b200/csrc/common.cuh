@@ -89,6 +89,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
+// the same for waits that are expected to last (a producer ahead of its consumer, epilogue warps waiting for the next accumulator, the
+// flag publisher): the hardware may park the thread for up to `hint_ns` instead of returning at once, and wakes it when the phase
+// completes.  A bare try_wait loop re-issues every few cycles (ncu: 35 M of a launch's 300 M warp instructions were such spins) and
+// the tower runs against the power cap.
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity, uint32_t hint_ns = 20000) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+            : "memory");
+    } while (!ok);
+}
 // global -> shared bulk copy (UBLKCP), completion signalled on an mbarrier as transaction bytes
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(

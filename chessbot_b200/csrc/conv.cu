@@ -41,9 +41,9 @@ namespace cb {
 constexpr int CONV_THREADS = 384;  // activation producer, MMA issuer, weight producer, flag publisher, 8 epilogue warps
 constexpr int CTRL_REGS = 56, EPI_REGS = 224;  // setmaxnreg split: 128 * 56 + 256 * 224 <= 64 K registers
 constexpr int PUB_SLOTS = 8;
-constexpr int A_SLOTS = 3, B_SLOTS = 16;  // weight ring: up to 16 stages inside B_RING_BYTES
+constexpr int A_SLOTS = 2, B_SLOTS = 16;  // weight ring: up to 16 stages inside B_RING_BYTES
 constexpr int A_SLOT_BYTES = ACT_K64_BYTES;  // one board pair x 64 channels
-constexpr int B_RING_BYTES = 8 * 128 * 128;  // N = 256: 8 stages of one tap (16 KB per CTA); N <= 128: stages of three taps
+constexpr int B_RING_BYTES = 9 * 128 * 128;  // stages of three taps: N = 256: 3 x 48 KB per CTA, N = 128: 6 x 24 KB, N = 64: 12 x 12 KB
 constexpr int EPI_WARPS = 8;
 
 struct ConvSmem {
@@ -143,9 +143,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
     const int pairs = p.n_boards_dev ? min(p.pairs, (*p.n_boards_dev + 1) >> 1) : p.pairs;
     const int units = (pairs + 1) / 2;  // one unit = two board pairs = one M=256 accumulator stage
     const int n = p.n, nh = n >> 1, nl = p.nl;
-    // a weight stage = `tps` taps of one k-chunk (one TMA box of tps * N/2 rows per CTA): three taps for narrow layers, whose
-    // single-tap stages (4-8 KB, 32-64 tensor cycles per MMA) would be bound by barrier round trips, not by the tensor pipe
-    const int tps = conv_taps_per_stage(n), stages = 9 / tps;
+    // a weight stage = three taps of one k-chunk, fetched as `boxes` TMA boxes of `tpb` taps (kernels.cuh: conv_taps_per_stage)
+    constexpr int tps = 3, stages = 3;
+    const int tpb = conv_taps_per_box(n), boxes = tps / tpb;
     const uint32_t slot_bytes = (uint32_t)tps * nh * 128;
     const int nbs = min(B_SLOTS, B_RING_BYTES / (int)slot_bytes);
     const WorkRange w(cid, nclusters, units, nl);
@@ -215,7 +215,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
             advance(nl_, nk_);
             if (nl_ < nl && nl_ > 0) seen = ld_acquire_gpu(p.flags + 2 * w.unit(nk_) + rank);  // consumed at the top of the next item
             for (int kc = 0; kc < L.kc; ++kc) {
-                ptx::mbar_wait(&s->a_empty[as], aph);
+                ptx::mbar_wait_parked(&s->a_empty[as], aph);
                 if (ptx::elect_one()) {
                     if (rank == 0) ptx::mbar_expect_tx(&s->a_full[as], 2 * ACT_K64_BYTES);
                     ptx::tma_load_2d_pair(a_buf + as * A_SLOT_BYTES, tm_in, 0, (pair * L.cj_in + 8 * (kc % L.kc_in)) * (ACT_CHUNK_BYTES / 128),
@@ -240,10 +240,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
                 for (int kc = 0; kc < kcs; ++kc) {
                     const int wrow = (kc * 2 + (int)rank) * 9 * nh;  // [kc][half][tap][8][N/2][8]
                     for (int sg = 0; sg < stages; ++sg) {
-                        ptx::mbar_wait(&s->b_empty[bs], bph);
+                        ptx::mbar_wait_parked(&s->b_empty[bs], bph);
                         if (ptx::elect_one()) {
                             if (rank == 0) ptx::mbar_expect_tx(&s->b_full[bs], 2 * slot_bytes);
-                            ptx::tma_load_2d_pair(b_buf + bs * slot_bytes, tm_w, 0, wrow + sg * tps * nh, b_full0 + bs * 8);
+                            for (int bx = 0; bx < boxes; ++bx)
+                                ptx::tma_load_2d_pair(b_buf + bs * slot_bytes + bx * tpb * nh * 128, tm_w, 0, wrow + (sg * tps + bx * tpb) * nh, b_full0 + bs * 8);
                         }
                         if (++bs == (uint32_t)nbs) { bs = 0; bph ^= 1; }
                     }
@@ -254,8 +255,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
         if (rank == 0) {
             // -------------------------------------------------------------- MMA issuer (leader CTA; whole warp, one elected lane issues)
             // The loop that feeds the tensor pipe must itself stay well under the 512 tensor cycles a weight stage of four N = 256 MMAs
-            // lasts (ncu: with runtime `% nbs` ring arithmetic it took ~70 dependent instructions per stage and the issuing warp was busy
-            // three quarters of the time): ring slots and phases are counters, the nine taps are unrolled so that their descriptor
+            // lasts (ncu: with runtime `% nbs` ring arithmetic it took ~70 dependent instructions per one-tap stage and the issuing warp was
+            // busy most of the time): ring slots and phases are counters, the nine taps are unrolled so that their descriptor
             // offsets are immediates.
             const uint32_t idesc = ptx::idesc_bf16_f32(256, n);
             // K-major / no-swizzle descriptors: hi word = SBO | version, lo word = address | LBO; a K=16 step adds to the address field only
@@ -275,8 +276,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
                     for (int kc = 0; kc < kcs; ++kc) {
                         ptx::mbar_wait(&s->a_full[as], aph);
                         const uint64_t a_desc = a_desc0 + (uint64_t)(as * (A_SLOT_BYTES / 16));
-                        if (tps == 1) mma_k_chunk<1>(s, d, a_desc, b_desc0, idesc, slot16, tap16, b_ks, nbs, bs, bph, kc != 0);
-                        else mma_k_chunk<3>(s, d, a_desc, b_desc0, idesc, slot16, tap16, b_ks, nbs, bs, bph, kc != 0);
+                        mma_k_chunk<tps>(s, d, a_desc, b_desc0, idesc, slot16, tap16, b_ks, nbs, bs, bph, kc != 0);
                         if (ptx::elect_one()) ptx::umma2_commit_mc(&s->a_empty[as]);
                         __syncwarp();
                         if (++as == A_SLOTS) { as = 0; aph ^= 1; }
@@ -297,7 +297,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
                 for (int k = 0; k < w.nu; ++k) {
                     const int u = w.unit(k);
                     if (!w.mine(u, l)) continue;
-                    ptx::mbar_wait(&s->pub_full[j % PUB_SLOTS], (j / PUB_SLOTS) & 1);
+                    ptx::mbar_wait_parked(&s->pub_full[j % PUB_SLOTS], (j / PUB_SLOTS) & 1);
                     ptx::mbar_arrive(&s->pub_empty[j % PUB_SLOTS]);
                     fence_proxy_async();  // the epilogue's generic stores (observed through the mbarrier) before the TMA reads that follow the flag
                     st_release_gpu(p.flags + 2 * u + rank, flag_base + l + 1);
@@ -365,7 +365,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
                     for (int r = 0; r < 4; ++r)
                         if (r < nk) load_skip(r, h + 2 * r);
                 }
-                ptx::mbar_wait(&s->acc_full[st], (j >> 1) & 1);
+                ptx::mbar_wait_parked(&s->acc_full[st], (j >> 1) & 1);
                 ptx::tc_fence_after();
                 if (active && has_skip && !skip_early) {
 #pragma unroll
@@ -487,7 +487,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
                 // per item at N = 64).
                 __syncwarp();
                 if (lane == 0) {
-                    ptx::mbar_wait(&s->pub_empty[j % PUB_SLOTS], ((j / PUB_SLOTS) & 1) ^ 1);
+                    ptx::mbar_wait_parked(&s->pub_empty[j % PUB_SLOTS], ((j / PUB_SLOTS) & 1) ^ 1);
                     ptx::mbar_arrive(&s->pub_full[j % PUB_SLOTS]);
                 }
                 __syncwarp();

@@ -37,7 +37,7 @@ struct LayerDesc {
 
 struct TowerParams {
     CUtensorMap tm_act[4];      // the activation buffers as rows of 128 B, box = one 64-channel chunk of a board pair (200 rows)
-    const CUtensorMap* maps;    // device array: packed weights of each layer as rows of 128 B, box = conv_taps_per_stage(n) tap blocks of n/2 rows
+    const CUtensorMap* maps;    // device array: packed weights of each layer as rows of 128 B, box = conv_taps_per_box(n) tap blocks of n/2 rows
     const LayerDesc* layers;    // device array [nl]
     uint8_t* bufs[4];           // raw pointers of the same four buffers (epilogue stores, skip reads)
     const float* head_w;        // [3][n] 1x1 head conv weights fused into the LAST layer, or nullptr
@@ -64,7 +64,12 @@ __host__ __device__ inline size_t conv_weight_index(int kc, int tap, int k /*0..
     const int nh = n >> 1, half = co >= nh, c = co - half * nh;
     return ((size_t)(((kc * 2 + half) * 9 + tap) * 8 + (k >> 3)) * nh + c) * 8 + (k & 7);
 }
-__host__ __device__ inline int conv_taps_per_stage(int n) { return n <= 128 ? 3 : 1; }
+// A weight stage (one ring slot, one "full" / "empty" barrier round trip, 12 MMAs) is always three taps of one k-chunk: the MMA-issuing warp
+// pays its per-stage bookkeeping once per 1536 tensor cycles at N = 256 instead of once per 512 (ncu: with one-tap stages that warp was busy
+// 92 % of the time and bounded the tensor pipe).  A TMA box holds at most 256 rows, so a stage is fetched as one box of three taps
+// (N <= 128) or three boxes of one tap (N = 256).
+__host__ __device__ inline int conv_taps_per_stage(int) { return 3; }
+__host__ __device__ inline int conv_taps_per_box(int n) { return n <= 128 ? 3 : 1; }
 
 struct HeadParams {
     const float* head_raw;   // [boards][64][3]

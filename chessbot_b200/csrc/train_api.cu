@@ -204,7 +204,7 @@ cb_trainer* cb_train_create(cb_ctx* ctx, int filters, int blocks, int batch, flo
     std::vector<CUtensorMap> wm(2 * nl);
     std::vector<LayerDesc> ld(2 * nl);
     if (t->ones.alloc(256) || t->zeros.alloc(256) || launch_fill(t->ones.p, 256, 1.f, nullptr)) return fail();
-    const uint32_t box = conv_taps_per_stage(N) * N / 2;
+    const uint32_t box = conv_taps_per_box(N) * N / 2;
     for (int l = 0; l < nl; ++l) {
         const int kc = l == 0 ? 4 : N / 64;
         if (conv_make_row_map(&wm[l], t->wf[l].p, (uint64_t)kc * 9 * N, box)) return fail();
