@@ -563,6 +563,200 @@ def run_leaf_eval_arm(args):
         dist.destroy_process_group()
 
 
+def _dist_setup():
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    return world, rank, local_rank, barrier
+
+
+def _reduce(world, maxes, sums):
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        t = torch.tensor(maxes, device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        u = torch.tensor(sums, device="cuda", dtype=torch.float64)
+        dist.all_reduce(u, op=dist.ReduceOp.SUM)
+        return t.tolist(), u.tolist()
+    return list(maxes), list(sums)
+
+
+def _oracle_top_moves(boards, weights, sims):
+    """Checker leg (untimed): the reference path's move for these positions — oracle/ref_mcts.py over the torch-fp32 network on the
+    GPU (TF32 off), no root noise, most-visited move with ties to the first (like the device side here)."""
+    import torch
+    from oracle import pychess_shim as ochess, ref_mcts, ref_model
+    from oracle.ref_game import Game as OGame, OracleConfig
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+    class FirstTie:
+        def choice(self, x):
+            return x[0]
+    net = ref_model.as_network(weights, "cuda")
+    out = []
+    for b in boards:
+        ob = ochess.Board()
+        for m in b.move_stack:
+            ob.push_uci(m.uci())
+        out.append(ref_mcts.run_mcts(OGame(OracleConfig(), board=ob), net, sims, 0, False, None, rng=FirstTie())[0])
+    return out
+
+
+def run_puzzles_arm(args):
+    """BASELINE config 4 (puzzles.py:83-86,194-215; eval_trt.py:31-39): a sweep of `--positions` synthetic puzzle positions,
+    `--sims` simulations each, no root noise, the most visited move is the answer.  Positions are sharded over the ranks; every
+    rank feeds them through selfplay.Bot-style batches of `--trees` positions, two batches alternating on the device
+    (mcts.SearchStream).  A step = one batch.  Top-move agreement against the reference path on a seeded subset (untimed)."""
+    import torch
+    from chessbot_b200 import mcts as cb_mcts
+    from chessbot_b200.config import Config
+    from chessbot_b200.game import Game
+    from chessbot_b200.model import DeviceNetwork, keras_init_weights
+    world, rank, local_rank, barrier = _dist_setup()
+    filters, blocks = parse_net(args.net)
+    trees, sims = args.trees, args.sims
+    n_total = args.positions
+    n_mine = len(range(rank, n_total, world))
+    weights = trained_like_bn(keras_init_weights(filters, blocks, seed=0), filters, blocks)
+    weights["policy.fc"] = weights["policy.fc"] * 4.0        # a sharper policy than random init: searches get a favourite (a trained net's regime)
+    net = DeviceNetwork(weights, filters, blocks, max_batch=trees, device=local_rank)
+    boards = random_positions_device(n_mine, seed=7000 + rank, min_plies=8, max_plies=120)
+    cfg = Config()
+    batches = [[Game(cfg, board=b) for b in boards[i:i + trees]] for i in range(0, n_mine, trees)]
+    class FirstTie:
+        def choice(self, x):
+            return x[0]
+    rng = FirstTie()
+    ss = cb_mcts.SearchStream(net, 2)
+    for g in batches[:2]:
+        ss.collect(ss.submit(g[:64], 8, False, None))       # warm both lanes
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    moves, evals, nsims, tickets = [], 0, 0, []
+    for bi, g in enumerate(batches):
+        tickets.append((ss.submit(g, sims, False, None), g))
+        if len(tickets) == 2:
+            tk, gg = tickets.pop(0)
+            moves += [m for m, _ in ss.collect_moves(tk, gg, 0, rng)]
+            evals += ss.last_counters["evals"]; nsims += ss.last_counters["sims"]
+    for tk, gg in tickets:
+        moves += [m for m, _ in ss.collect_moves(tk, gg, 0, rng)]
+        evals += ss.last_counters["evals"]; nsims += ss.last_counters["sims"]
+    barrier()
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    agree = None
+    if rank == 0 and not args.no_parity:
+        k = min(args.agreement_positions, n_mine)
+        ref = _oracle_top_moves(boards[:k], weights, sims)
+        same = sum(a == b for a, b in zip(moves[:k], ref))
+        agree = {"positions": k, "top_move_agreement": same / k, "sims": sims,
+                 "against": "oracle/ref_mcts.py + torch-fp32 network (the reference path), same positions, no root noise"}
+    (dt,), (evals, nsims, n_done) = _reduce(world, [dt], [evals, nsims, len(moves)])
+    if rank == 0:
+        emit(json.dumps({
+            "metric": METRIC, "value": evals / dt, "unit": UNIT, "sims_per_s": nsims / dt, "positions_per_s": n_done / dt, "n_gpus": world,
+            "steps": (n_total + trees * world - 1) // (trees * world), "warmup": 1, "ms_per_step": 1e3 * dt / max(1, len(batches)), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"puzzles.py eval sweep (BASELINE config 4): {n_total} synthetic puzzle positions x {sims} sims, {blocks}x{filters} net, "
+                                   f"batches of {trees} positions per GPU through mcts.SearchStream, most-visited move as the answer",
+                       "net": args.net, "positions": n_total, "sims": sims, "trees_per_gpu": trees, "timing": "wall clock, host objects in / moves out (end to end)"},
+            "agreement": agree, "e2e": {"value": evals / dt, "unit": UNIT, "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
+                                        "what": "the whole sweep IS end to end: host boards -> records -> searches -> moves"},
+            "gpu_launches": int(nsims / max(1, trees)) * 4, "clocks": clocks, "cpu_baseline": None}))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def run_selfplay_arm(args):
+    """BASELINE config 3 read literally (train.py:21-52): `--games` (512) concurrent self-play games in TOTAL, `--sims` (800) simulations per
+    move, sharded by game over the ranks.  With fewer games per GPU the evaluation batch is kept at >= 512 positions by selecting
+    several leaves per tree per step under virtual loss (leaves_per_tree = 512 / games per GPU).  A step = one move of every game (one
+    complete search per game + move choice + the moves played).  Strong scaling: total work is fixed."""
+    import torch
+    from chessbot_b200 import mcts as cb_mcts
+    from chessbot_b200.config import Config
+    from chessbot_b200.game import Game
+    from chessbot_b200.model import DeviceNetwork, keras_init_weights
+    world, rank, local_rank, barrier = _dist_setup()
+    filters, blocks = parse_net(args.net)
+    n_total, sims = args.games, args.sims
+    mine = list(range(rank, n_total, world))
+    leaves = args.leaves if args.leaves > 0 else max(1, min(16, 512 // max(1, len(mine))))
+    weights = trained_like_bn(keras_init_weights(filters, blocks, seed=0), filters, blocks)
+    net = DeviceNetwork(weights, filters, blocks, max_batch=len(mine) * leaves, device=local_rank)
+    all_boards = random_positions_device(n_total, seed=4242, min_plies=0, max_plies=40)     # every rank draws the same 512 openings, keeps its shard
+    cfg = Config()
+    games = [Game(cfg, board=all_boards[i]) for i in mine]
+    rng = np.random.default_rng(11 + rank)
+    K, W = args.steps, max(1, min(args.warmup, 2))
+
+    def move_all(lv):
+        res = cb_mcts.run_mcts_batch(games, net, sims, 30, True, None, rng=rng, leaves_per_tree=lv)
+        c = net.engine.search_status()
+        return res, c["evals"], c["sims"]
+
+    # cost of virtual loss, untimed: the same searches without noise, sequential vs `leaves` per step — do they pick the same move?
+    vl = None
+    if leaves > 1 and not args.no_parity:
+        class FirstTie:
+            def choice(self, x):
+                return x[0]
+        sub = games[:min(64, len(games))]
+        a = cb_mcts.run_mcts_batch(sub, net, sims, 0, False, None, rng=FirstTie(), leaves_per_tree=1)
+        b = cb_mcts.run_mcts_batch(sub, net, sims, 0, False, None, rng=FirstTie(), leaves_per_tree=leaves)
+        vl = {"positions": len(sub), "same_move_as_sequential": sum(x[0] == y[0] for x, y in zip(a, b)) / len(sub)}
+    for _ in range(W):
+        move_all(leaves)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    evals = nsims = 0
+    for _ in range(K):
+        res, e, s_ = move_all(leaves)
+        evals += e; nsims += s_
+        for g, (mv, _) in zip(games, res):
+            if not g.terminal():
+                g.make_move(mv)
+        games[:] = [g if not g.terminal() else Game(cfg) for g in games]       # a finished game is replaced by a new one (train.py:54-79 loops)
+    barrier()
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    (dt,), (evals, nsims) = _reduce(world, [dt], [evals, nsims])
+    if rank == 0:
+        emit(json.dumps({
+            "metric": METRIC, "value": evals / dt, "unit": UNIT, "sims_per_s": nsims / dt, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": 1e3 * dt / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"concurrent self-play (BASELINE config 3, literal): {n_total} games in total x {sims} sims per move, {blocks}x{filters} net, "
+                                   f"sharded by game over {world} GPU(s) = {len(mine)} games per GPU, {leaves} leaf/leaves per tree per step "
+                                   f"(evaluation batch {len(mine) * leaves}); a step = one move of every game",
+                       "net": args.net, "games_total": n_total, "games_per_gpu": len(mine), "sims": sims, "leaves_per_tree": leaves,
+                       "timing": "wall clock through mcts.run_mcts_batch: host objects in, moves played (end to end)"},
+            "virtual_loss_cost": vl,
+            "e2e": {"value": evals / dt, "unit": UNIT, "h2d_bytes_per_step": None, "d2h_bytes_per_step": None, "what": "the timed loop IS end to end"},
+            "gpu_launches": K * ((sims + leaves - 1) // leaves + 1) * 4, "clocks": clocks, "cpu_baseline": None}))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
 def run_train_arm(args):
     """BASELINE config 5: train.py step — 20x256 net, batch 4096 per GPU, data parallel with one NCCL
     all-reduce of the gradient buffer per step.  A step = forward + backward + all-reduce + SGD update on one synthetic batch."""
@@ -746,9 +940,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the untimed checker leg (device network vs the torch-fp32 oracle)")
     ap.add_argument("--stream", default="hilo", choices=["hilo", "bf16"], help="residual stream between blocks: bf16 hi + lo (default) or bf16 (round-1 datapath)")
-    ap.add_argument("--workload", default="search", choices=["search", "leaf_eval", "train"],
+    ap.add_argument("--workload", default="search", choices=["search", "leaf_eval", "train", "puzzles", "selfplay"],
                     help="search = the headline (batched MCTS, BASELINE north_star); leaf_eval = BASELINE config 2 (use --net 6x128); "
-                         "train = BASELINE config 5 (train.py step, --batch per GPU)")
+                         "train = BASELINE config 5 (train.py step, --batch per GPU); puzzles = BASELINE config 4 (--positions x --sims); "
+                         "selfplay = BASELINE config 3 read literally (--games in total x --sims, sharded over the GPUs)")
+    ap.add_argument("--positions", type=int, default=10000, help="puzzles workload: positions in the sweep (all GPUs together)")
+    ap.add_argument("--sims", type=int, default=None, help="puzzles / selfplay workloads: simulations per search (default 400 / 800)")
+    ap.add_argument("--games", type=int, default=512, help="selfplay workload: concurrent games in total")
+    ap.add_argument("--leaves", type=int, default=0, help="selfplay workload: leaves per tree per step (0 = 512 / games per GPU)")
+    ap.add_argument("--agreement-positions", type=int, default=32, help="puzzles workload: positions of the untimed top-move agreement check")
     ap.add_argument("--batch", type=int, default=4096, help="train workload: samples per GPU per step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -758,6 +958,14 @@ def main():
         run_leaf_eval_arm(args)
     elif args.workload == "train":
         run_train_arm(args)
+    elif args.workload == "puzzles":
+        args.sims = 400 if args.sims is None else args.sims
+        run_puzzles_arm(args)
+    elif args.workload == "selfplay":
+        args.sims = 800 if args.sims is None else args.sims
+        if "--steps" not in sys.argv:
+            args.steps = 3
+        run_selfplay_arm(args)
     else:
         run_gpu_arm(args)
 

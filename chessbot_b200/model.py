@@ -159,6 +159,13 @@ def load_weights(path):
 
 
 def load_network(path, max_batch=1024, device=None):
+    """A DeviceNetwork from a save_weights() .npz, or from the reference's own checkpoints: `model.save("….keras")` archives,
+    `.weights.h5` / legacy `.h5` files (train.py:124-136, init.py:44) through chessbot_b200.keras_io (no TensorFlow needed)."""
+    if str(path).endswith((".keras", ".h5", ".hdf5")):
+        from .keras_io import load_keras
+        w, filters, blocks = load_keras(path)
+        w["value.conv"], w["policy.conv"] = w["value.conv"].reshape(-1, 1), w["policy.conv"].reshape(-1, 2)
+        return DeviceNetwork(w, filters, blocks, max_batch, device)
     w, filters, blocks = load_weights(path)
     return DeviceNetwork(w, filters, blocks, max_batch, device)
 
