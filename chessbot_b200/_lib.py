@@ -38,6 +38,8 @@ _SIGS = {
     "cb_uci_to_action": (i32, [C.c_char_p, i32]),
     "cb_move_to_action": (i32, [C.c_uint16, i32]),
     "cb_move_to_uci": (i32, [C.c_uint16, C.c_char_p]),
+    "cb_set_device_allocator": (i32, [vp, vp, vp]),
+    "cb_search_workspace_bytes": (C.c_size_t, [i32, i32, i32, i32, i32]),
     "cb_ctx_create": (vp, [i32]),
     "cb_ctx_destroy": (None, [vp]),
     "cb_ctx_sm_count": (i32, [vp]),

@@ -64,6 +64,33 @@ __global__ void count_unfinished_kernel(const TreeState* trees, int n, int32_t* 
 
 using namespace cb;
 
+// ------------------------------------------------------------------------------------ device memory
+typedef void* (*cb_alloc_fn)(size_t bytes, int device, void* user);
+typedef void (*cb_free_fn)(void* ptr, void* user);
+static cb_alloc_fn g_alloc = nullptr;
+static cb_free_fn g_free = nullptr;
+static void* g_alloc_user = nullptr;
+static bool g_detached = false;   // the host allocator is gone (interpreter shutting down): whatever is still held is left to process exit
+
+int cb_device_alloc(void** ptr, size_t bytes) {
+    *ptr = nullptr;
+    if (!bytes) return 0;
+    if (g_alloc) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        *ptr = g_alloc(bytes, dev, g_alloc_user);
+        if (!*ptr) { cb_set_error("host allocator returned no memory for " + std::to_string(bytes) + " bytes"); return -1; }
+        return 0;
+    }
+    CB_CUDA_OK(cudaMalloc(ptr, bytes));
+    return 0;
+}
+void cb_device_free(void* ptr) {
+    if (!ptr || g_detached) return;
+    if (g_free) g_free(ptr, g_alloc_user);
+    else cudaFree(ptr);
+}
+
 namespace {
 template <class T>
 struct DevBuf {
@@ -73,11 +100,11 @@ struct DevBuf {
         free_();
         n = count;
         if (!count) return 0;
-        CB_CUDA_OK(cudaMalloc(&p, count * sizeof(T)));
+        if (cb_device_alloc((void**)&p, count * sizeof(T))) return -1;
         if (zero) CB_CUDA_OK(cudaMemset(p, 0, count * sizeof(T)));
         return 0;
     }
-    void free_() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void free_() { if (p) cb_device_free(p); p = nullptr; n = 0; }
     ~DevBuf() { free_(); }
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
@@ -204,6 +231,26 @@ static int upload(void* dst, const void* src, size_t bytes) {
 }
 
 extern "C" {
+
+int cb_set_device_allocator(void* (*alloc)(size_t bytes, int device, void* user), void (*release)(void* ptr, void* user), void* user) {
+    if ((alloc == nullptr) != (release == nullptr)) { cb_set_error("cb_set_device_allocator: give both functions or neither"); return -1; }
+    if (!alloc && g_alloc) g_detached = true;   // blocks handed out by the host allocator must not reach cudaFree
+    g_alloc = alloc;
+    g_free = release;
+    g_alloc_user = user;
+    return 0;
+}
+// bytes cb_search_create(max_trees, max_nodes, max_positions, ...) + cb_search_set_leaves(leaves) take from the allocator
+size_t cb_search_workspace_bytes(int max_trees, int max_nodes, int max_positions, int max_sims, int leaves) {
+    const size_t mt = max_trees, mm = mt * MAX_MOVES, ns = mt * (size_t)leaves;
+    size_t b = ((size_t)max_nodes + mt * NODE_CHUNK) * sizeof(Node) + ((size_t)max_positions + mt * POS_CHUNK) * sizeof(Pos) + mt * sizeof(TreeState);
+    b += mm * (8 + 8) + mt;                                                       // root priors f64, noise, flags
+    b += mm * (2 + 4 + 4 + 4 + 8) + mt * 12;                                      // dense read-back staging
+    b += cb_search_roots_compact_bytes(max_trees, (int)mm) + (mt + 1) * 4;        // packed read-back staging
+    b += (size_t)(max_sims + 8) * 16;                                             // ucb tables
+    b += ns * (4 + 8 * 4 + MCTS_MAX_PATH * 4 + MAX_MOVES * 2 + 4 + 4 + sizeof(SlotState)) + act_bytes((int)ns, 128) + ns * 7616 * 2;
+    return b;
+}
 
 cb_ctx* cb_ctx_create(int device) {
     int count = 0;

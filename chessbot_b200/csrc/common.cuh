@@ -9,6 +9,10 @@
 #include <string>
 
 void cb_set_error(const std::string& s);
+// Device memory of the library (network weights / activations, node and position pools, trainer buffers) comes from the allocator the
+// host installed with cb_set_device_allocator (PyTorch's caching allocator in the Python host), else from cudaMalloc.
+int cb_device_alloc(void** ptr, size_t bytes);
+void cb_device_free(void* ptr);
 
 #define CB_CUDA_OK(expr)                                                                      \
     do {                                                                                      \

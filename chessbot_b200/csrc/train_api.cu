@@ -26,15 +26,15 @@ struct TBuf {
     T* p = nullptr;
     size_t n = 0;
     int alloc(size_t count) {
-        if (p) cudaFree(p);
+        if (p) cb_device_free(p);
         p = nullptr;
         n = count;
         if (!count) return 0;
-        CB_CUDA_OK(cudaMalloc(&p, count * sizeof(T)));
+        if (cb_device_alloc((void**)&p, count * sizeof(T))) return -1;
         CB_CUDA_OK(cudaMemset(p, 0, count * sizeof(T)));
         return 0;
     }
-    ~TBuf() { if (p) cudaFree(p); }
+    ~TBuf() { if (p) cb_device_free(p); }
     TBuf() = default;
     TBuf(TBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
     TBuf(const TBuf&) = delete;

@@ -13,6 +13,41 @@ from ._lib import CB_MAX_MOVES, CB_NUM_ACTIONS, CB_POS_BYTES, check, last_error,
 EVAL_NET, EVAL_SYNTH, EVAL_EXTERNAL = 0, 1, 2
 _engines = {}
 
+# ---- device memory: the library allocates what it keeps between calls through PyTorch's caching allocator (cb_set_device_allocator)
+_live_blocks = {}
+
+
+@C.CFUNCTYPE(C.c_void_p, C.c_size_t, C.c_int, C.c_void_p)
+def _torch_alloc(nbytes, device, _user):
+    try:
+        t = torch.empty(int(nbytes), dtype=torch.uint8, device=torch.device("cuda", int(device)))
+    except Exception:                      # noqa: BLE001 - reported by the library as an allocation failure
+        return None
+    _live_blocks[t.data_ptr()] = t
+    return t.data_ptr()
+
+
+@C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)
+def _torch_free(ptr, _user):
+    _live_blocks.pop(ptr, None)
+
+
+def library_device_bytes():
+    """bytes of device memory the library currently holds (all of it PyTorch tensors)"""
+    return sum(t.numel() for t in _live_blocks.values())
+
+
+_allocator_installed = False
+
+
+def _install_allocator():
+    global _allocator_installed
+    if not _allocator_installed:
+        check(lib.cb_set_device_allocator(_torch_alloc, _torch_free, None), "set_device_allocator")
+        _allocator_installed = True
+        import atexit
+        atexit.register(lambda: lib.cb_set_device_allocator(None, None, None))   # no callbacks into a finalising interpreter
+
 
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -57,6 +92,7 @@ class Engine:
         self.device_index = torch.cuda.current_device() if device is None else int(device)
         self.device = torch.device("cuda", self.device_index)
         torch.cuda.set_device(self.device_index)
+        _install_allocator()
         self._h = lib.cb_ctx_create(self.device_index)
         if not self._h:
             raise RuntimeError(f"cb_ctx_create: {last_error()}")
@@ -189,6 +225,11 @@ class Engine:
         max_positions = max_positions or max_trees * (max_sims + 2 + 160)
         if self.search_shape == (max_trees, max_nodes, max_positions, max_sims):
             return
+        need = lib.cb_search_workspace_bytes(max_trees, max_nodes, max_positions, max_sims, 1)
+        free, _total = torch.cuda.mem_get_info(self.device_index)
+        if need > free + torch.cuda.memory_reserved(self.device_index) - torch.cuda.memory_allocated(self.device_index):
+            raise RuntimeError(f"search pool of {need / 2**30:.1f} GiB (trees {max_trees}, nodes {max_nodes}, positions {max_positions}) does not fit the "
+                               f"{free / 2**30:.1f} GiB free on cuda:{self.device_index}: lower max_nodes / max_sims or the number of trees")
         check(lib.cb_search_create(self._h, max_trees, max_nodes, max_positions, max_sims), "search_create")
         self.search_shape = (max_trees, max_nodes, max_positions, max_sims)
         self.search_leaves = 1

@@ -64,6 +64,14 @@ int cb_move_to_action(uint16_t move, int player_white);
 int cb_move_to_uci(uint16_t move, char out[6]);
 
 /* ---- device context --------------------------------------------------------------------------- */
+/* Device memory.  The tensors a call takes or returns are always caller-owned device pointers.  What the library keeps between calls
+ * (packed weights and activations of cb_net_*, the node / position pools of cb_search_*, the trainer's buffers) it takes from the
+ * allocator installed here - the Python host installs PyTorch's caching allocator, so every byte of device memory is owned by
+ * PyTorch - and from cudaMalloc only if none is installed.  Install before the first context is created; process-wide.  Passing NULLs
+ * afterwards detaches the host allocator (interpreter shutdown): blocks still held are then left to process exit. */
+int cb_set_device_allocator(void* (*alloc)(size_t bytes, int device, void* user), void (*release)(void* ptr, void* user), void* user);
+/* what cb_search_create(max_trees, max_nodes, max_positions, max_sims) followed by cb_search_set_leaves(leaves) will ask for */
+size_t cb_search_workspace_bytes(int max_trees, int max_nodes, int max_positions, int max_sims, int leaves);
 typedef struct cb_ctx cb_ctx;
 cb_ctx* cb_ctx_create(int device);                 /* one per GPU / process; NULL + cb_last_error() on failure */
 void cb_ctx_destroy(cb_ctx* ctx);

@@ -332,3 +332,23 @@ def test_config4_top_move_agreement_with_fp32_reference_path():
         in_top3 += omove in top3
     print(f"\nconfig 4 (40 positions x 100 sims, 4x48): top-move agreement {agree}/40, reference move in device top-3 {in_top3}/40")
     assert agree >= 30 and in_top3 >= 36
+
+
+def test_library_memory_is_owned_by_pytorch():
+    """SURVEY.md §8(b) / north_star "PyTorch for tensor ownership only": what the library keeps between calls (weights, activations,
+    node pools) is allocated through PyTorch's caching allocator (cb_set_device_allocator), so torch accounts for it."""
+    import torch
+    from chessbot_b200 import engine as E
+    from chessbot_b200.model import keras_init_weights
+    eng = E.Engine.get()
+    before_lib, before_torch = E.library_device_bytes(), torch.cuda.memory_allocated()
+    eng.load_network(keras_init_weights(64, 2, seed=1), 64, 2, max_batch=512)
+    grown = E.library_device_bytes() - before_lib
+    assert E.library_device_bytes() > 0
+    assert torch.cuda.memory_allocated() - before_torch >= grown > -1
+    need = E.lib.cb_search_workspace_bytes(256, 256 * 40 * 48, 256 * 300, 38, 1)
+    lib0 = E.library_device_bytes()
+    eng.search_shape = None
+    eng.search_create(256, max_nodes=256 * 40 * 48, max_positions=256 * 300, max_sims=38)
+    took = E.library_device_bytes() - lib0
+    assert 0.5 * need <= took <= 1.05 * need + (1 << 20), (need, took)

@@ -202,3 +202,13 @@ def test_batched_record_export_equals_per_board_export():
     recs, n_legal = export_records(boards)
     for b, r, k in zip(boards, recs, n_legal):
         assert np.array_equal(b.export_record(), r) and int(k) == len(b.legal_moves)
+
+
+def test_search_workspace_size_is_reported_before_allocation(cb):
+    """the caller (PyTorch) owns device memory - the library says what a search pool will take (host computation)"""
+    _lib, _ = cb
+    f = _lib.lib.cb_search_workspace_bytes
+    small, big = f(64, 64 * 102 * 48, 64 * 300, 100, 1), f(1024, 1024 * 802 * 48, 1024 * 1000, 800, 1)
+    assert 0 < small < big
+    assert big > 1024 * 802 * 48 * 32                      # at least the node pool (32-byte nodes)
+    assert f(1024, 1024 * 802 * 48, 1024 * 1000, 800, 8) > big
