@@ -54,6 +54,9 @@ _SIGS = {
     "cb_net_forward": (i32, [vp, vp, i32, vp, vp, vp, vp]),
     "cb_synth_forward": (i32, [vp, vp, i32, u32, vp, vp, vp]),
     "cb_policy_softmax": (i32, [vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]),
+    "cb_leaf_eval": (i32, [vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]),
+    "cb_leaf_eval_packed_bytes": (C.c_size_t, [i32, i32]),
+    "cb_leaf_eval_host_sync": (i32, [vp, vp, vp, i32, vp, C.c_size_t, vp]),
     "cb_search_create": (i32, [vp, i32, i32, i32, i32]),
     "cb_search_set_leaves": (i32, [vp, i32]),
     "cb_search_begin": (i32, [vp, i32, vp, vp, vp, vp, vp, vp, i32, i32, u32, vp]),

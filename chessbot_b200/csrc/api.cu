@@ -196,6 +196,17 @@ struct cb_ctx {
     DevBuf<float> exp_table;
     Net net;
     Search search;
+    // cb_leaf_eval_host_sync: device scratch (grow-only) and pinned staging
+    struct LeafEval {
+        int cap = 0;
+        DevBuf<uint8_t> pos, pack;
+        DevBuf<int32_t> frame_idx, cur_idx, cnt;
+        DevBuf<__nv_bfloat16> planes;
+        DevBuf<float> value, priors;
+        DevBuf<uint16_t> moves;
+        DevBuf<int16_t> actions;
+        PinBuf h_in, h_out;
+    } leaf;
 };
 
 // brackets one kernel launch with CUDA events on its stream when profiling is on
@@ -524,6 +535,86 @@ int cb_policy_softmax(cb_ctx* ctx, const void* pos_dev, const int32_t* cur_idx_d
                               out_moves_dev, out_actions_dev, out_priors_dev, out_n_dev, st) || prof_end(ctx, st))
         return -1;
     return 0;
+}
+
+// ---- BASELINE config 2: batched leaf evaluation outside a tree (encode + forward + legal-move mask / softmax) -------------
+int cb_leaf_eval(cb_ctx* ctx, const void* pos_dev, const int32_t* frame_idx_dev, const int32_t* cur_idx_dev, int n, void* planes_act_dev,
+                 float* value_dev, uint16_t* moves_dev, int16_t* actions_dev, float* priors_dev, int32_t* n_moves_dev, void* stream) {
+    CB_ENTER(ctx);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (prof_begin(ctx, CB_PROF_ENCODE, st) || launch_encode((const Pos*)pos_dev, frame_idx_dev, n, (__nv_bfloat16*)planes_act_dev, nullptr, st) ||
+        prof_end(ctx, st))
+        return -1;
+    if (net_tower(ctx, planes_act_dev, n, value_dev, st)) return -1;
+    if (prof_begin(ctx, CB_PROF_POLICY_SOFTMAX, st) ||
+        launch_leaf_priors((const Pos*)pos_dev, cur_idx_dev, n, ctx->net.pfeat.p, ctx->net.wpt.p, ctx->exp_table.p, moves_dev, actions_dev, priors_dev,
+                           n_moves_dev, st) ||
+        prof_end(ctx, st))
+        return -1;
+    return 0;
+}
+size_t cb_leaf_eval_packed_bytes(int n, int total_moves) { return (size_t)n * 12 + 4 + (size_t)total_moves * 8; }
+// The same from HOST game records, end to end: records -> pinned staging -> H2D -> kernels -> packed results -> ONE small + one sized
+// device-to-host copy.  out_host receives value f32[n] | n_moves i32[n] | offsets i32[n + 1] | priors f32[T] | moves u16[T] | actions i16[T]
+// (T = offsets[n] <= total legal moves); returns T, or -1.  out_cap_bytes must hold cb_leaf_eval_packed_bytes(n, T).
+int cb_leaf_eval_host_sync(cb_ctx* ctx, const void* records_host, const int32_t* rec_len, int n, void* out_host, size_t out_cap_bytes, void* stream) {
+    CB_ENTER(ctx);
+    cudaStream_t st = (cudaStream_t)stream;
+    auto& L = ctx->leaf;
+    if (n < 1) { cb_set_error("cb_leaf_eval_host_sync: n < 1"); return -1; }
+    size_t total = 0;
+    for (int i = 0; i < n; ++i) total += rec_len[i];
+    const int cap_moves = n * MAX_MOVES;
+    if (n > L.cap) {
+        const size_t nn = n;
+        if (L.frame_idx.alloc(nn * 8, false) || L.cur_idx.alloc(nn, false) || L.cnt.alloc(nn, false) || L.planes.alloc(act_bytes(n, 128) / 2) ||
+            L.value.alloc(nn, false) || L.priors.alloc(nn * MAX_MOVES, false) || L.moves.alloc(nn * MAX_MOVES, false) ||
+            L.actions.alloc(nn * MAX_MOVES, false) || L.pack.alloc(cb_leaf_eval_packed_bytes(n, cap_moves), false))
+            return -1;
+        L.cap = n;
+    }
+    if (L.pos.n < total * sizeof(Pos) && L.pos.alloc(total * sizeof(Pos) * 5 / 4 + 4096, false)) return -1;
+    // staging: positions | frame_idx [n][8] | cur_idx [n]
+    const size_t b_pos = total * sizeof(Pos), o_fi = (b_pos + 15) & ~(size_t)15, o_ci = o_fi + (size_t)n * 32;
+    if (L.h_in.reserve(o_ci + (size_t)n * 4)) return -1;
+    memcpy(L.h_in.p, records_host, b_pos);
+    const Pos* rec = reinterpret_cast<const Pos*>(L.h_in.p);
+    int32_t* fi = reinterpret_cast<int32_t*>(L.h_in.p + o_fi);
+    int32_t* ci = reinterpret_cast<int32_t*>(L.h_in.p + o_ci);
+    size_t off = 0;
+    for (int i = 0; i < n; ++i) {  // frames newest first: back to the start of the record or of the game (gameimage.py:170-181)
+        int cur = (int)(off + rec_len[i] - 1);
+        ci[i] = cur;
+        for (int t = 0; t < 8; ++t) fi[i * 8 + t] = -1;
+        for (int t = 0; t < 8; ++t) {
+            fi[i * 8 + t] = cur;
+            if (rec[cur].ply == 0 || cur == (int)off) break;
+            --cur;
+        }
+        off += rec_len[i];
+    }
+    CB_CUDA_OK(cudaMemcpyAsync(L.pos.p, L.h_in.p, b_pos, cudaMemcpyHostToDevice, st));
+    CB_CUDA_OK(cudaMemcpyAsync(L.frame_idx.p, fi, (size_t)n * 32, cudaMemcpyHostToDevice, st));
+    CB_CUDA_OK(cudaMemcpyAsync(L.cur_idx.p, ci, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    if (cb_leaf_eval(ctx, L.pos.p, L.frame_idx.p, L.cur_idx.p, n, L.planes.p, L.value.p, L.moves.p, L.actions.p, L.priors.p, L.cnt.p, stream)) return -1;
+    if (launch_pack_leaf_eval(n, L.value.p, L.cnt.p, L.moves.p, L.actions.p, L.priors.p, L.pack.p, cap_moves, st)) return -1;
+    const size_t b_hdr = (size_t)n * 12 + 4;
+    if (L.h_out.reserve(cb_leaf_eval_packed_bytes(n, cap_moves))) return -1;
+    CB_CUDA_OK(cudaMemcpyAsync(L.h_out.p, L.pack.p, b_hdr, cudaMemcpyDeviceToHost, st));
+    CB_CUDA_OK(cudaStreamSynchronize(st));
+    const int T = reinterpret_cast<const int32_t*>(L.h_out.p)[3 * n];
+    if (T < 0 || T > cap_moves) { cb_set_error("cb_leaf_eval_host_sync: corrupt offsets"); return -1; }
+    if (cb_leaf_eval_packed_bytes(n, T) > out_cap_bytes) { cb_set_error("cb_leaf_eval_host_sync: output buffer too small"); return -1; }
+    const uint8_t* d_pri = L.pack.p + b_hdr;
+    const uint8_t* d_mv = d_pri + (size_t)cap_moves * 4;
+    const uint8_t* d_act = d_mv + (size_t)cap_moves * 2;
+    uint8_t* h = L.h_out.p + b_hdr;
+    CB_CUDA_OK(cudaMemcpyAsync(h, d_pri, (size_t)T * 4, cudaMemcpyDeviceToHost, st));
+    CB_CUDA_OK(cudaMemcpyAsync(h + (size_t)T * 4, d_mv, (size_t)T * 2, cudaMemcpyDeviceToHost, st));
+    CB_CUDA_OK(cudaMemcpyAsync(h + (size_t)T * 6, d_act, (size_t)T * 2, cudaMemcpyDeviceToHost, st));
+    CB_CUDA_OK(cudaStreamSynchronize(st));
+    memcpy(out_host, L.h_out.p, cb_leaf_eval_packed_bytes(n, T));
+    return T;
 }
 
 int cb_profile(cb_ctx* ctx, int enable) {

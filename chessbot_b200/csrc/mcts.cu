@@ -451,6 +451,97 @@ __global__ void __launch_bounds__(128) policy_softmax_kernel(const Pos* __restri
     for (int k = lane; k < nm; k += 32) out_priors[(size_t)i * MAX_MOVES + k] = __fdiv_rn(s_p[warp][k], sum);
     if (lane == 0) out_n[i] = nm;
 }
+// BASELINE config 2 without the dense 4672-logit matrix: one warp per position generates the ordered legal moves of pos[cur_idx[i]] and
+// evaluates the policy Dense only for them - a lane per move, the 128-long fmaf chain over the transposed weights WT[action] in the
+// same order as the dense kernel and the search's expansion (same bits) - then bf16 -> exp table, NumPy pairwise sum, divide
+// (mcts.py:91-101).  ~35 of 4672 logits per position: 130 x less Dense work, no [n][4672] tensor in HBM.
+__global__ void __launch_bounds__(128) leaf_priors_kernel(const Pos* __restrict__ pos, const int32_t* __restrict__ cur_idx, int n,
+                                                          const float* __restrict__ pfeat, const float* __restrict__ wpt, const float* __restrict__ exp_table,
+                                                          uint16_t* __restrict__ out_moves, int16_t* __restrict__ out_actions,
+                                                          float* __restrict__ out_priors, int32_t* __restrict__ out_n) {
+    __shared__ float s_p[4][MAX_MOVES];
+    __shared__ uint16_t s_m[4][MAX_MOVES];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 4 + warp;
+    if (i >= n) return;
+    const Pos p = pos[cur_idx[i]];
+    const int nm = generate_legal_warp(p, s_m[warp], lane);
+    __syncwarp();
+    const float4* pf = reinterpret_cast<const float4*>(pfeat + (size_t)i * 128);
+    for (int k = lane; k < nm; k += 32) {
+        const int a = move_to_action(s_m[warp][k], p.turn);
+        const float4* wr = reinterpret_cast<const float4*>(wpt + (size_t)a * 128);
+        float acc = 0.f;
+#pragma unroll 8
+        for (int q = 0; q < 32; ++q) {
+            const float4 w = wr[q], f = pf[q];
+            acc = fmaf(f.x, w.x, acc); acc = fmaf(f.y, w.y, acc); acc = fmaf(f.z, w.z, acc); acc = fmaf(f.w, w.w, acc);
+        }
+        out_moves[(size_t)i * MAX_MOVES + k] = s_m[warp][k];
+        out_actions[(size_t)i * MAX_MOVES + k] = (int16_t)a;
+        s_p[warp][k] = exp_table[__bfloat16_as_ushort(__float2bfloat16_rn(acc))];
+    }
+    __syncwarp();
+    const float sum = numpy_sum_f32_warp(s_p[warp], nm, lane);
+    for (int k = lane; k < nm; k += 32) out_priors[(size_t)i * MAX_MOVES + k] = __fdiv_rn(s_p[warp][k], sum);
+    if (lane == 0) out_n[i] = nm;
+}
+int launch_leaf_priors(const Pos* pos, const int32_t* cur_idx, int n, const float* pfeat, const float* wpt, const float* exp_table,
+                       uint16_t* out_moves, int16_t* out_actions, float* out_priors, int32_t* out_n, cudaStream_t stream) {
+    if (n <= 0) return 0;
+    leaf_priors_kernel<<<(n + 3) / 4, 128, 0, stream>>>(pos, cur_idx, n, pfeat, wpt, exp_table, out_moves, out_actions, out_priors, out_n);
+    CB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// dense [n][MAX_MOVES] rows -> one packed buffer (one device-to-host copy): a single block scans the counts, then every position's
+// row is copied to its offset.  Sections: value f32[n] | n_moves i32[n] | offsets i32[n + 1] | priors f32[T] | moves u16[T] | actions i16[T]
+__global__ void __launch_bounds__(1024) pack_leaf_eval_kernel(int n, const float* __restrict__ value, const int32_t* __restrict__ cnt,
+                                                              const uint16_t* __restrict__ moves, const int16_t* __restrict__ actions,
+                                                              const float* __restrict__ priors, uint8_t* __restrict__ out, int cap) {
+    __shared__ int32_t s_scan[1024];
+    __shared__ int32_t s_base;
+    float* o_value = reinterpret_cast<float*>(out);
+    int32_t* o_cnt = reinterpret_cast<int32_t*>(o_value + n);
+    int32_t* o_off = o_cnt + n;
+    float* o_pri = reinterpret_cast<float*>(o_off + n + 1);
+    uint16_t* o_mv = reinterpret_cast<uint16_t*>(o_pri + cap);
+    int16_t* o_act = reinterpret_cast<int16_t*>(o_mv + cap);
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int c = i < n ? cnt[i] : 0;
+        s_scan[threadIdx.x] = c;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            const int v = threadIdx.x >= o ? s_scan[threadIdx.x - o] : 0;
+            __syncthreads();
+            s_scan[threadIdx.x] += v;
+            __syncthreads();
+        }
+        const int off = s_base + s_scan[threadIdx.x] - c;
+        if (i < n) {
+            o_value[i] = value[i]; o_cnt[i] = c; o_off[i] = off;
+            for (int k = 0; k < c; ++k) {
+                o_pri[off + k] = priors[(size_t)i * MAX_MOVES + k];
+                o_mv[off + k] = moves[(size_t)i * MAX_MOVES + k];
+                o_act[off + k] = actions[(size_t)i * MAX_MOVES + k];
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) s_base += s_scan[1023];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) o_off[n] = s_base;
+}
+int launch_pack_leaf_eval(int n, const float* value, const int32_t* cnt, const uint16_t* moves, const int16_t* actions, const float* priors,
+                          uint8_t* out, int cap, cudaStream_t stream) {
+    pack_leaf_eval_kernel<<<1, 1024, 0, stream>>>(n, value, cnt, moves, actions, priors, out, cap);
+    CB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int launch_policy_softmax(const Pos* pos, const int32_t* cur_idx, int n, const __nv_bfloat16* logits, const float* exp_table,
                           uint16_t* out_moves, int16_t* out_actions, float* out_priors, int32_t* out_n, cudaStream_t stream) {
     if (n <= 0) return 0;

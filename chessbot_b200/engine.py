@@ -122,20 +122,17 @@ class Engine:
     # ------------------------------------------------------------------ gameimage
     def upload_records(self, records):
         """records: list of uint8 [k_i, 96] game records (Board.export_record) -> (pos tensor, frame_idx [n,8])."""
-        lens = [len(r) for r in records]
-        flat = np.concatenate(records, axis=0)
-        # predecessor links (Pos.pad_[0], byte offset 84) and frame lists, newest first
-        ply = flat[:, 74].astype(np.int32) | (flat[:, 75].astype(np.int32) << 8)
-        frame_idx = np.full((len(records), 8), -1, dtype=np.int32)
-        off = 0
-        for i, k in enumerate(lens):
-            cur = off + k - 1
-            for t in range(8):
-                frame_idx[i, t] = cur
-                if ply[cur] == 0 or cur == off:
-                    break
-                cur -= 1
-            off += k
+        if isinstance(records, tuple):
+            flat, lens = np.ascontiguousarray(records[0]), np.asarray(records[1], dtype=np.int64)
+        else:
+            lens = np.array([len(r) for r in records], dtype=np.int64)
+            flat = np.concatenate(records, axis=0)
+        # frame lists, newest first: back to the start of the record or of the game (ply 0), at most 8 (gameimage.py:170-181)
+        ply = flat[:, 74].astype(np.int64) | (flat[:, 75].astype(np.int64) << 8)
+        last = np.cumsum(lens) - 1
+        n_frames = np.minimum(np.minimum(lens, 8), ply[last] + 1)
+        t = np.arange(8)
+        frame_idx = np.where(t[None, :] < n_frames[:, None], last[:, None] - t[None, :], -1).astype(np.int32)
         pos = torch.from_numpy(flat).to(self.device)
         return pos, torch.from_numpy(frame_idx).to(self.device)
 
@@ -181,18 +178,53 @@ class Engine:
                                     _ptr(priors), _ptr(counts), _stream()), "policy_softmax")
         return moves, actions, priors, counts
 
-    def evaluate_positions(self, records, pos=None, frame_idx=None):
-        """BASELINE config 2 — batched leaf evaluation outside a tree: encode (K1) -> tower + heads (K2-K4, dense
-        bf16 logits) -> legal-move gather / exp / normalise (K5).  records: game records of the positions (host),
-        or pos / frame_idx already on the device.  Returns device tensors (value [n], moves [n,224] uint16 codes as
-        int16, actions [n,224], priors [n,224] f32, n_moves [n])."""
+    def evaluate_positions(self, records, pos=None, frame_idx=None, dense_logits=False):
+        """BASELINE config 2 — batched leaf evaluation outside a tree: encode (K1) -> tower + heads (K2/K3) -> legal-move gather / exp /
+        normalise (K5).  records: game records of the positions (host), or pos / frame_idx already on the device.  The policy Dense is
+        evaluated for the legal moves only (cb_leaf_eval); dense_logits=True takes the round-1 route through the dense [n, 4672] bf16
+        logits (K4 + cb_policy_softmax; same bits).  Returns device tensors (value [n], moves [n,224] uint16 codes as int16, actions
+        [n,224], priors [n,224] f32, n_moves [n])."""
         if pos is None:
             pos, frame_idx = self.upload_records(records)
         n = frame_idx.shape[0]
-        act, _ = self.encode(pos, frame_idx)
-        value, lb, _ = self.forward(act, n, want_bf16=True, want_f32=False)
-        moves, actions, priors, counts = self.policy_softmax(pos, frame_idx[:, 0].contiguous(), lb)
+        if dense_logits:
+            act, _ = self.encode(pos, frame_idx)
+            value, lb, _ = self.forward(act, n, want_bf16=True, want_f32=False)
+            moves, actions, priors, counts = self.policy_softmax(pos, frame_idx[:, 0].contiguous(), lb)
+            return value, moves, actions, priors, counts
+        key = ("leaf_scratch", n)
+        if getattr(self, "_leaf_scratch_key", None) != key:
+            self._leaf_scratch = torch.zeros(lib.cb_planes_act_bytes(n) // 2, dtype=torch.bfloat16, device=self.device)
+            self._leaf_scratch_key = key
+        value = torch.empty(n, dtype=torch.float32, device=self.device)
+        moves = torch.zeros(n, CB_MAX_MOVES, dtype=torch.int16, device=self.device)
+        actions = torch.zeros(n, CB_MAX_MOVES, dtype=torch.int16, device=self.device)
+        priors = torch.zeros(n, CB_MAX_MOVES, dtype=torch.float32, device=self.device)
+        counts = torch.zeros(n, dtype=torch.int32, device=self.device)
+        cur = frame_idx[:, 0].contiguous()
+        check(lib.cb_leaf_eval(self._h, _ptr(pos), _ptr(frame_idx), _ptr(cur), n, _ptr(self._leaf_scratch), _ptr(value), _ptr(moves), _ptr(actions),
+                               _ptr(priors), _ptr(counts), _stream()), "leaf_eval")
         return value, moves, actions, priors, counts
+
+    def evaluate_records(self, records):
+        """The same end to end for HOST game records (list of uint8 [k_i, 96], or (flat, lens) as board.export_records(flat=True)
+        returns): one C call - pinned staging, H2D, kernels, packed device-to-host read.  Returns host arrays
+        {"value" [n], "n_moves" [n], "off" [n+1], "priors" [T], "moves" [T] uint16, "actions" [T] int16}: position i owns [off[i], off[i+1])."""
+        if isinstance(records, tuple):
+            flat, lens = np.ascontiguousarray(records[0]), np.ascontiguousarray(records[1], dtype=np.int32)
+        else:
+            lens = np.array([len(r) for r in records], dtype=np.int32)
+            flat = np.ascontiguousarray(np.concatenate(records, axis=0))
+        n = len(lens)
+        buf = np.empty(lib.cb_leaf_eval_packed_bytes(n, n * CB_MAX_MOVES), dtype=np.uint8)
+        T = check(lib.cb_leaf_eval_host_sync(self._h, flat.ctypes.data, lens.ctypes.data, n, buf.ctypes.data, buf.nbytes, _stream()), "leaf_eval_host")
+        o, out = 0, {}
+        for key, dt, cnt in (("value", np.float32, n), ("n_moves", np.int32, n), ("off", np.int32, n + 1), ("priors", np.float32, T),
+                             ("moves", np.uint16, T), ("actions", np.int16, T)):
+            nb = cnt * np.dtype(dt).itemsize
+            out[key] = buf[o:o + nb].view(dt)
+            o += nb
+        return out
 
     PROF_STAGES = ("encode", "conv", "heads", "mcts_step", "policy_dense", "policy_softmax")
 

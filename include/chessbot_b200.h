@@ -116,6 +116,18 @@ int cb_policy_softmax(cb_ctx* ctx, const void* pos_dev, const int32_t* cur_idx_d
                       uint16_t* out_moves_dev, int16_t* out_actions_dev, float* out_priors_dev, int32_t* out_n_dev,
                       void* stream);
 
+/* ---- batched leaf evaluation outside a tree (BASELINE config 2; mcts.expand, mcts.py:80-103, for n positions at once) ---------- */
+/* encode + tower + heads + legal-move gather / exp / normalise WITHOUT the dense [n][4672] logits: the policy Dense is evaluated for the
+ * legal moves only (same arithmetic, same bits as cb_net_forward + cb_policy_softmax).  cur_idx_dev[n]: index of each position in
+ * pos_dev (= frame_idx_dev[i][0]); planes_act_dev: zeroed scratch of cb_planes_act_bytes(n); outputs [n][CB_MAX_MOVES] rows. */
+int cb_leaf_eval(cb_ctx* ctx, const void* pos_dev, const int32_t* frame_idx_dev, const int32_t* cur_idx_dev, int n, void* planes_act_dev,
+                 float* value_dev, uint16_t* moves_dev, int16_t* actions_dev, float* priors_dev, int32_t* n_moves_dev, void* stream);
+/* the same end to end from HOST game records (concatenated cb_board_export_record blocks, rec_len[n] positions each): pinned staging,
+ * one H2D, the kernels, a packed result, two small D2H.  out_host: value f32[n] | n_moves i32[n] | offsets i32[n+1] | priors f32[T] |
+ * moves u16[T] | actions i16[T]; returns T (<0: error).  out_cap_bytes >= cb_leaf_eval_packed_bytes(n, T); n * CB_MAX_MOVES always fits. */
+size_t cb_leaf_eval_packed_bytes(int n, int total_moves);
+int cb_leaf_eval_host_sync(cb_ctx* ctx, const void* records_host, const int32_t* rec_len, int n, void* out_host, size_t out_cap_bytes, void* stream);
+
 /* ---- mcts.run_mcts over many concurrent trees (mcts.py:38-161) ---------------------------------- */
 #define CB_EVAL_NET 0        /* the network loaded with cb_net_* */
 #define CB_EVAL_SYNTH 1      /* synthetic hash network */

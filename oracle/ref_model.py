@@ -94,6 +94,49 @@ def forward(w, images, device="cpu", return_tower=False):
         return v.cpu().numpy(), logits.cpu().numpy()
 
 
+def forward_bf16_rounding(w, images, device="cpu", stream_hi_lo=True):
+    """The same graph with the roundings of the device datapath applied where the device applies them, everything else in fp32: what an
+    ideal bf16-operand tensor-core tower computes.  Convolution operands (activations as stored in HBM, packed weights) are bf16, products
+    accumulate in fp32, BN / skip / LeakyReLU run in fp32 on the accumulator; the residual stream is kept as bf16 hi + lo (~fp32) between
+    blocks (stream_hi_lo=False: rounded to bf16, the round-1 datapath); the stem sees exact integers with bf16 hi + lo weights (~fp32); the
+    fused 1x1 head convolutions read the fp32 epilogue value.  The distance device <-> this oracle isolates kernel defects (it should be
+    accumulation-order noise); the distance of this oracle <-> `forward` is what bf16 operands cost, whatever the kernel."""
+    def rb(t):
+        return t.to(torch.bfloat16).to(torch.float32)
+
+    def fold(bn):
+        g, b, m, v = (torch.from_numpy(np.ascontiguousarray(bn[i])).to(device).double() for i in range(4))
+        s = g / torch.sqrt(v + BN_EPS)
+        return s.float().view(1, -1, 1, 1), (b - m * s).float().view(1, -1, 1, 1)
+
+    def kern(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).to(device).permute(3, 2, 0, 1).contiguous()
+
+    with torch.no_grad():
+        x = torch.as_tensor(np.asarray(images, dtype=np.float32)).to(device).permute(0, 3, 1, 2).contiguous()
+        s, b = fold(w["stem.bn"])
+        stream = F.leaky_relu(F.conv2d(x, kern(w["stem.w"]), padding=1) * s + b, SLOPE)
+        for i in range(num_blocks(w)):
+            s1, b1 = fold(w[f"res{i}.bn1"])
+            y = rb(F.leaky_relu(F.conv2d(rb(stream), rb(kern(w[f"res{i}.w1"])), padding=1) * s1 + b1, SLOPE))
+            s2, b2 = fold(w[f"res{i}.bn2"])
+            y = F.conv2d(y, rb(kern(w[f"res{i}.w2"])), padding=1) * s2 + b2
+            skip = stream if stream_hi_lo else rb(stream)
+            if stream_hi_lo:
+                hi = rb(stream)
+                skip = hi + rb(stream - hi)
+            stream = F.leaky_relu(skip + y, SLOPE)
+        x = stream
+        B = x.shape[0]
+        sv, bv = fold(w["value.bn"])
+        v = F.leaky_relu(F.conv2d(x, kern(w["value.conv"])) * sv + bv, SLOPE).permute(0, 2, 3, 1).reshape(B, 64)
+        v = F.leaky_relu(v @ torch.from_numpy(w["value.fc1"]).to(device), SLOPE)
+        v = torch.tanh(v @ torch.from_numpy(w["value.fc2"]).to(device)).reshape(B)
+        sp, bp = fold(w["policy.bn"])
+        p = F.leaky_relu(F.conv2d(x, kern(w["policy.conv"])) * sp + bp, SLOPE).permute(0, 2, 3, 1).reshape(B, 128)
+        return v.cpu().numpy(), (p @ torch.from_numpy(w["policy.fc"]).to(device)).cpu().numpy()
+
+
 def calibrate_bn(w, images, device="cpu"):
     """Returns a copy of `w` whose BatchNorm moving statistics are the batch statistics of `images`,
     layer by layer (what training converges to): activations and logits become O(1), the regime the

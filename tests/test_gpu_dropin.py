@@ -345,10 +345,10 @@ def test_library_memory_is_owned_by_pytorch():
     eng.load_network(keras_init_weights(64, 2, seed=1), 64, 2, max_batch=512)
     grown = E.library_device_bytes() - before_lib
     assert E.library_device_bytes() > 0
-    assert torch.cuda.memory_allocated() - before_torch >= grown > -1
+    assert torch.cuda.memory_allocated() - before_torch >= 0.95 * grown and grown >= 0
     need = E.lib.cb_search_workspace_bytes(256, 256 * 40 * 48, 256 * 300, 38, 1)
+    fresh = E.Engine.actor(7)                       # a context that never held a pool
     lib0 = E.library_device_bytes()
-    eng.search_shape = None
-    eng.search_create(256, max_nodes=256 * 40 * 48, max_positions=256 * 300, max_sims=38)
+    fresh.search_create(256, max_nodes=256 * 40 * 48, max_positions=256 * 300, max_sims=38)
     took = E.library_device_bytes() - lib0
     assert 0.5 * need <= took <= 1.05 * need + (1 << 20), (need, took)
