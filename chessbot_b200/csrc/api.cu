@@ -200,7 +200,7 @@ struct cb_ctx {
     struct LeafEval {
         int cap = 0;
         DevBuf<uint8_t> pos, pack;
-        DevBuf<int32_t> frame_idx, cur_idx, cnt;
+        DevBuf<int32_t> cnt;
         DevBuf<__nv_bfloat16> planes;
         DevBuf<float> value, priors;
         DevBuf<uint16_t> moves;
@@ -567,16 +567,16 @@ int cb_leaf_eval_host_sync(cb_ctx* ctx, const void* records_host, const int32_t*
     const int cap_moves = n * MAX_MOVES;
     if (n > L.cap) {
         const size_t nn = n;
-        if (L.frame_idx.alloc(nn * 8, false) || L.cur_idx.alloc(nn, false) || L.cnt.alloc(nn, false) || L.planes.alloc(act_bytes(n, 128) / 2) ||
+        if (L.cnt.alloc(nn, false) || L.planes.alloc(act_bytes(n, 128) / 2) ||
             L.value.alloc(nn, false) || L.priors.alloc(nn * MAX_MOVES, false) || L.moves.alloc(nn * MAX_MOVES, false) ||
             L.actions.alloc(nn * MAX_MOVES, false) || L.pack.alloc(cb_leaf_eval_packed_bytes(n, cap_moves), false))
             return -1;
         L.cap = n;
     }
-    if (L.pos.n < total * sizeof(Pos) && L.pos.alloc(total * sizeof(Pos) * 5 / 4 + 4096, false)) return -1;
-    // staging: positions | frame_idx [n][8] | cur_idx [n]
-    const size_t b_pos = total * sizeof(Pos), o_fi = (b_pos + 15) & ~(size_t)15, o_ci = o_fi + (size_t)n * 32;
-    if (L.h_in.reserve(o_ci + (size_t)n * 4)) return -1;
+    // staging: positions | frame_idx [n][8] | cur_idx [n], mirrored by ONE device block (one H2D)
+    const size_t b_pos = total * sizeof(Pos), o_fi = (b_pos + 15) & ~(size_t)15, o_ci = o_fi + (size_t)n * 32, b_in = o_ci + (size_t)n * 4;
+    if (L.pos.n < b_in && L.pos.alloc(b_in * 5 / 4 + 4096, false)) return -1;
+    if (L.h_in.reserve(b_in)) return -1;
     memcpy(L.h_in.p, records_host, b_pos);
     const Pos* rec = reinterpret_cast<const Pos*>(L.h_in.p);
     int32_t* fi = reinterpret_cast<int32_t*>(L.h_in.p + o_fi);
@@ -593,27 +593,26 @@ int cb_leaf_eval_host_sync(cb_ctx* ctx, const void* records_host, const int32_t*
         }
         off += rec_len[i];
     }
-    CB_CUDA_OK(cudaMemcpyAsync(L.pos.p, L.h_in.p, b_pos, cudaMemcpyHostToDevice, st));
-    CB_CUDA_OK(cudaMemcpyAsync(L.frame_idx.p, fi, (size_t)n * 32, cudaMemcpyHostToDevice, st));
-    CB_CUDA_OK(cudaMemcpyAsync(L.cur_idx.p, ci, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-    if (cb_leaf_eval(ctx, L.pos.p, L.frame_idx.p, L.cur_idx.p, n, L.planes.p, L.value.p, L.moves.p, L.actions.p, L.priors.p, L.cnt.p, stream)) return -1;
-    if (launch_pack_leaf_eval(n, L.value.p, L.cnt.p, L.moves.p, L.actions.p, L.priors.p, L.pack.p, cap_moves, st)) return -1;
+    CB_CUDA_OK(cudaMemcpyAsync(L.pos.p, L.h_in.p, b_in, cudaMemcpyHostToDevice, st));
+    const int32_t* d_fi = reinterpret_cast<const int32_t*>(L.pos.p + o_fi);
+    const int32_t* d_ci = reinterpret_cast<const int32_t*>(L.pos.p + o_ci);
+    if (cb_leaf_eval(ctx, L.pos.p, d_fi, d_ci, n, L.planes.p, L.value.p, L.moves.p, L.actions.p, L.priors.p, L.cnt.p, stream)) return -1;
+    if (launch_pack_leaf_eval(n, L.value.p, L.cnt.p, L.moves.p, L.actions.p, L.priors.p, L.pack.p, st)) return -1;
+    // one speculative read (header + 64 moves per position: the average is ~30), a second one only if a batch needs more
     const size_t b_hdr = (size_t)n * 12 + 4;
-    if (L.h_out.reserve(cb_leaf_eval_packed_bytes(n, cap_moves))) return -1;
-    CB_CUDA_OK(cudaMemcpyAsync(L.h_out.p, L.pack.p, b_hdr, cudaMemcpyDeviceToHost, st));
+    const size_t b_all = cb_leaf_eval_packed_bytes(n, cap_moves), b_first = b_hdr + (size_t)n * 64 * 8 < b_all ? b_hdr + (size_t)n * 64 * 8 : b_all;
+    if (L.h_out.reserve(b_all)) return -1;
+    CB_CUDA_OK(cudaMemcpyAsync(L.h_out.p, L.pack.p, b_first, cudaMemcpyDeviceToHost, st));
     CB_CUDA_OK(cudaStreamSynchronize(st));
     const int T = reinterpret_cast<const int32_t*>(L.h_out.p)[3 * n];
     if (T < 0 || T > cap_moves) { cb_set_error("cb_leaf_eval_host_sync: corrupt offsets"); return -1; }
-    if (cb_leaf_eval_packed_bytes(n, T) > out_cap_bytes) { cb_set_error("cb_leaf_eval_host_sync: output buffer too small"); return -1; }
-    const uint8_t* d_pri = L.pack.p + b_hdr;
-    const uint8_t* d_mv = d_pri + (size_t)cap_moves * 4;
-    const uint8_t* d_act = d_mv + (size_t)cap_moves * 2;
-    uint8_t* h = L.h_out.p + b_hdr;
-    CB_CUDA_OK(cudaMemcpyAsync(h, d_pri, (size_t)T * 4, cudaMemcpyDeviceToHost, st));
-    CB_CUDA_OK(cudaMemcpyAsync(h + (size_t)T * 4, d_mv, (size_t)T * 2, cudaMemcpyDeviceToHost, st));
-    CB_CUDA_OK(cudaMemcpyAsync(h + (size_t)T * 6, d_act, (size_t)T * 2, cudaMemcpyDeviceToHost, st));
-    CB_CUDA_OK(cudaStreamSynchronize(st));
-    memcpy(out_host, L.h_out.p, cb_leaf_eval_packed_bytes(n, T));
+    const size_t b_need = cb_leaf_eval_packed_bytes(n, T);
+    if (b_need > out_cap_bytes) { cb_set_error("cb_leaf_eval_host_sync: output buffer too small"); return -1; }
+    if (b_need > b_first) {
+        CB_CUDA_OK(cudaMemcpyAsync(L.h_out.p + b_first, L.pack.p + b_first, b_need - b_first, cudaMemcpyDeviceToHost, st));
+        CB_CUDA_OK(cudaStreamSynchronize(st));
+    }
+    memcpy(out_host, L.h_out.p, b_need);
     return T;
 }
 

@@ -210,7 +210,7 @@ int launch_mcts_step(const SearchParams& sp, cudaStream_t stream);
 int launch_leaf_priors(const Pos* pos, const int32_t* cur_idx, int n, const float* pfeat, const float* wpt, const float* exp_table,
                        uint16_t* out_moves, int16_t* out_actions, float* out_priors, int32_t* out_n, cudaStream_t stream);
 int launch_pack_leaf_eval(int n, const float* value, const int32_t* cnt, const uint16_t* moves, const int16_t* actions, const float* priors,
-                          uint8_t* out, int cap, cudaStream_t stream);
+                          uint8_t* out, cudaStream_t stream);
 int launch_policy_softmax(const Pos* pos, const int32_t* cur_idx, int n, const __nv_bfloat16* logits, const float* exp_table,
                           uint16_t* out_moves, int16_t* out_actions, float* out_priors, int32_t* out_n, cudaStream_t stream);
 

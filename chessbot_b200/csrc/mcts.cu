@@ -494,19 +494,17 @@ int launch_leaf_priors(const Pos* pos, const int32_t* cur_idx, int n, const floa
     return 0;
 }
 
-// dense [n][MAX_MOVES] rows -> one packed buffer (one device-to-host copy): a single block scans the counts, then every position's
-// row is copied to its offset.  Sections: value f32[n] | n_moves i32[n] | offsets i32[n + 1] | priors f32[T] | moves u16[T] | actions i16[T]
+// dense [n][MAX_MOVES] rows -> one packed buffer (read back with one device-to-host copy): a single block scans the counts, then every
+// position's row is copied to its offset.  Sections, contiguous: value f32[n] | n_moves i32[n] | offsets i32[n + 1] | priors f32[T] |
+// moves u16[T] | actions i16[T], T = offsets[n].
 __global__ void __launch_bounds__(1024) pack_leaf_eval_kernel(int n, const float* __restrict__ value, const int32_t* __restrict__ cnt,
                                                               const uint16_t* __restrict__ moves, const int16_t* __restrict__ actions,
-                                                              const float* __restrict__ priors, uint8_t* __restrict__ out, int cap) {
+                                                              const float* __restrict__ priors, uint8_t* __restrict__ out) {
     __shared__ int32_t s_scan[1024];
     __shared__ int32_t s_base;
     float* o_value = reinterpret_cast<float*>(out);
     int32_t* o_cnt = reinterpret_cast<int32_t*>(o_value + n);
     int32_t* o_off = o_cnt + n;
-    float* o_pri = reinterpret_cast<float*>(o_off + n + 1);
-    uint16_t* o_mv = reinterpret_cast<uint16_t*>(o_pri + cap);
-    int16_t* o_act = reinterpret_cast<int16_t*>(o_mv + cap);
     if (threadIdx.x == 0) s_base = 0;
     __syncthreads();
     for (int base = 0; base < n; base += 1024) {
@@ -520,24 +518,31 @@ __global__ void __launch_bounds__(1024) pack_leaf_eval_kernel(int n, const float
             s_scan[threadIdx.x] += v;
             __syncthreads();
         }
-        const int off = s_base + s_scan[threadIdx.x] - c;
-        if (i < n) {
-            o_value[i] = value[i]; o_cnt[i] = c; o_off[i] = off;
-            for (int k = 0; k < c; ++k) {
-                o_pri[off + k] = priors[(size_t)i * MAX_MOVES + k];
-                o_mv[off + k] = moves[(size_t)i * MAX_MOVES + k];
-                o_act[off + k] = actions[(size_t)i * MAX_MOVES + k];
-            }
-        }
+        if (i < n) { o_value[i] = value[i]; o_cnt[i] = c; o_off[i] = s_base + s_scan[threadIdx.x] - c; }
         __syncthreads();
         if (threadIdx.x == 1023) s_base += s_scan[1023];
         __syncthreads();
     }
-    if (threadIdx.x == 0) o_off[n] = s_base;
+    const int T = s_base;
+    if (threadIdx.x == 0) o_off[n] = T;
+    __syncthreads();
+    float* o_pri = reinterpret_cast<float*>(o_off + n + 1);
+    uint16_t* o_mv = reinterpret_cast<uint16_t*>(o_pri + T);
+    int16_t* o_act = reinterpret_cast<int16_t*>(o_mv + T);
+    // a warp per position: coalesced row copies
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = warp; i < n; i += 32) {
+        const int c = o_cnt[i], off = o_off[i];
+        for (int k = lane; k < c; k += 32) {
+            o_pri[off + k] = priors[(size_t)i * MAX_MOVES + k];
+            o_mv[off + k] = moves[(size_t)i * MAX_MOVES + k];
+            o_act[off + k] = actions[(size_t)i * MAX_MOVES + k];
+        }
+    }
 }
 int launch_pack_leaf_eval(int n, const float* value, const int32_t* cnt, const uint16_t* moves, const int16_t* actions, const float* priors,
-                          uint8_t* out, int cap, cudaStream_t stream) {
-    pack_leaf_eval_kernel<<<1, 1024, 0, stream>>>(n, value, cnt, moves, actions, priors, out, cap);
+                          uint8_t* out, cudaStream_t stream) {
+    pack_leaf_eval_kernel<<<1, 1024, 0, stream>>>(n, value, cnt, moves, actions, priors, out);
     CB_CUDA_OK(cudaGetLastError());
     return 0;
 }

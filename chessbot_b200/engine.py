@@ -208,7 +208,8 @@ class Engine:
 
     def evaluate_records(self, records):
         """The same end to end for HOST game records (list of uint8 [k_i, 96], or (flat, lens) as board.export_records(flat=True)
-        returns): one C call - pinned staging, H2D, kernels, packed device-to-host read.  Returns host arrays
+        returns): one C call - pinned staging, H2D, kernels, packed device-to-host read.  Returns host arrays (views of a buffer the
+        engine reuses: copy what must outlive the next call)
         {"value" [n], "n_moves" [n], "off" [n+1], "priors" [T], "moves" [T] uint16, "actions" [T] int16}: position i owns [off[i], off[i+1])."""
         if isinstance(records, tuple):
             flat, lens = np.ascontiguousarray(records[0]), np.ascontiguousarray(records[1], dtype=np.int32)
@@ -216,7 +217,9 @@ class Engine:
             lens = np.array([len(r) for r in records], dtype=np.int32)
             flat = np.ascontiguousarray(np.concatenate(records, axis=0))
         n = len(lens)
-        buf = np.empty(lib.cb_leaf_eval_packed_bytes(n, n * CB_MAX_MOVES), dtype=np.uint8)
+        buf = getattr(self, "_leaf_out", None)                  # reused between calls (the views returned are valid until the next call)
+        if buf is None or buf.nbytes < lib.cb_leaf_eval_packed_bytes(n, n * CB_MAX_MOVES):
+            buf = self._leaf_out = np.zeros(lib.cb_leaf_eval_packed_bytes(n, n * CB_MAX_MOVES), dtype=np.uint8)
         T = check(lib.cb_leaf_eval_host_sync(self._h, flat.ctypes.data, lens.ctypes.data, n, buf.ctypes.data, buf.nbytes, _stream()), "leaf_eval_host")
         o, out = 0, {}
         for key, dt, cnt in (("value", np.float32, n), ("n_moves", np.int32, n), ("off", np.int32, n + 1), ("priors", np.float32, T),
