@@ -790,6 +790,7 @@ static int search_begin_impl(cb_ctx* ctx, int n_trees, const void* records_host,
     for (int i = 0; i < n_trees; ++i) {
         for (int k = 0; k < rec_len[i]; ++k) rec[off + k].pad_[0] = k ? (uint32_t)(off + k - 1) : 0xFFFFFFFFu;  // predecessor link
         ts[i].root_pos = (int32_t)(off + rec_len[i] - 1);
+        ts[i].rec_start = (int32_t)off;
         ts[i].sims_target = sims[i];
         ts[i].status = 1;
         ts[i].noisy = noise_off && noise_off[i + 1] > noise_off[i];

@@ -54,7 +54,7 @@ struct ConvSmem {
     uint32_t tmem_base;
 };
 static_assert(sizeof(ConvSmem) <= 1024, "barrier block");
-constexpr int CONV_SMEM_PARAM_FLOATS = 256 * 3 + 2 * 128 * 3 + EPI_WARPS * 256;  // head weights, head partials, per-warp BN scale / shift
+constexpr int CONV_SMEM_PARAM_FLOATS = 256 * 3 + 2 * 128 * 3 + EPI_WARPS * 512;  // head weights, head partials, per-warp BN scale / shift of two layers
 constexpr size_t CONV_SMEM_BYTES = 1024 + A_SLOTS * A_SLOT_BYTES + B_RING_BYTES + CONV_SMEM_PARAM_FLOATS * 4;
 
 // This cluster's share of the flattened (unit, layer) items i = unit * nl + layer: the range [lo, hi).
@@ -71,6 +71,17 @@ struct WorkRange {
     // the unit the PREVIOUS cluster began goes last (its flag has had a whole round to arrive)
     __device__ int unit(int k) const { return nu == 1 ? u_first : (k == 0 ? u_first + nu - 1 : (k == nu - 1 ? u_first : u_first + k)); }
     __device__ bool mine(int u, int l) const { const int i = u * nl + l; return i >= lo && i < hi; }
+    // The order every role walks this cluster's items in: rounds r = 0 .. nl, unit slots k = 0 .. nu - 1 within a round, and the odd
+    // slots run ONE LAYER BEHIND the even ones (layer = r - (k & 1)).  Consecutive items then alternate between a layer with a
+    // residual add (long epilogue: skip tile read, hi + lo written) and one without (short epilogue), so the two TMEM accumulator
+    // stages average the epilogue time out; layer-major order made 3-4 long epilogues in a row, each longer than its MMAs.
+    // (u, l) still follows (u, l - 1) by a whole round.
+    __device__ bool item(int r, int k, int& u, int& l) const {
+        l = r - (k & 1);
+        if (l < 0 || l >= nl) return false;
+        u = unit(k);
+        return mine(u, l);
+    }
 };
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
@@ -189,20 +200,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
         const uint32_t a_full0 = ptx::mapa(ptx::smem_u32(&s->a_full[0]), 0);
         // flat walk over this cluster's items with one item of look-ahead: the progress flag of the NEXT item is read
         // (ld.acquire.gpu, an L2 round trip) while this item's loads are being issued
-        int l = 0, k = -1;
-        auto advance = [&](int& ll, int& kk) {  // next (layer, unit slot) of this cluster, ll == nl at the end
+        int r = 0, k = -1, u = 0, l = 0;
+        auto advance = [&](int& rr, int& kk, int& uu, int& ll) {  // next item of this cluster, rr > nl at the end
             do {
-                if (++kk == w.nu) { kk = 0; ++ll; }
-            } while (ll < nl && !w.mine(w.unit(kk), ll));
+                if (++kk == w.nu) { kk = 0; ++rr; }
+            } while (rr <= nl && !w.item(rr, kk, uu, ll));
         };
-        advance(l, k);
-        int seen = l < nl && l > 0 ? ld_acquire_gpu(p.flags + 2 * w.unit(k) + rank) : 0;
+        advance(r, k, u, l);
+        int seen = r <= nl && l > 0 ? ld_acquire_gpu(p.flags + 2 * u + rank) : 0;
         int l_loaded = -1;
         LayerDesc L{};
-        while (l < nl) {
+        while (r <= nl) {
             if (l != l_loaded) { L = p.layers[l]; l_loaded = l; }
             const CUtensorMap* tm_in = &p.tm_act[L.in_buf];
-            const int u = w.unit(k);
             const int pair = min(2 * u + (int)rank, pairs - 1);  // odd tail: the peer re-reads the last pair, its result is dropped
             if (l > 0) {
                 // the input of this item is the output of (unit, layer - 1): written by this CTA's epilogue warps, or by
@@ -211,9 +221,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
                 while (seen < flag_base + l) seen = ld_acquire_gpu(flag);
                 fence_proxy_async();
             }
-            int nl_ = l, nk_ = k;
-            advance(nl_, nk_);
-            if (nl_ < nl && nl_ > 0) seen = ld_acquire_gpu(p.flags + 2 * w.unit(nk_) + rank);  // consumed at the top of the next item
+            int nr = r, nk_ = k, nu_ = u, nl_ = l;
+            advance(nr, nk_, nu_, nl_);
+            if (nr <= nl && nl_ > 0) seen = ld_acquire_gpu(p.flags + 2 * nu_ + rank);  // consumed at the top of the next item
             for (int kc = 0; kc < L.kc; ++kc) {
                 ptx::mbar_wait_parked(&s->a_empty[as], aph);
                 if (ptx::elect_one()) {
@@ -223,20 +233,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
                 }
                 if (++as == A_SLOTS) { as = 0; aph ^= 1; }
             }
-            l = nl_;
-            k = nk_;
+            r = nr; k = nk_; u = nu_; l = nl_;
         }
     } else if (warp == 2) {
         // ------------------------------------------------------------------ weight producer (both CTAs): the weight stream does not depend on
         // any activation, so it runs ahead of the progress flags the activation producer has to wait for
         uint32_t bs = 0, bph = 1;  // ring slot and the parity of its "empty" barrier (a fresh barrier passes a wait on parity 1)
         const uint32_t b_full0 = ptx::mapa(ptx::smem_u32(&s->b_full[0]), 0);
-        for (int l = 0; l < nl; ++l) {
-            const int kcs = p.layers[l].kc;
-            const CUtensorMap* tm_w = &p.maps[p.layers[l].w_map];
-            if (ptx::elect_one()) ptx::tma_prefetch_desc(tm_w);
+        for (int r = 0; r <= nl; ++r) {
             for (int k = 0; k < w.nu; ++k) {
-                if (!w.mine(w.unit(k), l)) continue;
+                int u, l;
+                if (!w.item(r, k, u, l)) continue;
+                const int kcs = p.layers[l].kc;
+                const CUtensorMap* tm_w = &p.maps[p.layers[l].w_map];
                 for (int kc = 0; kc < kcs; ++kc) {
                     const int wrow = (kc * 2 + (int)rank) * 9 * nh;  // [kc][half][tap][8][N/2][8]
                     for (int sg = 0; sg < stages; ++sg) {
@@ -265,10 +274,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
             const uint32_t b_ks = 2 * nh;  // descriptor address units of 16 B
             const uint32_t slot16 = slot_bytes / 16, tap16 = (uint32_t)nh * 8;
             uint32_t as = 0, aph = 0, bs = 0, bph = 0, j = 0;
-            for (int l = 0; l < nl; ++l) {
-                const int kcs = p.layers[l].kc;
+            for (int r = 0; r <= nl; ++r) {
                 for (int k = 0; k < w.nu; ++k) {
-                    if (!w.mine(w.unit(k), l)) continue;
+                    int u, l;
+                    if (!w.item(r, k, u, l)) continue;
+                    const int kcs = p.layers[l].kc;
                     const uint32_t st = j & 1;
                     ptx::mbar_wait(&s->acc_empty[st], ((j >> 1) & 1) ^ 1);
                     ptx::tc_fence_after();
@@ -293,10 +303,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
         // for the activation producer of (unit, l + 1), here or in the next cluster
         if (lane == 0) {
             uint32_t j = 0;
-            for (int l = 0; l < nl; ++l)
+            for (int r = 0; r <= nl; ++r)
                 for (int k = 0; k < w.nu; ++k) {
-                    const int u = w.unit(k);
-                    if (!w.mine(u, l)) continue;
+                    int u, l;
+                    if (!w.item(r, k, u, l)) continue;
                     ptx::mbar_wait_parked(&s->pub_full[j % PUB_SLOTS], (j / PUB_SLOTS) & 1);
                     ptx::mbar_arrive(&s->pub_empty[j % PUB_SLOTS]);
                     fence_proxy_async();  // the epilogue's generic stores (observed through the mbarrier) before the TMA reads that follow the flag
@@ -323,16 +333,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
         // folded BN scale / shift of THIS warp's channel batches, staged in a warp-private slice of shared memory once per layer: read
         // from global memory in the batch loop they cost an L1 / L2 round trip in front of every group of FFMAs (ncu: half of the
         // epilogue's stall samples), and the epilogue is what bounds the layers with a residual add
-        float* s_bn = s_hpart + 768 + (warp - 4) * 256;  // [0..127] scale, [128..255] shift of batches h, h + 2, ...
+        // two slices, one per layer parity: consecutive items alternate between two layers (WorkRange::item)
+        float* s_bn2 = s_hpart + 768 + (warp - 4) * 512;  // per slice: [0..127] scale, [128..255] shift of batches h, h + 2, ...
+        int bn_l0 = -1, bn_l1 = -1;  // layer whose scale / shift each slice holds
         uint32_t j = 0;
-        for (int l = 0; l < nl; ++l) {
+        for (int rd = 0; rd <= nl; ++rd)
+        for (int k = 0; k < w.nu; ++k) {
+            int u, l;
+            if (!w.item(rd, k, u, l)) continue;
             const LayerDesc L = p.layers[l];
-            __syncwarp();
-            for (int k = 0; k < nk; ++k) {
-                s_bn[k * 32 + lane] = __ldg(L.scale + (h + 2 * k) * 32 + lane);
-                s_bn[128 + k * 32 + lane] = __ldg(L.shift + (h + 2 * k) * 32 + lane);
+            float* s_bn = s_bn2 + (l & 1) * 256;
+            if (((l & 1) ? bn_l1 : bn_l0) != l) {
+                __syncwarp();
+                for (int kb = 0; kb < nk; ++kb) {
+                    s_bn[kb * 32 + lane] = __ldg(L.scale + (h + 2 * kb) * 32 + lane);
+                    s_bn[128 + kb * 32 + lane] = __ldg(L.shift + (h + 2 * kb) * 32 + lane);
+                }
+                __syncwarp();
+                if (l & 1) bn_l1 = l; else bn_l0 = l;
             }
-            __syncwarp();
             const uint8_t* skip_buf = (!STATS && L.skip_buf >= 0) ? p.bufs[L.skip_buf] : nullptr;
             uint8_t* out_buf = p.bufs[L.out_buf];
             const bool has_skip = !STATS && skip_buf != nullptr;
@@ -342,9 +361,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
             const bool skip_lo = has_skip && lo_buf != nullptr;
             const bool write_lo = lo_buf != nullptr && (has_skip || l == 0) && !(nl == 1);
             const bool heads = !STATS && p.head_w != nullptr && l == nl - 1;
-            for (int k = 0; k < w.nu; ++k) {
-                const int u = w.unit(k);
-                if (!w.mine(u, l)) continue;
+            {
                 const uint32_t st = j & 1;
                 const int pair = 2 * u + (int)rank;
                 const bool active = pair < pairs;
@@ -441,7 +458,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
                                     ol.w = *reinterpret_cast<uint32_t*>(&u3);
                                     uint8_t* dl = lo_buf + ooff;
                                     *reinterpret_cast<uint4*>(dl) = ol;
-                                    if (p.full_sectors && edge) *reinterpret_cast<uint4*>(dl + edge) = make_uint4(0u, 0u, 0u, 0u);
+                                    // no whole-sector border store here: on skip layers this very thread has just READ the cell's sector (its
+                                    // lo input), so the sector is complete in L2 when the store lands; only the stem writes lo blind
+                                    if (p.full_sectors && edge && l == 0) *reinterpret_cast<uint4*>(dl + edge) = make_uint4(0u, 0u, 0u, 0u);
                                 }
                                 // a board row (8 cells, 128 B) starts 16 B into a 32-B sector: the first / last column also store the zero
                                 // border cell next to theirs, so every row is five WHOLE sectors and L2 never has to fetch a partially

@@ -108,7 +108,7 @@ struct TreeState {  // 80 bytes
     int32_t sims_done, sims_target;
     int32_t n_pending;   // leaves of this tree waiting for their evaluation (slots tree * leaves + 0 .. n_pending - 1)
     int32_t noise_off;   // first of this root's Gamma samples in SearchParams::noise (root children follow in legal-move order)
-    int32_t pad1_;
+    int32_t rec_start;   // first position of this root's game record in the pool (the record is contiguous, one ply per slot)
     int32_t status;
     int32_t n_nodes, n_evals;
     int32_t noisy;       // add_exploration_noise applied at the root (P held in f64)

@@ -113,11 +113,14 @@ __device__ __forceinline__ void settle_path(Node* nodes, const int32_t* path, in
 }
 
 constexpr int MCTS_WARPS = 4;
+constexpr int MCTS_TERMINAL_SIMS_PER_STEP = 4;
 
 __global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_step_kernel(SearchParams sp) {
     __shared__ float s_p[MCTS_WARPS][MAX_MOVES];
     __shared__ uint16_t s_m[MCTS_WARPS][MAX_MOVES];
     __shared__ int32_t s_path[MCTS_WARPS][MCTS_MAX_PATH];
+    __shared__ u64 s_hh[MCTS_WARPS][MCTS_HIST];      // key hashes / position ids of the reversible history of the leaf being set up
+    __shared__ int32_t s_hp[MCTS_WARPS][MCTS_HIST];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tree = blockIdx.x * MCTS_WARPS + warp;
     if (tree >= sp.n_trees) return;
@@ -214,7 +217,7 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_step_kernel(SearchParams
     const int sims_target = ts.sims_target;
     const bool noisy = ts.noisy != 0;
     const double cpuct_fixed = ts.cpuct;
-    int n_new = 0;
+    int n_new = 0, n_term = 0;
     while (sims_done + n_new < sims_target && n_new < L) {
         int node = ts.root_node;
         int parent_pos = ts.root_pos;
@@ -294,16 +297,14 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_step_kernel(SearchParams
             term = nd.term;
             leaf_pos = nd.pos_id;
             if (leaf_pos < 0) {
-                const Pos* ppg = sp.pos + parent_pos;
-                const Pos pp = *ppg;  // private copy: the rules code reads its fields many times
+                const Pos pp = sp.pos[parent_pos];  // private copy: the rules code reads its fields many times
                 Pos np_ = push_move(pp, nd.move);
                 np_.pad_[0] = (uint32_t)parent_pos;
-                np_.occur = (uint8_t)count_occurrences(np_, ppg, PoolPrev{sp.pos});
                 leaf_pos = chunk_alloc(ts.pos_next, ts.pos_end, 1, POS_CHUNK, sp.pos_count, sp.max_pos);
                 if (leaf_pos < 0) {
                     err = 1;
                 } else {
-                    sp.pos[leaf_pos] = np_;
+                    sp.pos[leaf_pos] = np_;  // occur = 1 for now: the count follows from the whole warp
                     sp.nodes[node].pos_id = leaf_pos;
                     fresh = 1;
                     __threadfence_block();
@@ -313,21 +314,42 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_step_kernel(SearchParams
         __syncwarp();
         fresh = __shfl_sync(0xffffffffu, fresh, 0);
         if (fresh) {
-            // first visit of this node: legal moves by the whole warp, then the outcome
+            // first visit of this node: repetition history, legal moves, outcome - all by the whole warp
             leaf_pos = __shfl_sync(0xffffffffu, leaf_pos, 0);
-            const Pos cur = sp.pos[leaf_pos];  // private copy per lane
+            Pos cur = sp.pos[leaf_pos];  // private copy per lane
+            const int W = depth > 0 ? gather_history_warp(sp.pos, sp.nodes, path, depth, ts.root_pos, ts.rec_start, cur.irrev_in != 0,
+                                                          s_hh[warp], s_hp[warp], lane)
+                                    : -1;
+            __syncwarp();
+            int occ;
+            if (W >= 0) {
+                occ = count_occurrences_warp(cur, sp.pos, s_hh[warp], s_hp[warp], W, lane);
+            } else {  // path not recorded or a window beyond MCTS_HIST plies: the serial walk
+                occ = lane == 0 ? count_occurrences(cur, sp.pos + parent_pos, PoolPrev{sp.pos}) : 0;
+                occ = __shfl_sync(0xffffffffu, occ, 0);
+            }
+            cur.occur = (uint8_t)occ;
+            if (lane == 0 && occ != 1) sp.pos[leaf_pos].occur = (uint8_t)occ;
             n_moves = generate_legal_warp(cur, sm, lane);
             __syncwarp();
             if (lane == 0) {
-                bool need_scan = false;
-                const int out = outcome_before_scan(cur, sm, n_moves, sp.pos + parent_pos, PoolPrev{sp.pos}, ts.max_len, &need_scan);
+                int out;
+                if (W >= 0) {
+                    out = outcome_before_history(cur, sm, n_moves, ts.max_len);
+                    scan = out == OUT_NONE && W >= 3;  // the claim-ahead scan needs three stored plies behind reversible moves
+                } else {
+                    bool need_scan = false;
+                    out = outcome_before_scan(cur, sm, n_moves, sp.pos + parent_pos, PoolPrev{sp.pos}, ts.max_len, &need_scan);
+                    scan = need_scan;
+                }
                 if (out != OUT_NONE) term = terminal_value_to_play(out) < 0 ? 2 : 1;
-                scan = need_scan;
             }
             scan = __shfl_sync(0xffffffffu, scan, 0);
             if (scan) {
                 bool found = false;
-                for (int i = lane; i < n_moves && !found; i += 32) found = move_claims_threefold(cur, sm[i], sp.pos + parent_pos, PoolPrev{sp.pos});
+                for (int i = lane; i < n_moves && !found; i += 32)
+                    found = W >= 0 ? move_claims_threefold_hist(cur, sm[i], sp.pos, s_hh[warp], s_hp[warp], W)
+                                   : move_claims_threefold(cur, sm[i], sp.pos + parent_pos, PoolPrev{sp.pos});
                 if (__any_sync(0xffffffffu, found)) term = 1;  // draw by threefold claim
             }
         }
@@ -352,6 +374,12 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_step_kernel(SearchParams
             }
             __syncwarp();
             ++sims_done;
+            // A simulation that ends in a terminal node needs no evaluation, so the tree goes straight on to the next one - but a tree whose
+            // favourite line ends in a claimable draw or a mate would run hundreds of descents inside ONE launch while the other 1023
+            // warps have long finished (measured: 50 us typical, 350-500 us spikes, all of it this tail).  After a few terminal
+            // simulations the tree yields: it has no leaf in the next batch and carries on in the next step.  The order of its
+            // simulations, hence every visit count, is unchanged; every step still advances every unfinished tree by >= 1 simulation.
+            if (++n_term >= MCTS_TERMINAL_SIMS_PER_STEP) break;
             continue;
         }
         // ---- a leaf for the network: evaluation slot n_new of this tree
@@ -380,7 +408,7 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_step_kernel(SearchParams
     }
     if (lane == 0) {
         ts.n_pending = n_new;
-        ts.status = n_new > 0 ? TREE_WAIT_LEAF : TREE_DONE;
+        ts.status = (n_new > 0 || sims_done < sims_target) ? TREE_WAIT_LEAF : TREE_DONE;  // n_new == 0 with simulations left: yielded
     }
 }
 

@@ -601,6 +601,25 @@ CB_HDN bool move_claims_threefold(const Pos& cur, Move m, const Pos* before, Pre
 // claim-ahead scan over the legal moves: *scan is set when that scan (move_claims_threefold for every legal
 // move, any order) still has to decide between OUT_THREEFOLD_REPETITION and the returned OUT_NONE.
 // `legal` / `n_legal` must hold generate_legal(cur).  max_len: config.max_game_length (game.py:55), 0 to disable.
+// the part of outcome_before_scan that needs no history beyond cur.occur; OUT_NONE here means "not over unless the claim-ahead scan says so"
+CB_HDN int outcome_before_history(const Pos& cur, const Move* legal, int n_legal, int max_len) {
+    if (max_len > 0 && cur.ply == max_len) return OUT_MAX_LENGTH;
+    if (n_legal == 0 && checkers_mask(cur)) return OUT_CHECKMATE;
+    if (is_insufficient_material(cur)) return OUT_INSUFFICIENT_MATERIAL;
+    if (n_legal == 0) return OUT_STALEMATE;
+    if (cur.halfmove >= 150) return OUT_SEVENTYFIVE_MOVES;
+    if (cur.occur >= 5) return OUT_FIVEFOLD_REPETITION;
+    if (cur.halfmove >= 100) return OUT_FIFTY_MOVES;  // can_claim_fifty_moves
+    if (cur.halfmove >= 99) {
+        for (int i = 0; i < n_legal; ++i) {
+            if (is_zeroing(cur, legal[i])) continue;
+            Pos nxt = push_move(cur, legal[i]);
+            if (has_legal_moves(nxt)) return OUT_FIFTY_MOVES;
+        }
+    }
+    if (cur.occur >= 3) return OUT_THREEFOLD_REPETITION;  // can_claim_threefold_repetition
+    return OUT_NONE;
+}
 template <class PrevFn>
 CB_HDN int outcome_before_scan(const Pos& cur, const Move* legal, int n_legal, const Pos* before, PrevFn prev, int max_len, bool* scan) {
     *scan = false;

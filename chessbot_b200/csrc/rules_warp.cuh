@@ -177,4 +177,73 @@ __device__ int generate_legal_warp(const Pos& p, Move* out, int lane) {
     return total;
 }
 
+// ---------------------------------------------------------------------------------- repetition history, warp-cooperative
+// python-chess's repetition scans (is_repetition, can_claim_threefold_repetition) walk the move stack back, one position per step, until
+// a move was irreversible.  On the device the positions before a tree leaf are a linked list (tree path, then the root's game record):
+// walked serially that is one dependent memory access per ply, three times per new leaf (occurrence count + the claim-ahead scan in
+// two rounds of 32 legal moves), up to 100 plies deep - the tail that set mcts_step's duration.  Here the whole window is fetched in
+// parallel, 32 plies per round: the tree part through the recorded path (node -> position id), the record part by index (a record is
+// contiguous, one ply per slot), and key hash + position id land in shared memory; the scans then compare hashes there and touch a
+// full position only on a hash match.
+constexpr int MCTS_HIST = 128;
+
+// W = number of positions before `cur` (1 .. W plies back) those scans examine: q_a is examined iff cur and q_1 .. q_(a-1) were all
+// entered by reversible moves and q_a is stored.  h_hash[a-1] / h_pos[a-1] are filled for a <= W.  -1: window longer than MCTS_HIST.
+// path[0 .. depth-1]: nodes root .. leaf; the leaf's own position is `cur`.
+__device__ int gather_history_warp(const Pos* pool, const Node* nodes, const int32_t* path, int depth, int root_pos, int rec_start, bool cur_irrev,
+                                   u64* h_hash, int32_t* h_pos, int lane) {
+    if (cur_irrev) return 0;
+    int W = 0;
+    for (int base = 0; base < MCTS_HIST; base += 32) {
+        const int a = base + lane + 1;  // plies back
+        int pid = -1;
+        if (a <= depth - 1) {
+            pid = nodes[path[depth - 1 - a]].pos_id;
+        } else {
+            const int idx = root_pos - (a - (depth - 1));
+            if (idx >= rec_start) pid = idx;
+        }
+        u64 h = 0;
+        bool irrev = false;
+        if (pid >= 0) {
+            h = pool[pid].hash;
+            irrev = pool[pid].irrev_in != 0;
+        }
+        h_hash[a - 1] = h;
+        h_pos[a - 1] = pid;
+        const unsigned exist = __ballot_sync(0xffffffffu, pid >= 0);
+        const unsigned irr = __ballot_sync(0xffffffffu, pid >= 0 && irrev);
+        const int n_exist = exist == 0xffffffffu ? 32 : __ffs(~exist) - 1;  // the stored positions are a prefix of the round
+        const int first_irr = irr ? __ffs(irr) - 1 : 32;                     // the position entered by an irreversible move is still examined
+        const int take = min(n_exist, first_irr + 1);
+        W += take;
+        if (take < 32) return W;
+    }
+    return -1;
+}
+
+// count_occurrences(cur, ...) over the gathered window: every lane returns the count (capped at 255 like the serial version)
+__device__ int count_occurrences_warp(const Pos& cur, const Pos* pool, const u64* h_hash, const int32_t* h_pos, int W, int lane) {
+    int n = 1;
+    for (int base = 0; base < W; base += 32) {
+        const int i = base + lane;
+        const bool hit = i < W && h_hash[i] == cur.hash && key_equal(pool[h_pos[i]], cur);
+        n += __popc(__ballot_sync(0xffffffffu, hit));
+    }
+    return n < 255 ? n : 255;
+}
+
+// move_claims_threefold(cur, m, ...) over the gathered window (one lane per move)
+__device__ bool move_claims_threefold_hist(const Pos& cur, Move m, const Pos* pool, const u64* h_hash, const int32_t* h_pos, int W) {
+    if (is_zeroing(cur, m)) return false;
+    Pos nxt = push_move(cur, m);
+    if (nxt.irrev_in) return false;
+    int n = 0;
+    for (int a = 1; a <= W; a += 2)  // same side to move as nxt: 1, 3, 5, ... plies back
+        if (h_hash[a - 1] == nxt.hash && key_equal(pool[h_pos[a - 1]], nxt)) {
+            if (++n >= 2) return true;
+        }
+    return false;
+}
+
 }  // namespace cb
