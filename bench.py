@@ -253,7 +253,7 @@ def parity_leg(eng, net, records, n):
             "max_dvalue": float(dv.max()), "top1_agree": float((lf.cpu().numpy().argmax(1) == p_ref.argmax(1)).mean()), "tolerance_abs": 2e-2,
             "holds": bool(dp.max() <= 2e-2 and dv.max() <= 2e-2),
             "against": "oracle/ref_model.py (torch fp32, TF32 off) on the positions and weights of the timed run; residual stream "
-                       + ("bf16 hi + lo" if net.stream_hi_lo else "bf16")}
+                       + ("bf16" if not net.stream_hi_lo else "bf16 hi + lo" if net.stream_hi_lo is True else f"hi + lo from block {net.stream_hi_lo - 1}")}
 
 
 def run_reference_arm(args):
@@ -316,7 +316,8 @@ def run_gpu_arm(args):
     W, K = args.warmup, args.steps
     eng = Engine.get(local_rank)
     net = DeviceNetwork(trained_like_bn(keras_init_weights(filters, blocks, seed=0), filters, blocks), filters, blocks,
-                        max_batch=trees, device=local_rank, stream_hi_lo=args.stream == "hilo")
+                        max_batch=trees, device=local_rank,
+                        stream_hi_lo=(args.stream == "hilo") if "@" not in args.stream else int(args.stream.split("@")[1]) + 1)
     boards = random_positions_device(trees, seed=1000 + rank)   # every rank searches its own shard of games
     records = [b.export_record() for b in boards]
     total_steps = W + 2 * K + 4
@@ -453,7 +454,7 @@ def run_gpu_arm(args):
                 "workload": f"batched MCTS leaf evaluation + tree update: {trees} concurrent games per GPU, {blocks}x{filters} "
                             f"ResNet (glorot kernels, trained-like BN statistics), one leaf per game per step (encode + forward + legal-move softmax + backup + select)",
                 "net": args.net, "trees_per_gpu": trees, "parallelism": f"games sharded over {world} GPU(s), no collective",
-                "residual_stream": "bf16 hi + lo" if args.stream == "hilo" else "bf16",
+                "residual_stream": {"hilo": "bf16 hi + lo", "bf16": "bf16"}.get(args.stream, args.stream),
                 "l2": "working set per step (49 MB weights + 3-4 x 52 MB activations + node pool) exceeds the 126 MB L2; no flush",
                 "fwd_gflop_per_position": flops_per_position(filters, blocks) / 1e9,
             },
@@ -947,7 +948,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the untimed checker leg (device network vs the torch-fp32 oracle)")
-    ap.add_argument("--stream", default="hilo", choices=["hilo", "bf16"], help="residual stream between blocks: bf16 hi + lo (default) or bf16 (round-1 datapath)")
+    ap.add_argument("--stream", default="hilo", help="residual stream between blocks: hilo = bf16 hi + lo (default), bf16 = round-1 datapath, "
+                                                      "hilo@K = hi + lo only from residual block K on")
     ap.add_argument("--workload", default="search", choices=["search", "leaf_eval", "train", "puzzles", "selfplay"],
                     help="search = the headline (batched MCTS, BASELINE north_star); leaf_eval = BASELINE config 2 (use --net 6x128); "
                          "train = BASELINE config 5 (train.py step, --batch per GPU); puzzles = BASELINE config 4 (--positions x --sims); "

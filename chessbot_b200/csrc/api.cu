@@ -149,6 +149,7 @@ struct Net {
     DevBuf<float> head_w, head_bn, fc1, fc2, wp, wpt;
     DevBuf<__nv_bfloat16> act[3], act_lo;            // act_lo: low half of the residual stream (stream_hi_lo)
     bool stream_hi_lo = true;
+    int hi_lo_from_block = 0;                        // residual blocks before this one keep a bf16 stream (0: hi + lo everywhere)
     DevBuf<float> head_raw, pfeat;
     DevBuf<LayerDesc> layer_desc, dbg_desc;          // tower kernel: per-layer descriptors (dbg_desc: cb_debug_conv_layer)
     DevBuf<CUtensorMap> wmaps;                       // tensor maps of the packed weights, one per layer
@@ -324,7 +325,9 @@ int cb_net_create(cb_ctx* ctx, int filters, int blocks, int max_batch, float lea
     return 0;
 }
 int cb_net_set_stream_precision(cb_ctx* ctx, int hi_lo) {
+    // hi_lo: 0 = bf16 stream, 1 = hi + lo from the stem on, k >= 2 = hi + lo from the output of residual block k - 1 on
     ctx->net.stream_hi_lo = hi_lo != 0;
+    ctx->net.hi_lo_from_block = hi_lo >= 2 ? hi_lo - 1 : 0;
     ctx->net.ready = false;
     return 0;
 }
@@ -492,6 +495,11 @@ static int net_tower(cb_ctx* ctx, const void* planes_act_dev, int n, float* valu
     tp.head_w = net.head_w.p;
     tp.head_out = net.head_raw.p;
     tp.lo_buf = (uint8_t*)net.act_lo.p;
+    {
+        static const bool probe = getenv("CB_TOWER_FP8_PROBE") != nullptr;  // measurement only: profiles/r2_precision_variants.md
+        tp.fp8_probe = probe;
+    }
+    tp.lo_from_layer = net.hi_lo_from_block > 0 ? 2 * net.hi_lo_from_block : 0;  // block b's output is layer 2 b + 2; its input stream is layer 2 b
     tp.n_boards_dev = n_dev;
     tp.full_sectors = (net.stream_hi_lo ? 4 : 3) * act_bytes(n, net.cpad) > ((size_t)96 << 20);  // the rotating activation buffers (+ lo) do not fit the 126 MB L2
     tp.flags = net.flags.p;

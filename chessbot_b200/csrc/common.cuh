@@ -211,6 +211,16 @@ __device__ __forceinline__ void umma2_bf16(uint32_t d_tmem, uint64_t a_desc, uin
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// the same on e4m3 x e4m3 operands (K = 32 per MMA: the same 32 bytes per row as a bf16 K = 16 step).  Only the throughput probe of
+// profiles/r2_precision_variants.md issues it (CB_TOWER_FP8_PROBE): e4m3 misses the 2e-2 tolerance by 4-7x, no datapath uses it.
+__device__ __forceinline__ void umma2_e4m3(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // completion of all MMAs issued so far arrives on the barrier at this offset in BOTH CTAs of the pair
 __device__ __forceinline__ void umma2_commit_mc(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
@@ -266,6 +276,8 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
 __device__ __forceinline__ uint32_t idesc_bf16_f32(int m, int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
+// kind::f8f6f4 instruction descriptor: e4m3 x e4m3 -> f32 (operand formats 0), both operands K-major
+__device__ __forceinline__ uint32_t idesc_e4m3_f32(int m, int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24); }
 // the same with both operands MN-major (bits 15 / 16): shared memory holds 8 consecutive M (or N) indices in 16 bytes and
 // steps along K from one 16-byte cell to the next.  In the no-swizzle descriptor LBO is then the stride between the
 // 8-cell groups along K and SBO the stride between 8-index groups along M / N.

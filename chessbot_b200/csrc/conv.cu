@@ -109,7 +109,7 @@ __device__ __forceinline__ void warp_transpose_sum32(float (&v)[32], int lane) {
 
 // One k-chunk (64 input channels) of one item: the 9 / TPS weight stages of TPS taps each, four K = 16 MMAs per tap.  Unrolled: the tap's
 // start cell (1 + dy) * 20 + 1 + dx inside the activation tile and the K steps are immediates added to the descriptors.
-template <int TPS>
+template <int TPS, bool FP8>
 __device__ __forceinline__ void mma_k_chunk(ConvSmem* s, uint32_t d, uint64_t a_desc, uint64_t b_desc0, uint32_t idesc, uint32_t slot16, uint32_t tap16,
                                             uint32_t b_ks, int nbs, uint32_t& bs, uint32_t& bph, uint32_t accumulate) {
     constexpr uint32_t a_ks = 2 * ACT_CHUNK_BYTES / 16;
@@ -126,7 +126,8 @@ __device__ __forceinline__ void mma_k_chunk(ConvSmem* s, uint32_t d, uint64_t a_
                 const uint64_t bd0 = bd_slot + (uint64_t)(t * tap16);  // one tap = N/2 rows x 128 B
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
-                    ptx::umma2_bf16(d, ad0 + ks * a_ks, bd0 + ks * b_ks, idesc, (tap | ks) != 0 ? 1u : accumulate);
+                    if constexpr (FP8) ptx::umma2_e4m3(d, ad0 + ks * a_ks, bd0 + ks * b_ks, idesc, (tap | ks) != 0 ? 1u : accumulate);
+                    else ptx::umma2_bf16(d, ad0 + ks * a_ks, bd0 + ks * b_ks, idesc, (tap | ks) != 0 ? 1u : accumulate);
             }
             ptx::umma2_commit_mc(&s->b_empty[bs]);  // weight stage of BOTH CTAs is free when these MMAs retire
         }
@@ -161,6 +162,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
     const int nbs = min(B_SLOTS, B_RING_BYTES / (int)slot_bytes);
     const WorkRange w(cid, nclusters, units, nl);
     const int flag_base = p.epoch << 8;
+    // throughput probe only (TowerParams::fp8_probe): an e4m3 layer has half the k-chunks (128 channels per 128-byte row)
+    const int kc_shift = (!STATS && p.fp8_probe) ? 1 : 0;
 
     if (STATS)
         for (int i = threadIdx.x; i < 512; i += CONV_THREADS) s_head[i] = 0.f;  // [2][256] running sums of this CTA (head weights are not used when training)
@@ -224,7 +227,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
             int nr = r, nk_ = k, nu_ = u, nl_ = l;
             advance(nr, nk_, nu_, nl_);
             if (nr <= nl && nl_ > 0) seen = ld_acquire_gpu(p.flags + 2 * nu_ + rank);  // consumed at the top of the next item
-            for (int kc = 0; kc < L.kc; ++kc) {
+            for (int kc = 0; kc < max(1, L.kc >> kc_shift); ++kc) {
                 ptx::mbar_wait_parked(&s->a_empty[as], aph);
                 if (ptx::elect_one()) {
                     if (rank == 0) ptx::mbar_expect_tx(&s->a_full[as], 2 * ACT_K64_BYTES);
@@ -244,7 +247,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
             for (int k = 0; k < w.nu; ++k) {
                 int u, l;
                 if (!w.item(r, k, u, l)) continue;
-                const int kcs = p.layers[l].kc;
+                const int kcs = max(1, p.layers[l].kc >> kc_shift);
                 const CUtensorMap* tm_w = &p.maps[p.layers[l].w_map];
                 for (int kc = 0; kc < kcs; ++kc) {
                     const int wrow = (kc * 2 + (int)rank) * 9 * nh;  // [kc][half][tap][8][N/2][8]
@@ -267,7 +270,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
             // lasts (ncu: with runtime `% nbs` ring arithmetic it took ~70 dependent instructions per one-tap stage and the issuing warp was
             // busy most of the time): ring slots and phases are counters, the nine taps are unrolled so that their descriptor
             // offsets are immediates.
-            const uint32_t idesc = ptx::idesc_bf16_f32(256, n);
+            const bool probe = !STATS && p.fp8_probe;
+            const uint32_t idesc = probe ? ptx::idesc_e4m3_f32(256, n) : ptx::idesc_bf16_f32(256, n);
             // K-major / no-swizzle descriptors: hi word = SBO | version, lo word = address | LBO; a K=16 step adds to the address field only
             const uint64_t a_desc0 = ptx::smem_desc(ptx::smem_u32(a_buf), ACT_CHUNK_BYTES, 160);
             const uint64_t b_desc0 = ptx::smem_desc(ptx::smem_u32(b_buf), (uint32_t)nh * 16, 128);
@@ -278,7 +282,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
                 for (int k = 0; k < w.nu; ++k) {
                     int u, l;
                     if (!w.item(r, k, u, l)) continue;
-                    const int kcs = p.layers[l].kc;
+                    const int kcs = max(1, p.layers[l].kc >> kc_shift);
                     const uint32_t st = j & 1;
                     ptx::mbar_wait(&s->acc_empty[st], ((j >> 1) & 1) ^ 1);
                     ptx::tc_fence_after();
@@ -286,7 +290,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
                     for (int kc = 0; kc < kcs; ++kc) {
                         ptx::mbar_wait(&s->a_full[as], aph);
                         const uint64_t a_desc = a_desc0 + (uint64_t)(as * (A_SLOT_BYTES / 16));
-                        mma_k_chunk<tps>(s, d, a_desc, b_desc0, idesc, slot16, tap16, b_ks, nbs, bs, bph, kc != 0);
+                        if (probe) mma_k_chunk<tps, true>(s, d, a_desc, b_desc0, idesc, slot16, tap16, b_ks, nbs, bs, bph, kc != 0);
+                        else mma_k_chunk<tps, false>(s, d, a_desc, b_desc0, idesc, slot16, tap16, b_ks, nbs, bs, bph, kc != 0);
                         if (ptx::elect_one()) ptx::umma2_commit_mc(&s->a_empty[as]);
                         __syncwarp();
                         if (++as == A_SLOTS) { as = 0; aph ^= 1; }
@@ -358,8 +363,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
             // residual stream in two bf16 halves: layers whose output IS the stream (stem, second conv of a block) also store
             // lo = bf16(x - hi); the skip add of the next block reads hi + lo.  Same thread, same cell: updated in place.
             uint8_t* lo_buf = STATS ? nullptr : p.lo_buf;
-            const bool skip_lo = has_skip && lo_buf != nullptr;
-            const bool write_lo = lo_buf != nullptr && (has_skip || l == 0) && !(nl == 1);
+            // p.lo_from_layer: the stream carries a low half from the output of that layer on (0 = from the stem)
+            const bool skip_lo = has_skip && lo_buf != nullptr && l - 2 >= p.lo_from_layer;
+            const bool write_lo = lo_buf != nullptr && (has_skip || l == 0) && !(nl == 1) && l >= p.lo_from_layer;
             const bool heads = !STATS && p.head_w != nullptr && l == nl - 1;
             {
                 const uint32_t st = j & 1;

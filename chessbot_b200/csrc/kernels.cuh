@@ -44,6 +44,8 @@ struct TowerParams {
     float* head_out;            // [boards][64][3]
     uint8_t* lo_buf;            // low half of the residual stream (bf16(x - bf16(x)), same tile-native layout as the activation buffers, only the
                                 // epilogue reads / writes it, in place), or nullptr: stream rounded to bf16 at every block
+    int fp8_probe;              // THROUGHPUT PROBE ONLY (env CB_TOWER_FP8_PROBE): e4m3 MMAs over half the k-chunks, results meaningless
+    int lo_from_layer;          // the low half exists from the output of this layer on (0: whole tower); earlier blocks round the stream to bf16
     double* stats;              // training forward (one layer per launch, no skip): [2][n] per-channel sum / sum of squares of the
                                 // bf16-rounded outputs, accumulated on top of what is there; nullptr otherwise
     int full_sectors;           // epilogue also stores the zero border cells beside the first / last column (whole 32-B DRAM sectors per board

@@ -147,7 +147,9 @@ class Engine:
     def load_network(self, weights, filters, blocks, max_batch, slope=0.3, eps=1e-3, stream_hi_lo=True):
         """stream_hi_lo: residual stream kept as bf16 hi + lo between blocks (cb_net_set_stream_precision)"""
         check(lib.cb_net_create(self._h, filters, blocks, max_batch, slope, eps), "net_create")
-        check(lib.cb_net_set_stream_precision(self._h, int(bool(stream_hi_lo))), "net_set_stream_precision")
+        # True / False, or an int k >= 2: hi + lo only from residual block k - 1 on
+        mode = int(stream_hi_lo) if isinstance(stream_hi_lo, (bool, np.bool_)) else int(stream_hi_lo)
+        check(lib.cb_net_set_stream_precision(self._h, mode), "net_set_stream_precision")
         for name, arr in weights.items():
             a = np.ascontiguousarray(arr, dtype=np.float32)
             check(lib.cb_net_set_tensor(self._h, name.encode(), a.ctypes.data, a.size), "net_set_tensor")

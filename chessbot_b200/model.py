@@ -57,7 +57,7 @@ class DeviceNetwork:
         from .engine import Engine
         self.weights = {k: np.asarray(v, dtype=np.float32) for k, v in weights.items()}
         self.filters, self.blocks, self.max_batch = filters, blocks, max_batch
-        self.stream_hi_lo = bool(stream_hi_lo)          # residual stream as bf16 hi + lo between blocks (engine.load_network)
+        self.stream_hi_lo = stream_hi_lo                # residual stream as bf16 hi + lo between blocks (engine.load_network): bool, or k >= 2
         self.engine = Engine.get(device) if engine is None else engine
         self.load()
 

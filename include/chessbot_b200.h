@@ -100,7 +100,8 @@ int cb_net_finalize(cb_ctx* ctx);                  /* fold BN, pack bf16 weights
 /* How the residual stream x_{i+1} = LReLU(x_i + branch_i) of model.py:19-28 is kept between blocks.  1 (default): bf16 hi + bf16 lo
  * (~16 mantissa bits: at 20x256 the 2e-2 tolerance on the value holds with margin, profiles/r2_precision_variants.json);
  * 0: rounded to bf16 at every block (round-1 behaviour, one activation buffer less).  The reference's TF-TRT FP32 graph has no
- * counterpart (it never rounds).  Call between cb_net_create and cb_net_finalize. */
+ * counterpart (it never rounds).  k >= 2: hi + lo only from the input of residual block k - 1 on (earlier blocks round: a measured
+ * precision / speed trade, profiles/r2_precision_variants.md).  Call between cb_net_create and cb_net_finalize. */
 int cb_net_set_stream_precision(cb_ctx* ctx, int hi_lo);
 /* planes (tile-native bf16) -> value f32[n] and policy logits [n][4672] (bf16 and/or f32, either may be NULL) */
 int cb_net_forward(cb_ctx* ctx, const void* planes_act_dev, int n, float* value_dev, void* logits_bf16_dev,
