@@ -117,9 +117,15 @@ class DeviceNetwork:
         bs = min(32 if batch_size is None else int(batch_size), len(x))
         tr = getattr(self, "_trainer", None)
         if tr is None or tr.batch_size != bs:
-            tr = self._trainer = Trainer(self.weights if tr is None else tr.get_weights(), self.filters, self.blocks, bs,
+            # a trainer is built for one batch size; a new one inherits weights, optimizer momentum, step count and learning rate
+            old = tr
+            tr = self._trainer = Trainer(self.weights if old is None else old.get_weights(), self.filters, self.blocks, bs,
                                          device=self.engine.device_index)
-            self._lr = tr.config.learning_rate[0]
+            if old is None:
+                self._lr = tr.config.learning_rate[0]
+            else:
+                tr.set_weights(old.get_velocity(), what=2)
+                tr.steps = old.steps
         history = {"loss": [], "value_head_loss": [], "policy_head_loss": []}
         for epoch in range(initial_epoch, epochs):
             schedules = [cb.schedule for cb in (callbacks or []) if hasattr(cb, "schedule")]

@@ -50,13 +50,39 @@ def shard_batch(n, rank=None, world=None):
     return slice(lo, lo + base + (1 if rank < extra else 0))
 
 
-def allreduce_gradients(flat):
-    """Sums the flat gradient buffer over the ranks in place (NCCL over NVLink on the GPUs; gloo in the CPU tests) and returns
-    the factor that turns the sum of per-rank mean gradients into the gradient of the global mean loss (equal shards)."""
+def allreduce_gradients(flat, local_n=None):
+    """Sums the flat gradient buffer over the ranks in place (NCCL over NVLink on the GPUs; gloo in the CPU tests) and returns the
+    factor that turns that sum into the gradient of the GLOBAL mean loss.  Every rank holds the mean gradient of its own shard; with
+    local_n (samples of this rank's shard) given, shards may be unequal (shard_batch hands the remainder to the first ranks): each
+    rank's buffer is weighted by its share local_n / global_n before the sum (one extra scalar all-reduce).  Without local_n the
+    shards are taken as equal and the factor is 1 / world."""
     _, world = data_parallel_world()
-    if world > 1:
+    if world == 1:
+        return 1.0
+    if local_n is None:
         torch.distributed.all_reduce(flat)
+        return 1.0 / world
+    count = torch.tensor([float(local_n)], dtype=torch.float64, device=flat.device)
+    torch.distributed.all_reduce(count)
+    share = float(local_n) / float(count.item())
+    if abs(share * world - 1.0) > 1e-12:
+        flat.mul_(share * world)                           # equal shards skip the pass over the buffer
+    torch.distributed.all_reduce(flat)
     return 1.0 / world
+
+
+def average_over_ranks(arrays):
+    """element-wise mean over the ranks of a dict of float32 host arrays (BatchNormalization moving statistics before a checkpoint)"""
+    _, world = data_parallel_world()
+    if world == 1:
+        return arrays
+    dev = "cuda" if torch.distributed.get_backend() == "nccl" else "cpu"
+    out = {}
+    for k in sorted(arrays):
+        t = torch.as_tensor(np.ascontiguousarray(arrays[k], dtype=np.float32)).to(dev)
+        torch.distributed.all_reduce(t)
+        out[k] = (t / world).cpu().numpy()
+    return out
 
 
 def tensor_shapes(filters, blocks):
@@ -132,8 +158,25 @@ class Trainer:
     def get_velocity(self):
         return self._get(2)
 
-    def save(self, path):
-        """checkpoint for resuming (train.py:124-136 reloads the Keras model with its optimizer state): weights, momentum, step"""
+    def sync_moving_statistics(self):
+        """Data parallel: BatchNormalization's moving mean / variance are per GPU (every rank normalises its own shard, like
+        data-parallel Keras); this sets them to the mean over the ranks on every rank, so that a checkpoint does not depend on
+        which rank writes it.  Collective: every rank must call it."""
+        if self.world == 1:
+            return
+        w = self.get_weights()
+        bn = average_over_ranks({k: a[2:4] for k, a in w.items() if k.endswith("bn") or ".bn" in k})
+        for k, rows in bn.items():
+            w[k][2:4] = rows
+        self.set_weights(w)
+
+    def save(self, path, sync=True):
+        """checkpoint for resuming (train.py:124-136 reloads the Keras model with its optimizer state): weights, momentum, step.
+        Data parallel: collective (sync=True averages the BN moving statistics over the ranks first); rank 0 writes the file."""
+        if sync:
+            self.sync_moving_statistics()
+        if self.world > 1 and self.rank != 0:
+            return
         w, v = self.get_weights(), self.get_velocity()
         np.savez(path, __filters=self.filters, __blocks=self.blocks, __steps=self.steps,
                  **{"w/" + k: a for k, a in w.items()}, **{"v/" + k: a for k, a in v.items()})
@@ -157,11 +200,14 @@ class Trainer:
             raise ValueError("expected images [B,8,8,119], terminal values [B], search statistics [B,4672]")
         check(lib.cb_train_forward_backward(self._h, _ptr(img), _ptr(zt), _ptr(pt), n, _stream()), "train_forward_backward")
         self._keep = (img, zt, pt)     # the kernels read them asynchronously
+        self._last_n = n
 
     def apply(self, lr, momentum=None, nesterov=True, l2=None):
         momentum = self.config.momentum if momentum is None else momentum
         l2 = self.config.l2_reg if l2 is None else l2
-        scale = allreduce_gradients(self.grads)            # NCCL over NVLink: the only collective of the training step
+        # NCCL over NVLink: the only collective of the training step.  Every rank's trainer has a fixed batch, so shards are equal
+        # unless the ranks were built with different batch sizes (weighted_shards=True then weights them by their sample counts)
+        scale = allreduce_gradients(self.grads, getattr(self, "_last_n", None) if getattr(self, "weighted_shards", False) else None)
         check(lib.cb_train_apply(self._h, float(lr), float(momentum), int(nesterov), float(l2), scale, _stream()), "train_apply")
         self.steps += 1
 
