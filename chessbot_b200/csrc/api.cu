@@ -169,7 +169,7 @@ struct Search {
     DevBuf<Node> nodes;
     DevBuf<Pos> pos;
     DevBuf<TreeState> trees;
-    DevBuf<int32_t> node_count, pos_count, frame_idx, counters, scratch_i32, path, active_list, active_count;
+    DevBuf<int32_t> node_count, pos_count, frame_idx, counters, scratch_i32, path, active_list, active_count, slot_board;
     DevBuf<uint16_t> pend_moves;
     DevBuf<double> root_p64, noise, cpuct_tab, sqrt_tab;
     DevBuf<float> value, expvals;
@@ -475,7 +475,7 @@ static int next_epoch(Net& net, cudaStream_t st) {
 // tower + head features; leaves pfeat/value for the callers below
 // slot_list / n_dev (search loop): the batch holds *n_dev <= n boards, board b belongs to evaluation slot slot_list[b]
 static int net_tower(cb_ctx* ctx, const void* planes_act_dev, int n, float* value_dev, cudaStream_t st, const int32_t* slot_list = nullptr,
-                     const int* n_dev = nullptr) {
+                     const int* n_dev = nullptr, bool run_heads = true) {
     Net& net = ctx->net;
     if (!net.ready) { cb_set_error("network not finalized"); return -1; }
     if (n > net.max_batch) { cb_set_error("batch larger than max_batch"); return -1; }
@@ -509,6 +509,7 @@ static int net_tower(cb_ctx* ctx, const void* planes_act_dev, int n, float* valu
     tp.n = net.cpad;
     tp.slope = net.slope;
     if (prof_begin(ctx, CB_PROF_CONV, st) || launch_tower(tp, ctx->sms, st) || prof_end(ctx, st)) return -1;
+    if (!run_heads) return 0;  // the search finishes the heads inside mcts_step (SearchParams::head_raw)
     HeadParams hp{net.head_raw.p, net.head_bn.p, net.fc1.p, net.fc2.p, net.filters, net.slope, value_dev, net.pfeat.p, slot_list, n_dev};
     if (prof_begin(ctx, CB_PROF_HEADS, st) || launch_head_features(hp, n, st) || prof_end(ctx, st)) return -1;
     return 0;
@@ -748,7 +749,7 @@ int cb_search_set_leaves(cb_ctx* ctx, int leaves) {
     if (s.max_trees <= 0) { cb_set_error("cb_search_create first"); return -1; }
     if (leaves == s.leaves) return 0;
     const size_t ns = (size_t)s.max_trees * leaves;
-    if (s.active_list.alloc(ns) || s.active_count.alloc(1) || s.frame_idx.alloc(ns * 8) || s.path.alloc(ns * MCTS_MAX_PATH) || s.pend_moves.alloc(ns * MAX_MOVES) || s.value.alloc(ns) ||
+    if (s.active_list.alloc(ns) || s.slot_board.alloc(ns) || s.active_count.alloc(1) || s.frame_idx.alloc(ns * 8) || s.path.alloc(ns * MCTS_MAX_PATH) || s.pend_moves.alloc(ns * MAX_MOVES) || s.value.alloc(ns) ||
         s.synth_hash.alloc(ns) || s.slots.alloc(ns) || s.planes_act.alloc(act_bytes((int)ns, 128) / 2) || s.planes_i16.alloc(ns * 7616))
         return -1;
     s.expvals.free_();
@@ -824,7 +825,21 @@ static int search_begin_impl(cb_ctx* ctx, int n_trees, const void* records_host,
     s.sp.pfeat = ctx->net.pfeat.p;
     s.sp.wpt = ctx->net.wpt.p;
     s.sp.expvals = s.expvals.p;
-    return launch_mcts_begin(s.sp, st);
+    // fused step with the device network: heads in mcts_step's phase A, the selected leaf encoded at the end of its phase B
+    const bool fused = eval_mode == CB_EVAL_NET;
+    s.sp.slot_board = s.slot_board.p;
+    s.sp.head_raw = fused ? ctx->net.head_raw.p : nullptr;
+    s.sp.head_bn = ctx->net.head_bn.p; s.sp.fc1 = ctx->net.fc1.p; s.sp.fc2 = ctx->net.fc2.p;
+    s.sp.head_c = ctx->net.filters; s.sp.slope = ctx->net.slope;
+    s.sp.planes_act = fused ? s.planes_act.p : nullptr;
+    if (launch_mcts_begin(s.sp, st)) return -1;
+    if (fused) {  // the roots are the first batch: encoded by the stand-alone kernel, every later batch by mcts_step itself
+        if (prof_begin(ctx, CB_PROF_ENCODE, st) ||
+            launch_encode(s.pos.p, s.frame_idx.p, s.n_trees * s.leaves, s.planes_act.p, nullptr, st, s.active_list.p, s.active_count.p) ||
+            prof_end(ctx, st))
+            return -1;
+    }
+    return 0;
 }
 
 int cb_search_begin(cb_ctx* ctx, int n_trees, const void* records_host, const int32_t* rec_len, const int32_t* sims,
@@ -868,12 +883,10 @@ int cb_search_step(cb_ctx* ctx, void* stream) {
     Search& s = ctx->search;
     cudaStream_t st = (cudaStream_t)stream;
     if (s.eval_mode == CB_EVAL_NET) {
-        // only the slots that hold a pending leaf are encoded and evaluated (compacted batch, size known on the device only)
-        if (prof_begin(ctx, CB_PROF_ENCODE, st) ||
-            launch_encode(s.pos.p, s.frame_idx.p, s.n_trees * s.leaves, s.planes_act.p, nullptr, st, s.active_list.p, s.active_count.p) ||
-            prof_end(ctx, st) || debug_sync(st, "encode"))
-            return -1;
-        if (net_tower(ctx, s.planes_act.p, s.n_trees * s.leaves, s.value.p, st, s.active_list.p, s.active_count.p) || debug_sync(st, "tower"))
+        // only the slots that hold a pending leaf are in the batch (compacted, size known on the device only); their planes were written by
+        // the previous mcts_step (the roots' by cb_search_begin), and mcts_step finishes the heads: two launches per step
+        if (net_tower(ctx, s.planes_act.p, s.n_trees * s.leaves, s.value.p, st, s.active_list.p, s.active_count.p, /*run_heads=*/false) ||
+            debug_sync(st, "tower"))
             return -1;
     } else if (s.eval_mode == CB_EVAL_SYNTH) {
         if (launch_encode(s.pos.p, s.frame_idx.p, s.n_trees * s.leaves, nullptr, s.planes_i16.p, st)) return -1;

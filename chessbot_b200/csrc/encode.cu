@@ -13,7 +13,7 @@
 // per frame: White to move -> row = 7 - rank, col = file; Black to move -> row = rank, col = 7 - file,
 // "player 1" = the side to move of that frame, gameimage.py:37-41).  Phase 2: each lane writes 16-byte
 // cells (8 channels of one square), 512 contiguous-ish bytes per warp instruction.
-#include "kernels.cuh"
+#include "encode.cuh"
 
 namespace cb {
 
@@ -32,93 +32,9 @@ __global__ void __launch_bounds__(ENC_WARPS * 32) encode_planes_kernel(const Pos
     if (pos_i >= n || (n_dev && pos_i >= *n_dev)) return;
     const int32_t* fi = frame_idx + (size_t)(slot_list ? slot_list[pos_i] : pos_i) * 8;
 
-    // ---- phase 1: 112 oriented masks (channel c = 14*slot + plane, slot = 7 - t for t plies back)
-    for (int c = lane; c < 112; c += 32) {
-        const int slot = c / 14, plane = c % 14, t = 7 - slot;
-        const int idx = fi[t];
-        u64 m = 0;
-        if (idx >= 0) {
-            const Pos& f = pos_base[idx];
-            const int turn = f.turn;
-            if (plane < 12) {
-                // plane order P,N,B,R,K,Q (gameimage.py:10-17); bb order P,N,B,R,Q,K
-                const int pt = plane % 6;
-                const int bbi = pt == 4 ? KING : (pt == 5 ? QUEEN : pt);
-                const int color = plane < 6 ? turn : (turn ^ 1);
-                const u64 raw = f.bb[bbi] & f.occ[color];
-                // White to move: index = (7-rank)*8 + file = sq ^ 56 (byte swap).
-                // Black to move: index = rank*8 + (7-file) = sq ^ 7 (bit-reverse then byte swap).
-                const u64 x = turn == WHITE ? raw : __brevll(raw);
-                m = ((u64)__byte_perm((uint32_t)x, 0, 0x0123) << 32) | __byte_perm((uint32_t)(x >> 32), 0, 0x0123);
-            } else {
-                m = (f.occur >= (plane == 12 ? 2 : 3)) ? ~0ULL : 0ULL;  // is_repetition(2 | 3), gameimage.py:72-74
-            }
-        }
-        s_mask[warp][c] = m;
-    }
-    if (lane < 8) {
-        const Pos& cur = pos_base[fi[0]];
-        const int w = cur.turn == WHITE;
-        int v = 0;
-        switch (lane) {
-            case 0: v = w; break;                                                      // colour (gameimage.py:88-91)
-            case 1: v = cur.ply; break;                                                // len(move_stack) (:103)
-            case 2: v = (cur.castling & (w ? CR_WK : CR_BK)) != 0; break;              // mover kingside (:119-132)
-            case 3: v = (cur.castling & (w ? CR_WQ : CR_BQ)) != 0; break;
-            case 4: v = (cur.castling & (w ? CR_BK : CR_WK)) != 0; break;              // opponent
-            case 5: v = (cur.castling & (w ? CR_BQ : CR_WQ)) != 0; break;
-            case 6: v = cur.halfmove; break;                                           // halfmove clock (:146)
-            default: v = 0;
-        }
-        s_scalar[warp][lane] = v;
-    }
-    __syncwarp();
-
-    // ---- phase 2a: bf16 cells in tile-native layout.  Per 8-channel chunk the warp writes the 64
-    // squares in two instructions; 8 lanes cover one board row = 128 contiguous bytes.
-    if (planes_act) {
-        const int pair = pos_i >> 1, bip = pos_i & 1;
-        uint8_t* out = reinterpret_cast<uint8_t*>(planes_act);
-        const int ply = s_scalar[warp][1], hm = s_scalar[warp][6];
-        // what bf16 holds exactly (8 significant bits) stays in place, the remainder goes next door
-        const float ply_hi = __uint_as_float(__float_as_uint((float)ply) & 0xFFFF0000u);
-        const float hm_hi = __uint_as_float(__float_as_uint((float)hm) & 0xFFFF0000u);
-        for (int chunk = 0; chunk < 16; ++chunk) {
-            uint32_t w_scalar[4] = {0, 0, 0, 0};
-            if (chunk >= 14) {
-                float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                if (chunk == 14) {
-#pragma unroll
-                    for (int e = 0; e < 6; ++e) v[e] = (float)s_scalar[warp][e];
-                    v[1] = ply_hi;
-                    v[6] = hm_hi;
-                    v[7] = (float)ply - ply_hi;  // channel 119
-                } else {
-                    v[0] = (float)hm - hm_hi;    // channel 120
-                }
-#pragma unroll
-                for (int e = 0; e < 8; e += 2) {
-                    __nv_bfloat162 b2 = __floats2bfloat162_rn(v[e], v[e + 1]);
-                    w_scalar[e >> 1] = *reinterpret_cast<uint32_t*>(&b2);
-                }
-            }
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int sq = half * 32 + lane;  // row*8 + col
-                uint32_t w[4] = {w_scalar[0], w_scalar[1], w_scalar[2], w_scalar[3]};
-                if (chunk < 14) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e)
-                        if ((s_mask[warp][chunk * 8 + e] >> sq) & 1) w[e >> 1] |= (e & 1) ? 0x3F800000u : 0x00003F80u;
-                }
-                uint8_t* dst = out + act_offset_bytes(pair, 16, chunk, act_cell(sq >> 3, bip, sq & 7));
-                *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
-                // whole 32-B sectors per board row: the first / last column also store the zero border cell next to theirs
-                if ((sq & 7) == 0) *reinterpret_cast<uint4*>(dst - 16) = make_uint4(0u, 0u, 0u, 0u);
-                if ((sq & 7) == 7) *reinterpret_cast<uint4*>(dst + 16) = make_uint4(0u, 0u, 0u, 0u);
-            }
-        }
-    }
+    // ---- phase 1 + 2a (encode.cuh: the same warp routines mcts_step_kernel uses for the leaf it selects)
+    encode_masks_warp(pos_base, fi, s_mask[warp], s_scalar[warp], lane);
+    if (planes_act) encode_cells_warp(s_mask[warp], s_scalar[warp], pos_i, planes_act, lane);
     // ---- phase 2b: the reference's int16 [8][8][119] image (exact integers)
     if (planes_i16) {
         int16_t* o = planes_i16 + (size_t)pos_i * 64 * 119;

@@ -154,6 +154,16 @@ struct SearchParams {
     int32_t* path;             // [slots][MCTS_MAX_PATH] node ids root..leaf of every pending leaf
     int32_t* active_list;      // [slots] the evaluation slots that hold a pending leaf after this step, in claim order: the next
     int32_t* active_count;     // step encodes / evaluates only these (a batch shrinks as trees finish their simulations)
+    // EVAL_NET, fused step (tower + mcts_step only): the tree's warp finishes the heads of its own leaf in phase A and encodes the
+    // leaf it selects at the end of phase B, so a step is two launches instead of four
+    int32_t* slot_board;       // [slots] index of the slot's leaf in the evaluation batch it was claimed into (= its row in head_raw)
+    const float* head_raw;     // [batch][64][3] raw 1x1 head convolutions of the tower (nullptr: heads come from sp.value / sp.pfeat)
+    const float* head_bn;      // [3][2] folded scale / shift of the value conv and the two policy conv channels
+    const float* fc1;          // [64][c] value Dense
+    const float* fc2;          // [c]
+    int head_c;                // filters
+    float slope;               // LeakyReLU slope
+    __nv_bfloat16* planes_act; // [batch] input planes of the NEXT step's batch (nullptr: a separate encode launch does it)
 };
 
 // Weight gradient of one 3x3 convolution (wgrad.cu)

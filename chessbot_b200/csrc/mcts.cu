@@ -13,6 +13,7 @@
 //      immediately (the reference re-evaluates them on every visit, mcts.py:67-74) and the descent
 //      restarts; a non-terminal leaf records its ordered legal moves + the 8 frames to encode.
 #include "kernels.cuh"
+#include "encode.cuh"
 #include "policy.cuh"
 #include "rules_warp.cuh"
 
@@ -112,6 +113,35 @@ __device__ __forceinline__ void settle_path(Node* nodes, const int32_t* path, in
     }
 }
 
+// K3 as a warp routine: the heads of ONE board (model.py:43-56 after the fused 1x1 convolutions), bit for bit what head_features_kernel
+// (heads.cu, one block of 256 threads per board) computes - same fmaf chains, the same 32-lane xor butterflies per group of 32
+// channels, the same sequential sum of the eight group totals - so a position's value and policy features do not depend on which of
+// the two produced them.  pfeat (128) and v0 (64) live in the warp's shared-memory scratch; every lane returns the value.
+__device__ __forceinline__ float head_features_warp(const float* __restrict__ raw /*[64][3]*/, const float* __restrict__ bn, const float* __restrict__ fc1,
+                                                    const float* __restrict__ fc2, int c, float slope, float* s_v0 /*[64]*/, float* s_pfeat /*[128]*/,
+                                                    int lane) {
+    auto lrelu = [slope](float x) { return x > 0.f ? x : x * slope; };
+    for (int t = lane; t < 64; t += 32) s_v0[t] = lrelu(fmaf(raw[t * 3], bn[0], bn[1]));
+    for (int t = lane; t < 128; t += 32) {
+        const int sq = t >> 1, ch = t & 1;
+        s_pfeat[t] = lrelu(fmaf(raw[sq * 3 + 1 + ch], bn[2 + 2 * ch], bn[3 + 2 * ch]));
+    }
+    __syncwarp();
+    float s = 0.f;
+    for (int g = 0; g < 8; ++g) {  // group g = warp g of the block kernel: channels 32 g .. 32 g + 31
+        const int t = g * 32 + lane;
+        float part = 0.f;
+        if (t < c) {
+            float h = 0.f;
+            for (int sq = 0; sq < 64; ++sq) h = fmaf(s_v0[sq], fc1[sq * c + t], h);
+            part = lrelu(h) * fc2[t];
+        }
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        s += __shfl_sync(0xffffffffu, part, 0);  // the block kernel keeps lane 0's total of every group
+    }
+    return tanhf(s);
+}
+
 constexpr int MCTS_WARPS = 4;
 constexpr int MCTS_TERMINAL_SIMS_PER_STEP = 4;
 
@@ -121,6 +151,10 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_step_kernel(SearchParams
     __shared__ int32_t s_path[MCTS_WARPS][MCTS_MAX_PATH];
     __shared__ u64 s_hh[MCTS_WARPS][MCTS_HIST];      // key hashes / position ids of the reversible history of the leaf being set up
     __shared__ int32_t s_hp[MCTS_WARPS][MCTS_HIST];
+    __shared__ float s_pf[MCTS_WARPS][128];          // fused step: policy features / value-head inputs of the leaf being expanded
+    __shared__ float s_v0[MCTS_WARPS][64];
+    __shared__ u64 s_mask[MCTS_WARPS][112];          // fused step: encoder scratch for the leaf selected at the end
+    __shared__ int s_scal[MCTS_WARPS][8];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tree = blockIdx.x * MCTS_WARPS + warp;
     if (tree >= sp.n_trees) return;
@@ -139,12 +173,19 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_step_kernel(SearchParams
         const int n = sl.n_moves, leaf = sl.leaf_node;
         const uint16_t* moves = sp.pend_moves + (size_t)slot * MAX_MOVES;
         const int turn = sp.pos[sl.leaf_pos].turn;
+        const bool fused = sp.eval_mode == EVAL_NET && sp.head_raw != nullptr;
+        float value_fused = 0.f;
+        if (fused) {
+            value_fused = head_features_warp(sp.head_raw + (size_t)sp.slot_board[slot] * 192, sp.head_bn, sp.fc1, sp.fc2, sp.head_c, sp.slope,
+                                             s_v0[warp], s_pf[warp], lane);
+            __syncwarp();
+        }
         for (int i = lane; i < n; i += 32) {
             const int a = move_to_action(moves[i], turn);
             float e;
             if (sp.eval_mode == EVAL_NET) {
                 const float4* wr = reinterpret_cast<const float4*>(sp.wpt + (size_t)a * 128);
-                const float4* pf = reinterpret_cast<const float4*>(sp.pfeat + (size_t)slot * 128);
+                const float4* pf = fused ? reinterpret_cast<const float4*>(s_pf[warp]) : reinterpret_cast<const float4*>(sp.pfeat + (size_t)slot * 128);
                 float acc = 0.f;
 #pragma unroll 8
                 for (int k = 0; k < 32; ++k) {
@@ -187,7 +228,7 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_step_kernel(SearchParams
         }
         __syncwarp();
         const int plen = sl.path_len;
-        const float v = -sp.value[slot];  // update(node, -value), mcts.py:74
+        const float v = -(fused ? value_fused : sp.value[slot]);  // update(node, -value), mcts.py:74
         if (lane == 0) {
             Node& lf = sp.nodes[leaf];
             lf.first_child = base;
@@ -393,16 +434,25 @@ __global__ void __launch_bounds__(MCTS_WARPS * 32) mcts_step_kernel(SearchParams
         }
         if (vl && depth > 0) virtual_loss_path(sp.nodes, path, depth, lane);
         __syncwarp();
+        int board = 0;
         if (lane == 0) {
             SlotState sl;
             sl.leaf_node = node; sl.leaf_pos = leaf_pos; sl.n_moves = n_moves; sl.path_len = depth > 0 ? depth : 0;
             sp.slots[slot] = sl;
             if (vl) sp.nodes[node].term = 3;
             fill_frames(sp, slot, leaf_pos);
-            sp.active_list[atomicAdd(sp.active_count, 1)] = slot;  // this leaf is in the next step's evaluation batch
+            board = atomicAdd(sp.active_count, 1);
+            sp.active_list[board] = slot;  // this leaf is in the next step's evaluation batch
+            if (sp.slot_board) sp.slot_board[slot] = board;
             __threadfence_block();
         }
         __syncwarp();
+        if (sp.planes_act) {  // fused step: the input planes of the leaf, at its place in the next batch
+            board = __shfl_sync(0xffffffffu, board, 0);
+            encode_masks_warp(sp.pos, sp.frame_idx + (size_t)slot * 8, s_mask[warp], s_scal[warp], lane);
+            encode_cells_warp(s_mask[warp], s_scal[warp], board, sp.planes_act, lane);
+            __syncwarp();
+        }
         ++n_new;
         if (vl && depth <= 0) break;  // no recorded path, no virtual loss: do not select a second leaf on top of it
     }
@@ -438,7 +488,9 @@ __global__ void __launch_bounds__(128) mcts_begin_kernel(SearchParams sp) {
     uint16_t* pm = sp.pend_moves + (size_t)slot0 * MAX_MOVES;
     for (int i = 0; i < ml.n; ++i) pm[i] = ml.m[i];
     for (int i = 0; i < sp.leaves; ++i) fill_frames(sp, slot0 + i, ts.root_pos);  // every slot of the batch encodes a valid position
-    sp.active_list[atomicAdd(sp.active_count, 1)] = slot0;                        // the root is the first evaluation of the tree
+    const int board = atomicAdd(sp.active_count, 1);
+    sp.active_list[board] = slot0;                                                // the root is the first evaluation of the tree
+    if (sp.slot_board) sp.slot_board[slot0] = board;
 }
 
 int launch_mcts_begin(const SearchParams& sp, cudaStream_t stream) {
