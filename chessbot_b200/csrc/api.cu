@@ -496,7 +496,9 @@ static int net_tower(cb_ctx* ctx, const void* planes_act_dev, int n, float* valu
     tp.head_out = net.head_raw.p;
     tp.lo_buf = (uint8_t*)net.act_lo.p;
     {
-        static const bool probe = getenv("CB_TOWER_FP8_PROBE") != nullptr;  // measurement only: profiles/r2_precision_variants.md
+        // measurement only (profiles/r2_precision_variants.md): bit 0 = e4m3 throughput probe; CB_TOWER_DIAG bits 1 / 2 = the hi + lo stream
+        // without its lo stores / without its lo loads (numerically meaningless: where does its cost come from?)
+        static const int probe = (getenv("CB_TOWER_FP8_PROBE") ? 1 : 0) | (getenv("CB_TOWER_DIAG") ? 2 * atoi(getenv("CB_TOWER_DIAG")) : 0);
         tp.fp8_probe = probe;
     }
     tp.lo_from_layer = net.hi_lo_from_block > 0 ? 2 * net.hi_lo_from_block : 0;  // block b's output is layer 2 b + 2; its input stream is layer 2 b

@@ -163,7 +163,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
     const WorkRange w(cid, nclusters, units, nl);
     const int flag_base = p.epoch << 8;
     // throughput probe only (TowerParams::fp8_probe): an e4m3 layer has half the k-chunks (128 channels per 128-byte row)
-    const int kc_shift = (!STATS && p.fp8_probe) ? 1 : 0;
+    const int kc_shift = (!STATS && (p.fp8_probe & 1)) ? 1 : 0;
 
     if (STATS)
         for (int i = threadIdx.x; i < 512; i += CONV_THREADS) s_head[i] = 0.f;  // [2][256] running sums of this CTA (head weights are not used when training)
@@ -270,7 +270,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
             // lasts (ncu: with runtime `% nbs` ring arithmetic it took ~70 dependent instructions per one-tap stage and the issuing warp was
             // busy most of the time): ring slots and phases are counters, the nine taps are unrolled so that their descriptor
             // offsets are immediates.
-            const bool probe = !STATS && p.fp8_probe;
+            const bool probe = !STATS && (p.fp8_probe & 1);
             const uint32_t idesc = probe ? ptx::idesc_e4m3_f32(256, n) : ptx::idesc_bf16_f32(256, n);
             // K-major / no-swizzle descriptors: hi word = SBO | version, lo word = address | LBO; a K=16 step adds to the address field only
             const uint64_t a_desc0 = ptx::smem_desc(ptx::smem_u32(a_buf), ACT_CHUNK_BYTES, 160);
@@ -364,8 +364,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1) tow
             // lo = bf16(x - hi); the skip add of the next block reads hi + lo.  Same thread, same cell: updated in place.
             uint8_t* lo_buf = STATS ? nullptr : p.lo_buf;
             // p.lo_from_layer: the stream carries a low half from the output of that layer on (0 = from the stem)
-            const bool skip_lo = has_skip && lo_buf != nullptr && l - 2 >= p.lo_from_layer;
-            const bool write_lo = lo_buf != nullptr && (has_skip || l == 0) && !(nl == 1) && l >= p.lo_from_layer;
+            const bool skip_lo = has_skip && lo_buf != nullptr && l - 2 >= p.lo_from_layer && !(p.fp8_probe & 4);
+            const bool write_lo = lo_buf != nullptr && (has_skip || l == 0) && !(nl == 1) && l >= p.lo_from_layer && !(p.fp8_probe & 2);
             const bool heads = !STATS && p.head_w != nullptr && l == nl - 1;
             {
                 const uint32_t st = j & 1;
