@@ -352,3 +352,52 @@ def test_library_memory_is_owned_by_pytorch():
     fresh.search_create(256, max_nodes=256 * 40 * 48, max_positions=256 * 300, max_sims=38)
     took = E.library_device_bytes() - lib0
     assert 0.5 * need <= took <= 1.05 * need + (1 << 20), (need, took)
+
+
+def test_search_stream_and_two_lane_self_play_equal_the_one_at_a_time_path():
+    """mcts.SearchStream keeps two searches in flight (two device contexts, one stream); selfplay.play_games alternates two groups of
+    games over it.  Neither may change a result: visit counts of a submitted search equal search_batch's, and games played with
+    lanes=2 equal the same games (same per-game generators) played with lanes=1, move for move."""
+    import chessbot_b200.mcts as mcts
+    from chessbot_b200 import selfplay
+    from chessbot_b200.config import Config
+    from chessbot_b200.game import Game
+    from chessbot_b200.model import DeviceNetwork
+    from oracle import ref_model
+    rng = np.random.default_rng(3)
+    images = rng.integers(0, 2, (16, 8, 8, 119)).astype(np.int16)
+    w = ref_model.calibrate_bn(ref_model.init_weights(64, 2, seed=6), images, device="cuda")
+    net = DeviceNetwork(w, 64, 2, max_batch=64)
+    cfg = Config()
+    lines = ["", "e2e4", "e2e4 e7e5", "d2d4 d7d5 c2c4", "g1f3 g8f6 c2c4 e7e6", "e2e4 c7c5 g1f3 d7d6 d2d4"]
+
+    def games():
+        out = []
+        for ln in lines:
+            g = Game(cfg)
+            for u in ln.split():
+                g.make_move(u)
+            out.append(g)
+        return out
+    noise = [np.random.default_rng(i).gamma(0.3, 1, len(g.board.legal_moves)) for i, g in enumerate(games())]
+    base = mcts.search_batch(games(), net, 40, True, None, noise=noise)
+    ss = mcts.SearchStream(net, 2)
+    ga, gb = games()[:3], games()[3:]
+    ta = ss.submit(ga, 40, True, None, noise=noise[:3])
+    tb = ss.submit(gb, 40, True, None, noise=noise[3:])
+    got = ss.collect(ta) + ss.collect(tb)
+    for r0, r1 in zip(base, got):
+        assert r0.N == r1.N and list(r0.children) == list(r1.children)
+        assert [c.N for c in r0.children.values()] == [c.N for c in r1.children.values()]
+        assert [c.Q for c in r0.children.values()] == [c.Q for c in r1.children.values()]
+    small = Config()
+    small.num_mcts_sims = (6, 10)
+    small.max_game_length = 12
+
+    def play(lanes):
+        return selfplay.play_games(net, 6, small, rngs=[np.random.default_rng(100 + i) for i in range(6)], lanes=lanes)
+    one, two = play(1), play(2)
+    for a, b in zip(one, two):
+        assert a[2] == b[2] and a[3] == b[3] and len(a[0]) == len(b[0])
+        assert all(np.array_equal(x, y) for x, y in zip(a[0], b[0]))
+        assert all(np.array_equal(x, y) for x, y in zip(a[1][1], b[1][1])) and a[1][0] == b[1][0]
