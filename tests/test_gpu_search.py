@@ -353,3 +353,30 @@ def test_virtual_loss_single_game_with_device_network():
     print(f"\nsingle game, 400 sims, 6x128: {res[1][2] * 1e3:.0f} ms sequential, {res[8][2] * 1e3:.0f} ms with 8 leaves per call")
     # (a random-init network has no favourite at the start position; move agreement is measured in the test above)
     assert res[8][0] in res[8][1].children and res[8][2] < res[1][2]
+
+
+def test_virtual_loss_and_yielding_stress_finishes_every_tree_exactly():
+    """Stress of the step protocol: many trees, several leaves per tree under virtual loss, few simulations left at the end, terminal-heavy
+    positions (mate-in-one and claimable draws make trees yield after a few terminal simulations): every tree must end with exactly its
+    simulation budget spent (root N = sims + 1), no pool errors, for 1, 3, 4 and 16 leaves per step and uneven budgets."""
+    from chessbot_b200.board import Board
+    from chessbot_b200.engine import EVAL_SYNTH, Engine
+    eng = Engine.get()
+    lines = ["", "f2f3 e7e5 g2g4", "e2e4 e7e5 d1h5 b8c6 f1c4 g8f6", "g1f3 g8f6 f3g1 f6g8 g1f3 g8f6 f3g1 f6g8 g1f3", "d2d4 d7d5 c2c4 e7e6 b1c3 g8f6 c1g5"]
+    recs = []
+    for i in range(120):
+        b = Board()
+        for u in lines[i % len(lines)].split():
+            b.push_uci(u)
+        recs.append(b.export_record())
+    sims = [17 + (i * 7) % 90 for i in range(120)]
+    eng.search_shape = None
+    eng.search_create(120, max_nodes=120 * 130 * 48, max_positions=120 * 400, max_sims=128)
+    for leaves in (1, 3, 4, 16):
+        out = eng.search(recs, sims, eval_mode=EVAL_SYNTH, seed=9, leaves=leaves)
+        assert out["unfinished"] == 0 and out["errors"] == 0
+        assert out["root_N"].tolist() == [s + 1 for s in sims], leaves
+        assert (out["N"].sum(1) == np.array(sims)).all() or leaves > 1   # sequential mode: every simulation is a visit of one root child
+        if leaves > 1:
+            assert (out["N"].sum(1) == np.array(sims)).all()
+        assert out["sims"] == sum(sims)
