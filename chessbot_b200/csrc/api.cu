@@ -150,6 +150,7 @@ struct Net {
     DevBuf<__nv_bfloat16> act[3], act_lo;            // act_lo: low half of the residual stream (stream_hi_lo)
     bool stream_hi_lo = true;
     int hi_lo_from_block = 0;                        // residual blocks before this one keep a bf16 stream (0: hi + lo everywhere)
+    size_t l2_persist_bytes = 0;                     // persisting-L2 set-aside last requested for the lo buffer
     DevBuf<float> head_raw, pfeat;
     DevBuf<LayerDesc> layer_desc, dbg_desc;          // tower kernel: per-layer descriptors (dbg_desc: cb_debug_conv_layer)
     DevBuf<CUtensorMap> wmaps;                       // tensor maps of the packed weights, one per layer
@@ -510,6 +511,28 @@ static int net_tower(cb_ctx* ctx, const void* planes_act_dev, int n, float* valu
     tp.pairs = pairs;
     tp.n = net.cpad;
     tp.slope = net.slope;
+    if (tp.lo_buf && tp.full_sectors) {
+        // The low half of the residual stream is written and read back two layers later by the same SM; when the activations overflow L2 it
+        // makes that round trip through DRAM (2 x 52 MB per block at 1024 boards of 20x256).  A persisting access-policy window on the
+        // launching stream keeps it in L2 instead (set-aside = the buffer's size, at most 64 MB of the 126 MB): tower -1 to -2 %, 40 MHz more
+        // SM clock at the power cap (measured, profiles/README.md).  CB_TOWER_L2_PERSIST=0 turns it off, =<MB> overrides the set-aside.
+        static const int persist_env = getenv("CB_TOWER_L2_PERSIST") ? atoi(getenv("CB_TOWER_L2_PERSIST")) : -1;
+        const size_t lo_bytes = act_bytes(n, net.cpad);
+        const size_t want = persist_env >= 0 ? (size_t)persist_env << 20 : ((lo_bytes + ((size_t)4 << 20)) < ((size_t)64 << 20) ? lo_bytes + ((size_t)4 << 20) : (size_t)64 << 20);
+        if (want > 0) {
+            if (net.l2_persist_bytes != want) {
+                if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) cudaGetLastError();  // not fatal: the window then has no effect
+                net.l2_persist_bytes = want;
+            }
+            cudaStreamAttrValue av{};
+            av.accessPolicyWindow.base_ptr = net.act_lo.p;
+            av.accessPolicyWindow.num_bytes = lo_bytes;
+            av.accessPolicyWindow.hitRatio = lo_bytes <= want ? 1.0f : (float)((double)want / (double)lo_bytes);
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) cudaGetLastError();
+        }
+    }
     if (prof_begin(ctx, CB_PROF_CONV, st) || launch_tower(tp, ctx->sms, st) || prof_end(ctx, st)) return -1;
     if (!run_heads) return 0;  // the search finishes the heads inside mcts_step (SearchParams::head_raw)
     HeadParams hp{net.head_raw.p, net.head_bn.p, net.fc1.p, net.fc2.p, net.filters, net.slope, value_dev, net.pfeat.p, slot_list, n_dev};
