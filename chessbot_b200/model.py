@@ -65,6 +65,10 @@ class DeviceNetwork:
         """(Re)installs these weights as the engine's network (one network per device context)."""
         self.engine.load_network(self.weights, self.filters, self.blocks, self.max_batch, stream_hi_lo=self.stream_hi_lo)
         self.engine.loaded_network = self
+        for sib in self.__dict__.get("_siblings", {}).values():     # the copies mcts.SearchStream's other lanes evaluate with follow (fit(), new weights)
+            if sib.weights is not self.weights:
+                sib.weights = self.weights
+                sib.load()
 
     def sibling(self, index):
         """The same network resident in extra device context number `index` of this GPU (Engine.actor): lets several batched
