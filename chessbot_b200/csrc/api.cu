@@ -432,8 +432,9 @@ int cb_net_finalize(cb_ctx* ctx) {
         upload(net.wp.p, pfc->data(), pfc->size() * 4) || upload(net.wpt.p, wpt.data(), wpt.size() * 4))
         return -1;
     const size_t act_elems = act_bytes(net.max_batch, N) / 2;
-    for (int i = 0; i < 3; ++i)
+    for (int i = 0; i < 2; ++i)
         if (net.act[i].alloc(act_elems)) return -1;  // zeroed: border cells stay zero forever
+    net.act[2].free_();
     if (net.stream_hi_lo ? net.act_lo.alloc(act_elems) : (net.act_lo.free_(), 0)) return -1;
     const size_t mb = (size_t)(net.max_batch + 3) / 4 * 4;
     if (net.head_raw.alloc(mb * 192) || net.pfeat.alloc(mb * 128)) return -1;
@@ -447,15 +448,20 @@ int cb_net_finalize(cb_ctx* ctx) {
         if (conv_make_row_map(&wm[l], L.w.p, (uint64_t)L.kc * 9 * N, conv_taps_per_box(N) * N / 2)) return -1;
         LayerDesc& d = ld[l];
         d.scale = L.scale.p; d.shift = L.shift.p; d.kc = L.kc; d.kc_in = L.kc_in; d.cj_in = L.cj_in; d.w_map = l; d.pad_ = 0;
+        // Two activation buffers: 1 = the residual stream, 2 = the block's inner activation.  The second convolution of a block writes the new
+        // stream value over the old one IN PLACE: the epilogue thread that reads a cell of the skip tile is the thread that stores that cell of
+        // the output, and nothing else reads the old stream any more (its first convolution is done).  One tensor less in the working set
+        // (3 x 52 MB instead of 4 at 1024 boards of 20x256 incl. the lo half), and the store hits a line the skip load has just brought in.
+        (void)cur;
         if (l == 0) { d.in_buf = 0; d.out_buf = 1; d.skip_buf = -1; }
-        else if (l & 1) { d.in_buf = 1 + cur; d.out_buf = 1 + (cur + 1) % 3; d.skip_buf = -1; }                    // first conv of a block
-        else { d.in_buf = 1 + (cur + 1) % 3; d.out_buf = 1 + (cur + 2) % 3; d.skip_buf = 1 + cur; cur = (cur + 2) % 3; }  // second conv + skip
+        else if (l & 1) { d.in_buf = 1; d.out_buf = 2; d.skip_buf = -1; }   // first conv of a block
+        else { d.in_buf = 2; d.out_buf = 1; d.skip_buf = 1; }               // second conv + skip
     }
     if (net.wmaps.alloc(nl, false) || net.layer_desc.alloc(nl, false) || net.dbg_desc.alloc(1, false) ||
         net.flags.alloc(2 * ((size_t)net.max_batch / 4 + 2)))
         return -1;
     if (upload(net.wmaps.p, wm.data(), nl * sizeof(CUtensorMap)) || upload(net.layer_desc.p, ld.data(), nl * sizeof(LayerDesc))) return -1;
-    for (int i = 0; i < 3; ++i)
+    for (int i = 0; i < 2; ++i)
         if (conv_make_row_map(&net.act_maps[i], net.act[i].p, (uint64_t)act_bytes(net.max_batch, N) / 128, ACT_K64_BYTES / 128)) return -1;
     net.planes_ptr = nullptr;
     net.epoch = 0;
@@ -490,7 +496,7 @@ static int net_tower(cb_ctx* ctx, const void* planes_act_dev, int n, float* valu
     TowerParams tp{};
     tp.tm_act[0] = net.planes_map;
     tp.bufs[0] = (uint8_t*)const_cast<void*>(planes_act_dev);
-    for (int i = 0; i < 3; ++i) { tp.tm_act[1 + i] = net.act_maps[i]; tp.bufs[1 + i] = (uint8_t*)net.act[i].p; }
+    for (int i = 0; i < 2; ++i) { tp.tm_act[1 + i] = net.act_maps[i]; tp.bufs[1 + i] = (uint8_t*)net.act[i].p; }
     tp.maps = net.wmaps.p;
     tp.layers = net.layer_desc.p;
     tp.head_w = net.head_w.p;
@@ -504,7 +510,7 @@ static int net_tower(cb_ctx* ctx, const void* planes_act_dev, int n, float* valu
     }
     tp.lo_from_layer = net.hi_lo_from_block > 0 ? 2 * net.hi_lo_from_block : 0;  // block b's output is layer 2 b + 2; its input stream is layer 2 b
     tp.n_boards_dev = n_dev;
-    tp.full_sectors = (net.stream_hi_lo ? 4 : 3) * act_bytes(n, net.cpad) > ((size_t)96 << 20);  // the rotating activation buffers (+ lo) do not fit the 126 MB L2
+    tp.full_sectors = (net.stream_hi_lo ? 3 : 2) * act_bytes(n, net.cpad) > ((size_t)96 << 20);  // stream + inner activation (+ lo) do not fit the 126 MB L2
     tp.flags = net.flags.p;
     tp.epoch = net.epoch;
     tp.nl = (int)net.layers.size();
