@@ -150,7 +150,7 @@ struct Net {
     DevBuf<__nv_bfloat16> act[3], act_lo;            // act_lo: low half of the residual stream (stream_hi_lo)
     bool stream_hi_lo = true;
     int hi_lo_from_block = 0;                        // residual blocks before this one keep a bf16 stream (0: hi + lo everywhere)
-    size_t l2_persist_bytes = 0;                     // persisting-L2 set-aside last requested for the lo buffer
+    size_t l2_persist_bytes = 0;                     // persisting-L2 set-aside last requested for the residual stream's window
     DevBuf<float> head_raw, pfeat;
     DevBuf<LayerDesc> layer_desc, dbg_desc;          // tower kernel: per-layer descriptors (dbg_desc: cb_debug_conv_layer)
     DevBuf<CUtensorMap> wmaps;                       // tensor maps of the packed weights, one per layer
@@ -442,7 +442,6 @@ int cb_net_finalize(cb_ctx* ctx) {
     const int nl = (int)net.layers.size();
     std::vector<CUtensorMap> wm(nl);
     std::vector<LayerDesc> ld(nl);
-    int cur = 0;
     for (int l = 0; l < nl; ++l) {
         ConvLayer& L = net.layers[l];
         if (conv_make_row_map(&wm[l], L.w.p, (uint64_t)L.kc * 9 * N, conv_taps_per_box(N) * N / 2)) return -1;
@@ -452,7 +451,6 @@ int cb_net_finalize(cb_ctx* ctx) {
         // stream value over the old one IN PLACE: the epilogue thread that reads a cell of the skip tile is the thread that stores that cell of
         // the output, and nothing else reads the old stream any more (its first convolution is done).  One tensor less in the working set
         // (3 x 52 MB instead of 4 at 1024 boards of 20x256 incl. the lo half), and the store hits a line the skip load has just brought in.
-        (void)cur;
         if (l == 0) { d.in_buf = 0; d.out_buf = 1; d.skip_buf = -1; }
         else if (l & 1) { d.in_buf = 1; d.out_buf = 2; d.skip_buf = -1; }   // first conv of a block
         else { d.in_buf = 2; d.out_buf = 1; d.skip_buf = 1; }               // second conv + skip
@@ -517,23 +515,24 @@ static int net_tower(cb_ctx* ctx, const void* planes_act_dev, int n, float* valu
     tp.pairs = pairs;
     tp.n = net.cpad;
     tp.slope = net.slope;
-    if (tp.lo_buf && tp.full_sectors) {
-        // The low half of the residual stream is written and read back two layers later by the same SM; when the activations overflow L2 it
-        // makes that round trip through DRAM (2 x 52 MB per block at 1024 boards of 20x256).  A persisting access-policy window on the
-        // launching stream keeps it in L2 instead (set-aside = the buffer's size, at most 64 MB of the 126 MB): tower -1 to -2 %, 40 MHz more
-        // SM clock at the power cap (measured, profiles/README.md).  CB_TOWER_L2_PERSIST=0 turns it off, =<MB> overrides the set-aside.
+    if (tp.full_sectors) {
+        // When the activations overflow L2 every tensor makes a round trip through DRAM between the layer that writes it and the layers that
+        // read it.  The residual stream is the most re-used one (written by a block's second convolution in place, read by the next block's
+        // first convolution and again as the skip tile): a persisting access-policy window on the launching stream keeps it L2-resident
+        // (set-aside = its size + 4 MB, at most 64 MB of the 126 MB).  Measured at 1024 boards of 20x256 (profiles/README.md): tower -1.5 %,
+        // +1.3 % evals/s at the power cap; the window on the lo half instead: +0.5 %.  CB_TOWER_L2_PERSIST=0 turns it off, =<MB> overrides the size.
         static const int persist_env = getenv("CB_TOWER_L2_PERSIST") ? atoi(getenv("CB_TOWER_L2_PERSIST")) : -1;
-        const size_t lo_bytes = act_bytes(n, net.cpad);
-        const size_t want = persist_env >= 0 ? (size_t)persist_env << 20 : ((lo_bytes + ((size_t)4 << 20)) < ((size_t)64 << 20) ? lo_bytes + ((size_t)4 << 20) : (size_t)64 << 20);
+        const size_t win_bytes = act_bytes(n, net.cpad);
+        const size_t want = persist_env >= 0 ? (size_t)persist_env << 20 : ((win_bytes + ((size_t)4 << 20)) < ((size_t)64 << 20) ? win_bytes + ((size_t)4 << 20) : (size_t)64 << 20);
         if (want > 0) {
             if (net.l2_persist_bytes != want) {
                 if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) cudaGetLastError();  // not fatal: the window then has no effect
                 net.l2_persist_bytes = want;
             }
             cudaStreamAttrValue av{};
-            av.accessPolicyWindow.base_ptr = net.act_lo.p;
-            av.accessPolicyWindow.num_bytes = lo_bytes;
-            av.accessPolicyWindow.hitRatio = lo_bytes <= want ? 1.0f : (float)((double)want / (double)lo_bytes);
+            av.accessPolicyWindow.base_ptr = net.act[0].p;
+            av.accessPolicyWindow.num_bytes = win_bytes;
+            av.accessPolicyWindow.hitRatio = win_bytes <= want ? 1.0f : (float)((double)want / (double)win_bytes);
             av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
             av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
             if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) cudaGetLastError();
