@@ -289,7 +289,10 @@ def run_reference_arm(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"batched MCTS leaf evaluation + tree update, {blocks}x{filters} net (reference CPU path, batch 1 per process)",
-                   "net": args.net, "processes": P},
+                   "net": args.net, "processes": P,
+                   "comparison": "a CPU PORT of the reference path (python-chess / TensorFlow replaced by the oracle shims, torch-fp32 network), bounded sample: "
+                                 f"{sims}-sim searches in fp32 against the GPU arm's 100-sim searches in bf16 - evaluations per second are what is compared, "
+                                 "not identical searches; the reference itself evaluates with TF-TRT on a GPU (108 sims/s on an RTX 2070 SUPER, main.ipynb)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": P, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
