@@ -232,11 +232,10 @@ static int prof_end(cb_ctx* ctx, cudaStream_t st) {
 }
 
 // every entry point runs on its context's device, whatever the caller's current device is (several contexts per process)
-#define CB_ENTER(ctx)                                                                                                 \
-    do {                                                                                                              \
-        if (!(ctx)) { cb_set_error("null context"); return -1; }                                                      \
-        if (cudaSetDevice((ctx)->device) != cudaSuccess) { cb_set_error("cudaSetDevice(context device) failed"); return -1; } \
-    } while (0)
+#define CB_ENTER(ctx)                                                                                                  \
+    if (!(ctx)) { cb_set_error("null context"); return -1; }                                                           \
+    cb_device_guard cb_guard_((ctx)->device);                                                                          \
+    if (!cb_guard_.ok) { cb_set_error("cudaSetDevice(context device) failed"); return -1; }
 
 static int upload(void* dst, const void* src, size_t bytes) {
     CB_CUDA_OK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
@@ -271,7 +270,8 @@ cb_ctx* cb_ctx_create(int device) {
         cb_set_error("no CUDA device: chessbot_b200 has no CPU fallback");
         return nullptr;
     }
-    if (cudaSetDevice(device) != cudaSuccess) { cb_set_error("cudaSetDevice failed"); return nullptr; }
+    cb_device_guard guard(device);
+    if (!guard.ok) { cb_set_error("cudaSetDevice failed"); return nullptr; }
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
     if (prop.major != 10) {
@@ -292,7 +292,8 @@ cb_ctx* cb_ctx_create(int device) {
     return ctx;
 }
 void cb_ctx_destroy(cb_ctx* ctx) {
-    if (ctx) cudaSetDevice(ctx->device);
+    if (!ctx) return;
+    cb_device_guard guard(ctx->device);
     delete ctx;
 }
 int cb_ctx_sm_count(const cb_ctx* ctx) { return ctx->sms; }

@@ -37,6 +37,21 @@ inline int cb_opt_in_dynamic_smem(const void* kernel, int bytes, std::atomic<uin
     return 0;
 }
 
+// Every entry point runs on its context's device and leaves the caller's current device as it found it.
+struct cb_device_guard {
+    int prev = -1, dev = -1;
+    bool ok = true;
+    explicit cb_device_guard(int device) : dev(device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~cb_device_guard() {
+        if (ok && prev >= 0 && prev != dev) cudaSetDevice(prev);
+    }
+    cb_device_guard(const cb_device_guard&) = delete;
+    cb_device_guard& operator=(const cb_device_guard&) = delete;
+};
+
 namespace cb {
 
 // ------------------------------------------------------------------ tile-native activation layout

@@ -167,7 +167,8 @@ size_t cb_train_param_count(int filters, int blocks, size_t* n_regularized) {
 cb_trainer* cb_train_create(cb_ctx* ctx, int filters, int blocks, int batch, float leaky_slope, float bn_eps, float bn_momentum, float* params_dev,
                             float* grads_dev, float* momentum_dev) {
     if (!ctx) { cb_set_error("cb_train_create: no context"); return nullptr; }
-    if (cudaSetDevice(cb_ctx_device(ctx)) != cudaSuccess) { cb_set_error("cudaSetDevice(context device) failed"); return nullptr; }
+    cb_device_guard cb_guard_(cb_ctx_device(ctx));
+    if (!cb_guard_.ok) { cb_set_error("cudaSetDevice(context device) failed"); return nullptr; }
     const int N = (filters + 63) / 64 * 64;
     if (filters < 4 || (filters & 3) || (N != 64 && N != 128 && N != 256) || blocks < 0 || batch < 1) {
         cb_set_error("cb_train_create: filters must be a multiple of 4 that pads to 64, 128 or 256 channels (4..64, 68..128, 196..256), batch >= 1");
@@ -257,7 +258,8 @@ cb_trainer* cb_train_create(cb_ctx* ctx, int filters, int blocks, int batch, flo
 }
 
 void cb_train_destroy(cb_trainer* t) {
-    if (t) cudaSetDevice(t->device);
+    if (!t) return;
+    cb_device_guard cb_guard_(t->device);
     if (!t) return;
     for (cudaEvent_t e : t->ev) cudaEventDestroy(e);
     if (t->graph_fb) cudaGraphExecDestroy(t->graph_fb);
@@ -307,7 +309,8 @@ static int find_tensor(cb_trainer* t, const std::string& name, Span* par, Span* 
 
 // what = 0: parameter (BN: gamma, beta, moving mean, moving variance), 2: momentum of the optimizer (BN: rows 2, 3 ignored)
 int cb_train_set_tensor(cb_trainer* t, const char* name, int what, const float* host, size_t count, void* stream) {
-    CB_CUDA_OK(cudaSetDevice(t->device));
+    cb_device_guard cb_guard_(t->device);
+    if (!cb_guard_.ok) { cb_set_error("cudaSetDevice(trainer device) failed"); return -1; }
     cudaStream_t st = (cudaStream_t)stream;
     Span par, mov;
     int bn_c;
@@ -323,7 +326,8 @@ int cb_train_set_tensor(cb_trainer* t, const char* name, int what, const float* 
 
 // what = 0: parameter (BN: gamma, beta, moving mean, moving variance), 1: gradient (BN: dgamma, dbeta, 0, 0), 2: momentum
 int cb_train_get_tensor(cb_trainer* t, const char* name, int what, float* host, size_t count, void* stream) {
-    CB_CUDA_OK(cudaSetDevice(t->device));
+    cb_device_guard cb_guard_(t->device);
+    if (!cb_guard_.ok) { cb_set_error("cudaSetDevice(trainer device) failed"); return -1; }
     cudaStream_t st = (cudaStream_t)stream;
     Span par, mov;
     int bn_c;
@@ -367,7 +371,8 @@ static int run_graphed(cb_trainer* t, int (*enqueue)(cb_trainer*, cudaStream_t),
 }
 
 int cb_train_forward_backward(cb_trainer* t, const int16_t* images_dev, const float* z_dev, const float* pi_dev, int n, void* stream) {
-    CB_CUDA_OK(cudaSetDevice(t->device));
+    cb_device_guard cb_guard_(t->device);
+    if (!cb_guard_.ok) { cb_set_error("cudaSetDevice(trainer device) failed"); return -1; }
     cudaStream_t st = (cudaStream_t)stream;
     if (n != t->batch) { cb_set_error("cb_train_forward_backward: n must equal the trainer's batch"); return -1; }
     if (t->weights_dirty && (tp_begin(t, TP_OPT, st) || pack_weights(t, st) || tp_end(t, st))) return -1;
@@ -481,7 +486,8 @@ static int enqueue_forward_backward(cb_trainer* t, cudaStream_t st) {
 }
 
 int cb_train_apply(cb_trainer* t, float lr, float momentum, int nesterov, float l2, float grad_scale, void* stream) {
-    CB_CUDA_OK(cudaSetDevice(t->device));
+    cb_device_guard cb_guard_(t->device);
+    if (!cb_guard_.ok) { cb_set_error("cudaSetDevice(trainer device) failed"); return -1; }
     cudaStream_t st = (cudaStream_t)stream;
     t->last_l2 = l2;
     const float hp[5] = {lr, momentum, l2, grad_scale, nesterov ? 1.f : 0.f};
@@ -500,7 +506,8 @@ static int enqueue_apply(cb_trainer* t, cudaStream_t st) {
 // out[0] = mean squared error of the value head, out[1] = mean policy cross-entropy, out[2] = l2 * sum of squared kernels
 // (as of the last cb_train_apply): the three terms Keras sums into `loss`
 int cb_train_losses_sync(cb_trainer* t, double* out3, void* stream) {
-    CB_CUDA_OK(cudaSetDevice(t->device));
+    cb_device_guard cb_guard_(t->device);
+    if (!cb_guard_.ok) { cb_set_error("cudaSetDevice(trainer device) failed"); return -1; }
     cudaStream_t st = (cudaStream_t)stream;
     double h[3];
     CB_CUDA_OK(cudaMemcpyAsync(h, t->losses.p, 24, cudaMemcpyDeviceToHost, st));
@@ -513,7 +520,8 @@ int cb_train_losses_sync(cb_trainer* t, double* out3, void* stream) {
 
 // value [n] and policy logits gradient buffer are internal; the forward outputs of the last step for inspection / tests
 int cb_train_outputs_sync(cb_trainer* t, float* value_host, void* stream) {
-    CB_CUDA_OK(cudaSetDevice(t->device));
+    cb_device_guard cb_guard_(t->device);
+    if (!cb_guard_.ok) { cb_set_error("cudaSetDevice(trainer device) failed"); return -1; }
     cudaStream_t st = (cudaStream_t)stream;
     CB_CUDA_OK(cudaMemcpyAsync(value_host, t->value.p, (size_t)t->batch * 4, cudaMemcpyDeviceToHost, st));
     CB_CUDA_OK(cudaStreamSynchronize(st));
@@ -526,7 +534,8 @@ int cb_train_profile(cb_trainer* t, int enable) {
     return 0;
 }
 int cb_train_profile_read_sync(cb_trainer* t, double* total_ms, int* launches) {
-    CB_CUDA_OK(cudaSetDevice(t->device));
+    cb_device_guard cb_guard_(t->device);
+    if (!cb_guard_.ok) { cb_set_error("cudaSetDevice(trainer device) failed"); return -1; }
     CB_CUDA_OK(cudaDeviceSynchronize());
     for (int k = 0; k < TP_STAGES; ++k) { total_ms[k] = 0; launches[k] = 0; }
     for (size_t i = 0; i + 1 < t->ev_used; i += 2) {

@@ -49,8 +49,9 @@ def _install_allocator():
         atexit.register(lambda: lib.cb_set_device_allocator(None, None, None))   # no callbacks into a finalising interpreter
 
 
-def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(device=None):
+    """torch's current stream of `device` (default: the current device) as the `void* stream` of the C ABI"""
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 def _ptr(t):
@@ -140,7 +141,7 @@ class Engine:
         n = frame_idx.shape[0]
         act = torch.zeros(lib.cb_planes_act_bytes(n) // 2, dtype=torch.bfloat16, device=self.device) if want_act else None
         i16 = torch.empty(n, 8, 8, 119, dtype=torch.int16, device=self.device) if want_i16 else None
-        check(lib.cb_encode(self._h, _ptr(pos), _ptr(frame_idx), n, _ptr(act), _ptr(i16), _stream()), "encode")
+        check(lib.cb_encode(self._h, _ptr(pos), _ptr(frame_idx), n, _ptr(act), _ptr(i16), _stream(self.device_index)), "encode")
         return act, i16
 
     # ------------------------------------------------------------------ model
@@ -160,14 +161,14 @@ class Engine:
         value = torch.empty(n, dtype=torch.float32, device=self.device)
         lb = torch.empty(n, CB_NUM_ACTIONS, dtype=torch.bfloat16, device=self.device) if want_bf16 else None
         lf = torch.empty(n, CB_NUM_ACTIONS, dtype=torch.float32, device=self.device) if want_f32 else None
-        check(lib.cb_net_forward(self._h, _ptr(planes_act), n, _ptr(value), _ptr(lb), _ptr(lf), _stream()), "net_forward")
+        check(lib.cb_net_forward(self._h, _ptr(planes_act), n, _ptr(value), _ptr(lb), _ptr(lf), _stream(self.device_index)), "net_forward")
         return value, lb, lf
 
     def synth_forward(self, planes_i16, seed=0):
         n = planes_i16.shape[0]
         value = torch.empty(n, dtype=torch.float32, device=self.device)
         lb = torch.empty(n, CB_NUM_ACTIONS, dtype=torch.bfloat16, device=self.device)
-        check(lib.cb_synth_forward(self._h, _ptr(planes_i16), n, seed, _ptr(value), _ptr(lb), _stream()), "synth_forward")
+        check(lib.cb_synth_forward(self._h, _ptr(planes_i16), n, seed, _ptr(value), _ptr(lb), _stream(self.device_index)), "synth_forward")
         return value, lb
 
     def policy_softmax(self, pos, cur_idx, logits_bf16):
@@ -177,7 +178,7 @@ class Engine:
         priors = torch.zeros(n, CB_MAX_MOVES, dtype=torch.float32, device=self.device)
         counts = torch.zeros(n, dtype=torch.int32, device=self.device)
         check(lib.cb_policy_softmax(self._h, _ptr(pos), _ptr(cur_idx), n, _ptr(logits_bf16), _ptr(moves), _ptr(actions),
-                                    _ptr(priors), _ptr(counts), _stream()), "policy_softmax")
+                                    _ptr(priors), _ptr(counts), _stream(self.device_index)), "policy_softmax")
         return moves, actions, priors, counts
 
     def evaluate_positions(self, records, pos=None, frame_idx=None, dense_logits=False):
@@ -205,7 +206,7 @@ class Engine:
         counts = torch.zeros(n, dtype=torch.int32, device=self.device)
         cur = frame_idx[:, 0].contiguous()
         check(lib.cb_leaf_eval(self._h, _ptr(pos), _ptr(frame_idx), _ptr(cur), n, _ptr(self._leaf_scratch), _ptr(value), _ptr(moves), _ptr(actions),
-                               _ptr(priors), _ptr(counts), _stream()), "leaf_eval")
+                               _ptr(priors), _ptr(counts), _stream(self.device_index)), "leaf_eval")
         return value, moves, actions, priors, counts
 
     def evaluate_records(self, records):
@@ -222,7 +223,7 @@ class Engine:
         buf = getattr(self, "_leaf_out", None)                  # reused between calls (the views returned are valid until the next call)
         if buf is None or buf.nbytes < lib.cb_leaf_eval_packed_bytes(n, n * CB_MAX_MOVES):
             buf = self._leaf_out = np.zeros(lib.cb_leaf_eval_packed_bytes(n, n * CB_MAX_MOVES), dtype=np.uint8)
-        T = check(lib.cb_leaf_eval_host_sync(self._h, flat.ctypes.data, lens.ctypes.data, n, buf.ctypes.data, buf.nbytes, _stream()), "leaf_eval_host")
+        T = check(lib.cb_leaf_eval_host_sync(self._h, flat.ctypes.data, lens.ctypes.data, n, buf.ctypes.data, buf.nbytes, _stream(self.device_index)), "leaf_eval_host")
         o, out = 0, {}
         for key, dt, cnt in (("value", np.float32, n), ("n_moves", np.int32, n), ("off", np.int32, n + 1), ("priors", np.float32, T),
                              ("moves", np.uint16, T), ("actions", np.int16, T)):
@@ -247,12 +248,12 @@ class Engine:
     def debug_conv_layer(self, layer, in_act, skip_act, n_boards, out_channels, use_reference=False):
         out = torch.zeros(((n_boards + 1) // 2) * (out_channels // 8) * 1600, dtype=torch.bfloat16, device=self.device)
         check(lib.cb_debug_conv_layer(self._h, layer, _ptr(in_act), _ptr(skip_act), _ptr(out), n_boards, int(use_reference),
-                                      _stream()), "debug_conv_layer")
+                                      _stream(self.device_index)), "debug_conv_layer")
         return out
 
     def debug_wgrad(self, in_act, dy_act, n_boards, cin_pad, n, use_reference=False):
         out = torch.zeros(9, cin_pad, n, dtype=torch.float32, device=self.device)
-        check(lib.cb_debug_wgrad(self._h, _ptr(in_act), _ptr(dy_act), n_boards, cin_pad, n, _ptr(out), int(use_reference), _stream()),
+        check(lib.cb_debug_wgrad(self._h, _ptr(in_act), _ptr(dy_act), n_boards, cin_pad, n, _ptr(out), int(use_reference), _stream(self.device_index)),
               "debug_wgrad")
         return out
 
@@ -305,27 +306,27 @@ class Engine:
         check(lib.cb_search_begin_csr(self._h, n, flat.ctypes.data, lens.ctypes.data, sims_a.ctypes.data, cp.ctypes.data,
                                       nz_flat.ctypes.data if nz_flat is not None and len(nz_flat) else None,
                                       nz_off.ctypes.data if nz_off is not None else None,
-                                      max_game_length, eval_mode, seed, _stream()), "search_begin")
+                                      max_game_length, eval_mode, seed, _stream(self.device_index)), "search_begin")
 
     def search_run(self, steps):
-        check(lib.cb_search_run(self._h, steps, _stream()), "search_run")
+        check(lib.cb_search_run(self._h, steps, _stream(self.device_index)), "search_run")
 
     def search_status(self):
         c = np.zeros(4, dtype=np.int64)
-        check(lib.cb_search_status_sync(self._h, c.ctypes.data, _stream()), "search_status")
+        check(lib.cb_search_status_sync(self._h, c.ctypes.data, _stream(self.device_index)), "search_status")
         return {"unfinished": int(c[0]), "evals": int(c[1]), "sims": int(c[2]), "errors": int(c[3])}
 
     def search_pending_planes(self):
         n = self._n_trees
         planes = np.empty((n, 8, 8, 119), dtype=np.int16)
         waiting = np.zeros(n, dtype=np.uint8)
-        check(lib.cb_search_pending_planes_sync(self._h, planes.ctypes.data, waiting.ctypes.data, _stream()), "pending_planes")
+        check(lib.cb_search_pending_planes_sync(self._h, planes.ctypes.data, waiting.ctypes.data, _stream(self.device_index)), "pending_planes")
         return planes, waiting.astype(bool)
 
     def search_step_external(self, values, expvals):
         v = np.ascontiguousarray(values, dtype=np.float32)
         e = np.ascontiguousarray(expvals, dtype=np.float32)
-        check(lib.cb_search_step_external(self._h, v.ctypes.data, e.ctypes.data, _stream()), "step_external")
+        check(lib.cb_search_step_external(self._h, v.ctypes.data, e.ctypes.data, _stream(self.device_index)), "step_external")
 
     def search_read_roots(self):
         n = self._n_trees
@@ -338,7 +339,7 @@ class Engine:
         root_n = np.zeros(n, dtype=np.int32)
         nodes = np.zeros(n, dtype=np.int32)
         check(lib.cb_search_read_roots_sync(self._h, moves.ctypes.data, N.ctypes.data, W.ctypes.data, Q.ctypes.data,
-                                            P.ctypes.data, nc.ctypes.data, root_n.ctypes.data, nodes.ctypes.data, _stream()),
+                                            P.ctypes.data, nc.ctypes.data, root_n.ctypes.data, nodes.ctypes.data, _stream(self.device_index)),
               "read_roots")
         return {"moves": moves, "N": N, "W": W, "Q": Q, "P": P, "n_children": nc, "root_N": root_n, "nodes": nodes}
 
@@ -348,7 +349,7 @@ class Engine:
         n = self._n_trees
         off = np.zeros(n + 1, dtype=np.int32)
         np.cumsum(n_legal, out=off[1:])
-        check(lib.cb_search_read_roots_compact_async(self._h, off.ctypes.data, _stream()), "read_roots_compact_async")
+        check(lib.cb_search_read_roots_compact_async(self._h, off.ctypes.data, _stream(self.device_index)), "read_roots_compact_async")
         return n, off
 
     def search_read_roots_compact_wait(self, ticket):

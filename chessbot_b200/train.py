@@ -137,13 +137,13 @@ class Trainer:
             a = np.ascontiguousarray(weights[name], dtype=np.float32)
             if a.size != int(np.prod(shape)):
                 raise ValueError(f"{name}: expected shape {shape}, got {a.shape}")
-            check(lib.cb_train_set_tensor(self._h, name.encode(), what, a.ctypes.data, a.size, _stream()), "train_set_tensor")
+            check(lib.cb_train_set_tensor(self._h, name.encode(), what, a.ctypes.data, a.size, _stream(self.device.index)), "train_set_tensor")
 
     def _get(self, what):
         out = {}
         for name, shape in self.shapes.items():
             a = np.empty(shape, dtype=np.float32)
-            check(lib.cb_train_get_tensor(self._h, name.encode(), what, a.ctypes.data, a.size, _stream()), "train_get_tensor")
+            check(lib.cb_train_get_tensor(self._h, name.encode(), what, a.ctypes.data, a.size, _stream(self.device.index)), "train_get_tensor")
             out[name] = a
         return out
 
@@ -198,7 +198,7 @@ class Trainer:
         n = img.shape[0]
         if tuple(img.shape) != (n, 8, 8, 119) or tuple(pt.shape) != (n, CB_NUM_ACTIONS) or zt.numel() != n:
             raise ValueError("expected images [B,8,8,119], terminal values [B], search statistics [B,4672]")
-        check(lib.cb_train_forward_backward(self._h, _ptr(img), _ptr(zt), _ptr(pt), n, _stream()), "train_forward_backward")
+        check(lib.cb_train_forward_backward(self._h, _ptr(img), _ptr(zt), _ptr(pt), n, _stream(self.device.index)), "train_forward_backward")
         self._keep = (img, zt, pt)     # the kernels read them asynchronously
         self._last_n = n
 
@@ -208,13 +208,13 @@ class Trainer:
         # NCCL over NVLink: the only collective of the training step.  Every rank's trainer has a fixed batch, so shards are equal
         # unless the ranks were built with different batch sizes (weighted_shards=True then weights them by their sample counts)
         scale = allreduce_gradients(self.grads, getattr(self, "_last_n", None) if getattr(self, "weighted_shards", False) else None)
-        check(lib.cb_train_apply(self._h, float(lr), float(momentum), int(nesterov), float(l2), scale, _stream()), "train_apply")
+        check(lib.cb_train_apply(self._h, float(lr), float(momentum), int(nesterov), float(l2), scale, _stream(self.device.index)), "train_apply")
         self.steps += 1
 
     def losses(self):
         """{"value": mse, "policy": cross-entropy, "l2": regularization term, "loss": their sum} of the last step (this GPU's batch)."""
         out = (C.c_double * 3)()
-        check(lib.cb_train_losses_sync(self._h, out, _stream()), "train_losses")
+        check(lib.cb_train_losses_sync(self._h, out, _stream(self.device.index)), "train_losses")
         return {"value": out[0], "policy": out[1], "l2": out[2], "loss": out[0] + out[1] + out[2]}
 
     def train_on_batch(self, images, z, pi, lr):
@@ -239,7 +239,7 @@ class Trainer:
 
     def values(self):
         out = np.empty(self.batch_size, dtype=np.float32)
-        check(lib.cb_train_outputs_sync(self._h, out.ctypes.data, _stream()), "train_outputs")
+        check(lib.cb_train_outputs_sync(self._h, out.ctypes.data, _stream(self.device.index)), "train_outputs")
         return out
 
     # ------------------------------------------------------------------ measurement
