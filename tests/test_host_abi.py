@@ -212,3 +212,14 @@ def test_search_workspace_size_is_reported_before_allocation(cb):
     assert 0 < small < big
     assert big > 1024 * 802 * 48 * 32                      # at least the node pool (32-byte nodes)
     assert f(1024, 1024 * 802 * 48, 1024 * 1000, 800, 8) > big
+
+
+def test_packed_buffer_sizes_match_their_documented_layouts(cb):
+    """host-side size helpers of the packed read-backs (include/chessbot_b200.h): the layouts the Python host slices by"""
+    _lib, _ = cb
+    n, T = 1024, 31337
+    # P f64 | N i32 | W f32 | Q f32 per child, four i32 header rows per tree, moves u16 per child
+    assert _lib.lib.cb_search_roots_compact_bytes(n, T) == T * (8 + 4 + 4 + 4) + n * 16 + T * 2
+    # value f32 | n_moves i32 | offsets i32 [n + 1], then priors f32 | moves u16 | actions i16 per legal move
+    assert _lib.lib.cb_leaf_eval_packed_bytes(n, T) == n * 12 + 4 + T * 8
+    assert _lib.lib.cb_search_roots_compact_bytes(0, 0) == 0
